@@ -1,0 +1,184 @@
+"""Pin the CPU oracle (oracle/) against outputs of the real reference (tests/golden)."""
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from helpers import golden, t, negative_table, rel_fro
+
+
+@pytest.mark.parametrize("name", ["knn_n300_d16_k15", "knn_n2000_d50_k90", "knn_n1500_d128_k15"])
+def test_knn_dense_bit_exact(name):
+    g = golden(name)
+    X, k = t(g["X"]), int(g["k"])
+    C, I = oracle.knn_dense(X, k, "sqeuclidean", True)
+    assert torch.equal(I, t(g["I"]))
+    assert torch.equal(C, t(g["C"]))
+    Ce, Ie = oracle.knn_dense(X, k, "euclidean", True)
+    assert torch.equal(Ie, t(g["Ie"])) and torch.equal(Ce, t(g["Ce"]))
+
+
+def test_knn_chunked_same_accuracy_class():
+    g = golden("knn_n2000_d50_k90")
+    X, k = t(g["X"]), int(g["k"])
+    C, I = oracle.knn_chunked(X, k, block=512)
+    idx64, d64, ok, set_ok = oracle.knn_ambiguity(X, k)
+    assert ok.float().mean() > 0.5 and set_ok.float().mean() > 0.5
+    assert torch.equal(I[ok].long(), idx64[ok])
+    assert torch.equal(t(g["I"])[ok].long(), idx64[ok])
+    same_set = (I.long().sort(1)[0] == idx64.sort(1)[0]).all(1)
+    assert bool(same_set[set_ok].all())
+    torch.testing.assert_close(C, t(g["C"]), rtol=1e-4, atol=1e-4)
+
+
+def test_pairwise_full_and_k_ge_n():
+    g = golden("pairwise_full_n64")
+    X, Y = t(g["X"]), t(g["Y"])
+    assert torch.equal(oracle.pairwise_full(X, None, "sqeuclidean", True), t(g["C_excl"]))
+    C, I = oracle.knn_dense(X, 70, "sqeuclidean", False)
+    assert I is None and torch.equal(C, t(g["C_kge_n"]))
+    Cxy = oracle.pairwise_full(X, Y)
+    v, i = Cxy.topk(5, dim=1, largest=False)
+    assert torch.equal(v, t(g["Cxy"])) and torch.equal(i.int(), t(g["Ixy"]))
+
+
+def test_unsupported_metric():
+    with pytest.raises(ValueError, match="distance is not supported"):
+        oracle.pairwise_full(torch.zeros(3, 2), None, "chebyshev")
+
+
+def test_umap_affinity_rows():
+    g = golden("umap_n300_d16_k15")
+    X = t(g["X"])
+    C, I = oracle.knn_dense(X, 15)
+    assert torch.equal(I, t(g["I"]))
+    P, rho, sig = oracle.umap_affinity_rows(C, 15, max_iter=100)
+    assert torch.equal(rho, t(g["rho"]))
+    assert torch.equal(sig, t(g["sigma"]))
+    assert torch.equal(P, t(g["P"]))
+
+
+def test_symmetrize_and_schedule():
+    g = golden("umap_n300_d16_k15")
+    V, J = oracle.symmetrize_ell(t(g["P"]), t(g["I"]))
+    assert torch.equal(J.int(), t(g["sym_idx"]))
+    assert torch.equal(V, t(g["sym_vals"]))
+    per, nxt = oracle.umap_edge_schedule(V, int(g["max_iter"]))
+    assert torch.equal(per, t(g["eps_per_sample"]))
+    rp, col, val = oracle.ell_to_csr(V, J)
+    V2, J2 = oracle.csr_to_ell(rp, col, val)
+    assert torch.equal(V2, V) and torch.equal(J2, J)
+
+
+def test_find_ab():
+    g = golden("umap_n300_d16_k15")
+    a, b = oracle.find_ab(1.0, 0.1)
+    assert a == float(g["a"]) and b == float(g["b"])
+
+
+def test_negative_table_matches_reference_draw():
+    g = golden("umap_n300_d16_k15")
+    neg = negative_table(int(g["seed"]), 0, 300, 75)
+    assert torch.equal(neg.int(), t(g["neg0"]))
+    assert not (neg == torch.arange(300)[:, None]).any()
+
+
+def test_umap_lr_schedule():
+    g = golden("umap_n300_d16_k15")
+    lrs = oracle.linear_lr_sequence(1.0, 100, 100)
+    np.testing.assert_array_equal(lrs, g["lr"].astype(np.float32))
+
+
+def test_umap_run_trajectory():
+    g = golden("umap_n300_d16_k15")
+    T, seed = int(g["max_iter"]), int(g["seed"])
+    V, J = t(g["sym_vals"]), t(g["sym_idx"]).long()
+    per, nxt = oracle.umap_edge_schedule(V, T)
+    negs = [negative_table(seed, s, 300, 75) for s in range(T)]
+    lrs = oracle.linear_lr_sequence(1.0, T, T)
+    Z, _, traj = oracle.umap_run(t(g["Z0"]), J, per, nxt, negs, lrs, float(g["a"]), float(g["b"]),
+                                 return_all=True)
+    for s in (1, 2, 5, 20, 50, 100):
+        assert torch.equal(traj[s - 1], t(g[f"Z_{s}"])), f"step {s}: {rel_fro(traj[s-1], g[f'Z_{s}'])}"
+
+
+def test_umap_run_partitioned_equals_single():
+    # distributed semantics (affinity_matcher.py:395-413): chunk gradients from the old Z
+    # (the loop is chaotic: a 1-ulp einsum-order difference at step 3 grows to 7e-4 by step 10
+    #  and O(1) by step 20 — measured — so multi-step comparisons stop at T=5)
+    g = golden("umap_n300_d16_k15")
+    T, seed = 5, int(g["seed"])
+    V, J = t(g["sym_vals"]), t(g["sym_idx"]).long()
+    per, nxt = oracle.umap_edge_schedule(V, int(g["max_iter"]))
+    negs = [negative_table(seed, s, 300, 75) for s in range(T)]
+    lrs = oracle.linear_lr_sequence(1.0, 100, T)
+    Z1, _ = oracle.umap_run(t(g["Z0"]), J, per, nxt, negs, lrs, float(g["a"]), float(g["b"]))
+    bounds = [oracle.chunk_bounds(300, r, 3) for r in range(3)]
+    negs_p = [[nt[s:e] for (s, e) in bounds] for nt in negs]
+    Z3, _ = oracle.umap_run(t(g["Z0"]), J, per, nxt, negs_p, lrs, float(g["a"]), float(g["b"]),
+                            bounds=bounds)
+    assert rel_fro(Z3, Z1) < 1e-5
+
+
+def test_entropic_rows():
+    g = golden("entropic_n300_d16_p10")
+    C = t(g["C"])
+    b0, b1 = oracle.entropic_bounds(C, int(g["perplexity"]))
+    assert torch.equal(b0, t(g["begin"])) and torch.equal(b1, t(g["end"]))
+    logP, eps, ln = oracle.entropic_affinity_rows(C, int(g["perplexity"]))
+    assert torch.equal(eps, t(g["eps"]))
+    assert torch.equal(ln, t(g["log_norm"]))
+    assert torch.equal(logP, t(g["logP"]))
+    logP2, eps2, _ = oracle.entropic_affinity_rows(C, int(g["perplexity"]), use_bounds=False)
+    assert torch.equal(eps2, t(g["eps_nobounds"]))
+    assert torch.equal(logP2, t(g["logP_nobounds"]))
+    # the reference's own property test (tests/test_affinity.py:204-210)
+    ln_ = logP + np.log(300.0)
+    torch.testing.assert_close(ln_.exp().sum(1), torch.ones(300), atol=1e-3, rtol=0)
+    H = -(ln_.exp() * (ln_ - 1)).sum(1)
+    torch.testing.assert_close(H, torch.full((300,), np.log(10.0) + 1, dtype=torch.float32), atol=1e-3, rtol=0)
+
+
+def test_entropic_p30_k90():
+    g = golden("entropic_n2000_d50_p30")
+    X = t(golden("knn_n2000_d50_k90")["X"])
+    C, I = oracle.knn_dense(X, 90)
+    logP, eps, ln = oracle.entropic_affinity_rows(C, 30)
+    assert torch.equal(eps, t(g["eps"]))
+    assert torch.equal(logP[:64], t(g["logP_head"]))
+    assert oracle.clamp_neighbor_param(30, 2000) == 30
+    assert oracle.clamp_neighbor_param(5000, 2000) == 1998
+    assert oracle.clamp_neighbor_param(1, 2000) == 2
+
+
+def test_largevis_run():
+    g = golden("largevis_n300_d16_p10")
+    seed = int(g["seed"])
+    negs = [negative_table(seed, s, 300, 5) for s in range(30)]
+    assert torch.equal(negs[0].int(), t(g["neg0"]))
+    Z, lrs, grads = oracle.largevis_run(t(g["Z0"]), t(g["P"]), t(g["I"]), negs, 30, return_grads=True)
+    np.testing.assert_allclose(np.asarray(lrs), g["lr"], rtol=1e-12)
+    assert torch.equal(grads[0], t(g["G_1"]))
+    assert torch.equal(Z, t(g["Z_30"]))
+
+
+def test_tsne_run():
+    g = golden("tsne_n300_d16_p10")
+    Z, grads = oracle.tsne_run(t(g["Z0"]), t(g["P"]), t(g["I"]), 20, exag_iter=int(g["exag_iter"]),
+                               return_grads=True)
+    assert torch.equal(grads[0], t(g["G_1"]))
+    assert torch.equal(grads[11], t(g["G_12"]))
+    assert torch.equal(Z, t(g["Z_20"]))
+
+
+def test_partition():
+    for n, w in [(100, 4), (10, 3), (7, 8), (50_000_000, 8)]:
+        prev = 0
+        for r in range(w):
+            s, e = oracle.chunk_bounds(n, r, w)
+            assert s == prev and e >= s
+            prev = e
+            if e > s:
+                assert oracle.owner_of(s, n, w) == r and oracle.owner_of(e - 1, n, w) == r
+        assert prev == n
