@@ -12,14 +12,15 @@ import torch
 
 
 def largevis_loss(Z, P, idx, neg, rows, n_total, lam=1.0, repulsion=1.0):
-    Zq = Z[rows]
+    # each loss gathers its own query rows (distance/base.py:336-339 is called twice);
+    # sharing one gather would change the autograd accumulation order
     # largevis.py:192-201 ; distance/base.py:384-385
-    D = torch.sum((Zq.unsqueeze(1) - Z[idx.long()]) ** 2, dim=-1)
+    D = torch.sum((Z[rows].unsqueeze(1) - Z[idx.long()]) ** 2, dim=-1)
     Q = 1.0 / (1.0 + D)
     Q = Q / (Q + 1)
     att = -(P * Q.log()).sum()  # utils/utils.py:121-124
     # largevis.py:181-190
-    Dn = torch.sum((Zq.unsqueeze(1) - Z[neg.long()]) ** 2, dim=-1)
+    Dn = torch.sum((Z[rows].unsqueeze(1) - Z[neg.long()]) ** 2, dim=-1)
     Qn = 1.0 / (1.0 + Dn)
     Qn = Qn / (Qn + 1)
     rep = -((1 - Qn).log()).sum() / n_total

@@ -5,7 +5,7 @@ directed kNN edges; repulsive = logsumexp over ALL N x N pairs, diagonal
 included, of -log(1 + C) with C in the expanded form of
 ``distance/torch.py:89-91``), ``neighbor_embedding/base.py:282-343``
 (early-exaggeration switch that rebuilds the optimiser; lr "auto"; momentum
-0.5 while lambda > 1 else 0.8) and ``affinity_matcher.py:414-429``.
+0.5 while lambda > 1 else 0.8 — but see the param-group note in tsne_run) and ``affinity_matcher.py:414-429``.
 """
 
 import torch
@@ -26,10 +26,17 @@ def tsne_run(Z0, P, idx, n_steps, exag=12.0, exag_iter=250, lr=None, return_grad
     Z = torch.nn.Parameter(Z0.clone())
     rows = torch.arange(n)
 
+    # affinity_matcher.py:588-590: params_ is ONE dict reused for every optimiser build.
+    # torch's add_param_group fills it with setdefault(), so when the optimiser is rebuilt at
+    # the end of early exaggeration the dict still carries the FIRST build's lr and momentum:
+    # only the momentum buffer is reset (verified on the reference: lr stays 50, momentum 0.5
+    # after the switch although lr_ becomes 75).  Restated as is.
+    group = {"params": Z}
+
     def make_opt(lam):
         lr_ = max(n / lam / 4, 50) if lr is None else lr  # NE base.py:299-310
         mom = 0.5 if lam > 1 else 0.8  # NE base.py:331-338
-        return torch.optim.SGD([Z], lr=lr_, momentum=mom)
+        return torch.optim.SGD([group], lr=lr_, momentum=mom)
 
     lam = exag
     opt = make_opt(lam)
