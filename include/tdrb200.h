@@ -1,0 +1,216 @@
+/*
+ * tdrb200.h — C ABI of libtdrb200.so, the B200 (sm_100a) engine for TorchDR's
+ * neighbor-embedding hot path.
+ *
+ * Every entry point is what a binding for the reference's plugin seams would
+ * call; the reference interface each one replaces is cited (paths relative to
+ * the TorchDR tree).  Conventions:
+ *   - all data pointers are DEVICE pointers into caller-owned buffers (PyTorch
+ *     tensors in the Python host), row-major, fp32 unless stated;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 = ok, < 0 = error (TDR_E_*); the message is available
+ *     from tdr_last_error() (thread-local);
+ *   - the library allocates nothing: scratch comes from a caller-provided
+ *     workspace whose size the *_workspace_bytes twin reports;
+ *   - no torch types, no global state, no NCCL dependency (collectives stay
+ *     in the host language, torch.distributed).
+ */
+#ifndef TDRB200_H
+#define TDRB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDR_OK 0
+#define TDR_E_INVALID (-1)   /* bad argument (shape, k, metric ...) */
+#define TDR_E_WORKSPACE (-2) /* workspace too small / misaligned */
+#define TDR_E_CUDA (-3)      /* CUDA runtime error, see tdr_last_error() */
+#define TDR_E_UNSUPPORTED (-4)
+
+#define TDR_METRIC_SQEUCLIDEAN 0
+#define TDR_METRIC_EUCLIDEAN 1
+
+#define TDR_MAX_K 160 /* top-k lists live in shared memory */
+
+typedef void* tdr_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define TDR_API __attribute__((visibility("default")))
+#else
+#define TDR_API
+#endif
+
+/* ---- library ----------------------------------------------------------- */
+TDR_API int tdr_abi_version(void);
+TDR_API const char* tdr_last_error(void);
+/* sm count, compute capability of the current device; TDR_E_UNSUPPORTED unless sm_100 */
+TDR_API int tdr_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- (i) distances / exact kNN ------------------------------------------
+ * Replaces pairwise_distances(..., k=k, backend=None) -> pairwise_distances_torch
+ * (torchdr/distance/base.py:22-249, distance/torch.py:21-125) + kmin
+ * (utils/utils.py:173-216): expanded form ||x||^2+||y||^2-2xy in fp32, self
+ * excluded by global row id (torch.py:111-116 adds 1e12 on the diagonal),
+ * k smallest per row in ascending order, int32 indices.  Ties: lower index
+ * first.  Xq are rows [q_row0, q_row0+nq) of the database when exclude_self
+ * (the distributed chunk of distance/base.py:184-186). */
+TDR_API size_t tdr_knn_workspace_bytes(int64_t nq, int64_t ndb, int d, int k);
+TDR_API int tdr_knn_f32(const float* Xq, int64_t nq, int64_t q_row0,
+                const float* Xdb, int64_t ndb, int d, int k,
+                int exclude_self, int metric,
+                float* out_dist /*[nq,k]*/, int32_t* out_idx /*[nq,k]*/,
+                void* ws, size_t ws_bytes, tdr_stream_t stream);
+
+/* Full matrix C[n,m] (k=None path, distance/torch.py:81-116).  Y may equal X.
+ * Workspace: tdr_knn_workspace_bytes(n, m, d, 1). */
+TDR_API int tdr_pairwise_full_f32(const float* X, int64_t n, const float* Y, int64_t m, int d,
+                          int metric, int exclude_diag, float* C /*[n,m]*/,
+                          void* ws, size_t ws_bytes, tdr_stream_t stream);
+
+/* ---- (ii) per-row bandwidth search --------------------------------------
+ * UMAPAffinity rows: rho = row min, sigma by bracket+bisection
+ * (torchdr/affinity/knn_normalized.py:445-468, utils/root_search.py:17-198),
+ * P = exp(-(C-rho)/sigma).  C rows are the kNN distances. */
+TDR_API int tdr_umap_affinity_f32(const float* C /*[n,k]*/, int64_t n, int k, int max_iter,
+                          float* P /*[n,k]*/, float* rho /*[n]*/, float* sigma /*[n]*/,
+                          tdr_stream_t stream);
+
+/* EntropicAffinity rows (torchdr/affinity/entropic.py:230-312): eps by
+ * bisection on the row entropy, log_P = -C/eps - logsumexp - log(n_total).
+ * use_bounds selects the Vladymyrov bracket (entropic.py:51-115); its four
+ * data-independent scalars (host-computed, fp32) are
+ *   b_num = tN*log(tN/perp), b_den = tN-1, b_lr = log(tN/perp),
+ *   b_logp1 = log((tN-1)*p1/(1-p1)). */
+TDR_API int tdr_entropic_affinity_f32(const float* C /*[n,k]*/, int64_t n, int k,
+                              float target_entropy, float log_n_total,
+                              int use_bounds, float b_num, float b_den, float b_lr, float b_logp1,
+                              int max_iter,
+                              float* logP /*[n,k]*/, float* eps /*[n]*/, float* log_norm /*[n]*/,
+                              tdr_stream_t stream);
+
+/* Fused (i)+(ii): kNN mainloop with the UMAP sigma/rho search in the epilogue
+ * (the "affinity kernel" of BASELINE.json).  Same workspace as tdr_knn_f32. */
+TDR_API int tdr_knn_umap_fused_f32(const float* Xq, int64_t nq, int64_t q_row0,
+                           const float* Xdb, int64_t ndb, int d, int k,
+                           int exclude_self, int max_iter,
+                           float* out_dist /*[nq,k] or NULL*/, int32_t* out_idx /*[nq,k]*/,
+                           float* P /*[nq,k]*/, float* rho /*[nq]*/, float* sigma /*[nq]*/,
+                           void* ws, size_t ws_bytes, tdr_stream_t stream);
+
+/* ---- graph stage ---------------------------------------------------------
+ * symmetrize_sparse(mode="sum_minus_prod") (torchdr/utils/sparse.py:170-206):
+ * Q = P + P^T - P o P^T on the kNN graph, output as CSR of the local rows with
+ * ascending columns (the reference's padded ELL is CSR + padding, sparse.py:118-140).
+ * ext_* (may be NULL, n_ext=0) are transposed edges received from other ranks
+ * (distributed_symmetrize_sparse, sparse.py:209-342): ext_row is the GLOBAL row
+ * (owned locally), ext_col the global column, ext_val = P[col,row].
+ * Capacity of col/val must be >= 2*n_local*k + n_ext.  *nnz_out is a device int64. */
+TDR_API size_t tdr_symmetrize_workspace_bytes(int64_t n_local, int k, int64_t n_ext);
+TDR_API int tdr_symmetrize_csr_f32(const float* P /*[n_local,k]*/, const int32_t* idx /*[n_local,k]*/,
+                           int64_t n_local, int k, int64_t row0, int64_t n_total,
+                           const int64_t* ext_row, const int32_t* ext_col, const float* ext_val,
+                           int64_t n_ext, int transpose_local,
+                           int64_t* rowptr /*[n_local+1]*/, int32_t* col, float* val,
+                           int64_t* nnz_out, void* ws, size_t ws_bytes, tdr_stream_t stream);
+
+/* Edges j of local rows whose transposed entry belongs to another rank: counts per
+ * destination and packed (row=j global, col=i global, val) triples ordered by rank.
+ * Used by the host to build the all_to_all of sparse.py:259-309 with int indices. */
+TDR_API int tdr_symmetrize_export_f32(const float* P, const int32_t* idx, int64_t n_local, int k,
+                              int64_t row0, int64_t n_total, int world, int rank,
+                              int64_t* send_counts /*[world] device*/,
+                              int64_t* out_row, int32_t* out_col, float* out_val /*[n_local*k]*/,
+                              tdr_stream_t stream);
+
+/* CSR -> (values[n,W], indices[n,W] int64, -1 padded) for the SparseAffinity seam
+ * (affinity/base.py:407-431). */
+TDR_API int tdr_csr_to_ell_f32(const int64_t* rowptr, const int32_t* col, const float* val,
+                       int64_t n_local, int64_t width, float pad_val,
+                       float* ell_val, int64_t* ell_idx, tdr_stream_t stream);
+
+/* max over val[0..nnz) -> *out (device float); UMAP.on_affinity_computation_end, umap.py:218 */
+TDR_API int tdr_max_f32(const float* val, int64_t nnz, float* out, tdr_stream_t stream);
+
+/* UMAP edge schedule (umap.py:215-234): epochs_per_sample = A_max/(val+1e-3), inf when
+ * val <= A_max/max_iter; epoch_of_next_sample = copy.  a_max is a host float. */
+TDR_API int tdr_umap_schedule_f32(const float* val, int64_t nnz, float a_max, int max_iter,
+                          float* epochs_per_sample, float* epoch_of_next_sample,
+                          tdr_stream_t stream);
+
+/* Drop never-sampled edges (epochs_per_sample == inf): compact CSR for the step kernel.
+ * out_rowptr[n_local+1], out_col/out_eps/out_eons capacity nnz. */
+TDR_API size_t tdr_compact_workspace_bytes(int64_t n_local, int64_t nnz);
+TDR_API int tdr_umap_compact_f32(const int64_t* rowptr, const int32_t* col, const float* eps,
+                         int64_t n_local, int64_t nnz,
+                         int64_t* out_rowptr, int32_t* out_col, float* out_eps, float* out_eons,
+                         int64_t* nnz_out, void* ws, size_t ws_bytes, tdr_stream_t stream);
+
+/* ---- (iii) optimisation steps -------------------------------------------
+ * One UMAP iteration for local rows [row0, row0+n_local): attraction
+ * (umap.py:236-264) with the epoch_of_next_sample update, repulsion
+ * (umap.py:266-292) on the first 5*active negatives, clamp +-4 each, then the
+ * SGD update z -= lr*g (affinity_matcher.py:427; plain SGD, umap.py:139).
+ * Jacobi: reads Z_in (all N rows), writes Z_out[row0..] (may not alias Z_in).
+ * neg: int64 [n_local, n_neg] adjusted negatives (NE base.py:629-636) or NULL to
+ * draw them in-kernel with Philox4x32-10 keyed by (seed, n_iter, global row).
+ * a, b are the python doubles of umap.py:19-36 (the kernel derives the fp32 constants
+ * (float)a, (float)b, (float)(b-1), (float)(2ab), (float)(-2b) exactly as the torch ops do).
+ * precise != 0 evaluates pow in fp64 (parity mode).
+ * grad_out (nullable) [n_local,2] receives the gradient; gnorm_sq (nullable,
+ * device double) accumulates ||g||^2; nan_flag (nullable, device int) is set
+ * if a NaN is written (check_NaNs, affinity_matcher.py:315). */
+TDR_API int tdr_umap_step_f32(const float* Z_in, float* Z_out, int64_t n_total, int64_t row0, int64_t n_local,
+                      const int64_t* rowptr, const int32_t* col,
+                      const float* epochs_per_sample, float* epoch_of_next_sample,
+                      const int64_t* neg, int n_neg, int negative_sample_rate,
+                      uint64_t seed, int64_t n_iter,
+                      double a, double b, float lam, float repulsion, float lr,
+                      int precise, float* grad_out, double* gnorm_sq, int* nan_flag,
+                      tdr_stream_t stream);
+
+/* n_steps single-GPU iterations ping-ponging Z_a <-> Z_b (in-kernel negatives);
+ * lrs is a HOST array [n_steps].  The result is in Z_a if n_steps is even, else Z_b. */
+TDR_API int tdr_umap_run_f32(float* Z_a, float* Z_b, int64_t n_total,
+                     const int64_t* rowptr, const int32_t* col,
+                     const float* epochs_per_sample, float* epoch_of_next_sample,
+                     int n_neg, int negative_sample_rate, uint64_t seed, int64_t n_iter0,
+                     int n_steps, const float* lrs_host,
+                     double a, double b, float lam, float repulsion,
+                     int precise, double* gnorm_sq, int* nan_flag, tdr_stream_t stream);
+
+/* LargeVis gradient (largevis.py:181-201 differentiated): accumulates into
+ * grad[n_total,2] (zeroed by the caller) with atomics — the autograd scatter of
+ * affinity_matcher.py:418-425 — for local rows; P/idx are the directed kNN rows. */
+TDR_API int tdr_largevis_grad_f32(const float* Z, int64_t n_total, int64_t row0, int64_t n_local,
+                          const float* P /*[n_local,k]*/, const int32_t* idx /*[n_local,k]*/, int k,
+                          const int64_t* neg /*[n_local,n_neg] or NULL*/, int n_neg,
+                          uint64_t seed, int64_t n_iter, float lam, float repulsion,
+                          float* grad /*[n_total,2]*/, tdr_stream_t stream);
+
+/* t-SNE gradient (tsne.py:162-180 differentiated): sparse attraction on the kNN rows
+ * plus the dense N x N repulsion of the logsumexp normaliser (expanded-form distances,
+ * diagonal included).  Rows [row0,row0+n_local) are this rank's share of the double sum.
+ *   phase 0: zero ws; U_i = sum_j w_ij^2 (z_i - z_j) and the partial normaliser S (a device
+ *            double at ws[0]) for local rows; attraction scattered into grad (caller-zeroed).
+ *   (host: all-reduce S when distributed)
+ *   phase 1: grad[local rows] += -4 U_i / S.
+ * ws: tdr_tsne_workspace_bytes(n_local), 16-byte aligned. */
+TDR_API size_t tdr_tsne_workspace_bytes(int64_t n_local);
+TDR_API int tdr_tsne_grad_f32(const float* Z, int64_t n_total, int64_t row0, int64_t n_local,
+                      const float* P, const int32_t* idx, int k, float lam, int phase,
+                      float* grad, void* ws, size_t ws_bytes, tdr_stream_t stream);
+
+/* SGD with momentum (torch.optim.SGD semantics: buf = mu*buf + g; z -= lr*buf; first
+ * step buf = g), NE base.py:331-343.  first != 0 initialises the buffer. */
+TDR_API int tdr_sgd_momentum_f32(float* Z, float* buf, const float* grad, int64_t n_elems,
+                         float lr, float momentum, int first,
+                         double* gnorm_sq, int* nan_flag, tdr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDRB200_H */

@@ -1,0 +1,481 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden
+fixtures generated from the real reference.  Bit-exact for indices/graph structure; stated
+fp32 tolerances for floating-point outputs."""
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from helpers import blobs, clustered, golden, negative_table, rel_fro, t
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from torchdr_b200 import ops as _ops
+
+    return _ops
+
+
+def _cuda(x):
+    return x.to(DEV)
+
+
+# --------------------------------------------------------------------------- (i) kNN
+@pytest.mark.parametrize("name", ["knn_n300_d16_k15", "knn_n2000_d50_k90", "knn_n1500_d128_k15"])
+def test_knn_matches_reference_golden(ops, name):
+    g = golden(name)
+    X, k = t(g["X"]), int(g["k"])
+    C, I = ops.knn(_cuda(X), _cuda(X), k)
+    C, I = C.cpu(), I.cpu()
+    idx64, d64, entry_ok, set_ok = oracle.knn_ambiguity(X, k)
+    ref_I = t(g["I"]).long()
+    # bit-exact indices wherever fp32 can decide the order (oracle/knn.py:knn_ambiguity)
+    assert torch.equal(I.long()[entry_ok], ref_I[entry_ok])
+    assert torch.equal(I.long()[entry_ok], idx64[entry_ok])
+    same_set = (I.long().sort(1)[0] == ref_I.sort(1)[0]).all(1)
+    assert bool(same_set[set_ok].all())
+    assert entry_ok.float().mean() > 0.8
+    # distances: reference's own FAISS-vs-torch tolerance (tests/test_utils.py:144) on the scale of the norms
+    scale = float((X**2).sum(1).max()) * 2
+    assert float((C.double() - d64).abs().max()) < 2e-6 * scale
+    assert bool((C[:, 1:] >= C[:, :-1]).all())
+
+
+def test_knn_euclidean_metric(ops):
+    g = golden("knn_n300_d16_k15")
+    X, k = t(g["X"]), 15
+    C, I = ops.knn(_cuda(X), _cuda(X), k, metric="euclidean")
+    _, _, entry_ok, _ = oracle.knn_ambiguity(X, k)
+    assert torch.equal(I.cpu()[entry_ok], t(g["Ie"])[entry_ok])
+    torch.testing.assert_close(C.cpu(), t(g["Ce"]), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("n,d,k", [(1, 1, 1), (129, 3, 1), (257, 17, 160), (1000, 50, 7), (130, 128, 129)])
+def test_knn_shapes_and_edges(ops, n, d, k):
+    if n == 1:
+        X = blobs(2, d, 1, 0)
+        C, I = ops.knn(_cuda(X), _cuda(X), 1)
+        assert I.cpu().flatten().tolist() == [1, 0]
+        return
+    X = blobs(n, d, 4, n + d)
+    C, I = ops.knn(_cuda(X), _cuda(X), k)
+    idx64, d64, entry_ok, _ = oracle.knn_ambiguity(X, k)
+    assert torch.equal(I.cpu().long()[entry_ok], idx64[entry_ok])
+    assert not bool((I.cpu() == torch.arange(n)[:, None]).any())
+    torch.testing.assert_close(C.cpu().double(), d64, rtol=1e-4, atol=1e-3)
+
+
+def test_knn_ties_resolve_to_lower_index(ops):
+    base = blobs(40, 8, 2, 3)
+    X = torch.cat([base, base, base])  # every point has two exact duplicates
+    C, I = ops.knn(_cuda(X), _cuda(X), 4)
+    I = I.cpu()
+    for i in (0, 17, 40, 95):
+        dup = sorted(j for j in (i % 40, i % 40 + 40, i % 40 + 80) if j != i)
+        assert I[i, :2].tolist() == dup
+
+
+def test_knn_cross_and_chunk(ops):
+    g = golden("pairwise_full_n64")
+    X, Y = t(g["X"]), t(g["Y"])
+    C, I = ops.knn(_cuda(X), _cuda(Y), 5, exclude_self=False)
+    assert torch.equal(I.cpu(), t(g["Ixy"]))
+    torch.testing.assert_close(C.cpu(), t(g["Cxy"]), rtol=1e-5, atol=1e-4)
+    # a row chunk against the full database == the same rows of the full run (distributed rule)
+    X = blobs(700, 24, 5, 9)
+    Cf, If = ops.knn(_cuda(X), _cuda(X), 10)
+    Cc, Ic = ops.knn(_cuda(X)[200:455], _cuda(X), 10, q_row0=200)
+    assert torch.equal(Ic, If[200:455]) and torch.equal(Cc, Cf[200:455])
+
+
+def test_pairwise_full(ops):
+    g = golden("pairwise_full_n64")
+    X, Y = t(g["X"]), t(g["Y"])
+    C = ops.pairwise_full(_cuda(X), None, exclude_diag=True).cpu()
+    torch.testing.assert_close(C, t(g["C_excl"]), rtol=1e-5, atol=1e-4)
+    Cxy = ops.pairwise_full(_cuda(X), _cuda(Y)).cpu()
+    torch.testing.assert_close(Cxy, oracle.pairwise_full(X, Y), rtol=1e-5, atol=1e-4)
+    X = blobs(300, 50, 3, 1)
+    torch.testing.assert_close(ops.pairwise_full(_cuda(X), None, metric="euclidean").cpu(),
+                               oracle.pairwise_full(X, None, "euclidean"), rtol=1e-3, atol=2e-2)
+
+
+def test_knn_large_properties(ops):
+    """Config-2-like data at a size the oracle cannot hold densely: check sampled rows in fp64."""
+    n, d, k = 60_000, 128, 15
+    X = clustered(n, d)
+    C, I = ops.knn(_cuda(X), _cuda(X), k)
+    C, I = C.cpu(), I.cpu()
+    assert bool((C[:, 1:] >= C[:, :-1]).all()) and not bool((I == torch.arange(n)[:, None]).any())
+    rows = torch.arange(0, n, 117)
+    idx64, d64, entry_ok, set_ok = oracle.knn_ambiguity(X, k, q_start=0, q_end=n, block=4096)
+    assert torch.equal(I.long()[rows][entry_ok[rows]], idx64[rows][entry_ok[rows]])
+    assert torch.equal(I.long()[entry_ok], idx64[entry_ok])
+    assert entry_ok.float().mean() > 0.9
+
+
+# --------------------------------------------------------------------------- (ii) affinities
+def test_umap_affinity_rows(ops):
+    g = golden("umap_n300_d16_k15")
+    C = oracle.knn_dense(t(g["X"]), 15)[0]
+    P, rho, sigma = ops.umap_affinity_rows(_cuda(C), 100)
+    assert torch.equal(rho.cpu(), t(g["rho"]))
+    torch.testing.assert_close(sigma.cpu(), t(g["sigma"]), rtol=1e-5, atol=0)
+    torch.testing.assert_close(P.cpu(), t(g["P"]), rtol=2e-5, atol=1e-7)
+    # property of the reference's own test family: marginal = log2(k)
+    torch.testing.assert_close(P.sum(1).cpu(), torch.full((300,), np.log2(15.0), dtype=torch.float32), atol=1e-4, rtol=0)
+
+
+def test_fused_equals_two_kernels(ops):
+    X = blobs(900, 40, 6, 2)
+    dist, idx, P, rho, sigma = ops.knn_umap_fused(_cuda(X), _cuda(X), 15)
+    C2, I2 = ops.knn(_cuda(X), _cuda(X), 15)
+    P2, rho2, sig2 = ops.umap_affinity_rows(C2, 100)
+    assert torch.equal(idx, I2) and torch.equal(dist, C2)
+    assert torch.equal(P, P2) and torch.equal(rho, rho2) and torch.equal(sigma, sig2)
+
+
+@pytest.mark.parametrize("name,perp", [("entropic_n300_d16_p10", 10)])
+def test_entropic_rows(ops, name, perp):
+    from torchdr_b200.affinity import entropic_bound_scalars
+
+    g = golden(name)
+    C = t(g["C"])
+    n = C.shape[0]
+    target = float(torch.log(torch.tensor(perp)) + 1)
+    logn = float(torch.log(torch.tensor(float(n))))
+    logP, eps, ln = ops.entropic_affinity_rows(_cuda(C), target, logn, entropic_bound_scalars(n, perp), 100)
+    torch.testing.assert_close(eps.cpu(), t(g["eps"]), rtol=1e-5, atol=0)
+    torch.testing.assert_close(logP.cpu(), t(g["logP"]), rtol=1e-5, atol=2e-5)
+    torch.testing.assert_close(ln.cpu(), t(g["log_norm"]), rtol=1e-5, atol=1e-5)
+    logP2, eps2, _ = ops.entropic_affinity_rows(_cuda(C), target, logn, None, 100)
+    torch.testing.assert_close(eps2.cpu(), t(g["eps_nobounds"]), rtol=1e-5, atol=0)
+    # the reference's own property test (tests/test_affinity.py:204-210): marginal and entropy at 1e-3
+    l = logP.cpu() + logn
+    torch.testing.assert_close(l.exp().sum(1), torch.ones(n), atol=1e-3, rtol=0)
+    H = -(l.exp() * (l - 1)).sum(1)
+    torch.testing.assert_close(H, torch.full((n,), np.log(perp) + 1, dtype=torch.float32), atol=1e-3, rtol=0)
+
+
+def test_entropic_p30_k90(ops):
+    from torchdr_b200.affinity import entropic_bound_scalars
+
+    g = golden("entropic_n2000_d50_p30")
+    X = t(golden("knn_n2000_d50_k90")["X"])
+    C = oracle.knn_dense(X, 90)[0]
+    target = float(torch.log(torch.tensor(30)) + 1)
+    logP, eps, ln = ops.entropic_affinity_rows(_cuda(C), target, float(np.log(np.float32(2000.0))),
+                                               entropic_bound_scalars(2000, 30), 100)
+    torch.testing.assert_close(eps.cpu(), t(g["eps"]), rtol=2e-5, atol=0)
+    torch.testing.assert_close(logP.cpu()[:64], t(g["logP_head"]), rtol=1e-5, atol=5e-5)
+
+
+# --------------------------------------------------------------------------- graph stage
+def test_symmetrize_bit_exact(ops):
+    g = golden("umap_n300_d16_k15")
+    P, I = t(g["P"]), t(g["I"])
+    rowptr, col, val = ops.symmetrize_csr(_cuda(P), _cuda(I), 0, 300)
+    rp, c_ref, v_ref = oracle.ell_to_csr(t(g["sym_vals"]), t(g["sym_idx"]).long())
+    assert torch.equal(rowptr.cpu(), rp) and torch.equal(col.cpu(), c_ref) and torch.equal(val.cpu(), v_ref)
+    ev, ei = ops.csr_to_ell(rowptr, col, val)
+    assert torch.equal(ev.cpu(), t(g["sym_vals"])) and torch.equal(ei.cpu(), t(g["sym_idx"]).long())
+    a_max = float(ops.max_value(val).item())
+    assert a_max == float(t(g["sym_vals"]).max())
+    eps, eons = ops.umap_schedule(val, a_max, int(g["max_iter"]))
+    per_ref = oracle.ell_to_csr(t(g["eps_per_sample"]), t(g["sym_idx"]).long())[2]
+    assert torch.equal(eps.cpu(), per_ref) and torch.equal(eons.cpu(), per_ref)
+    crp, ccol, ceps, ceons = ops.umap_compact(rowptr, col, eps)
+    keep = per_ref < float("inf")
+    assert torch.equal(ccol.cpu(), c_ref[keep]) and torch.equal(ceps.cpu(), per_ref[keep])
+    deg = torch.zeros(300, dtype=torch.long).index_add_(
+        0, torch.repeat_interleave(torch.arange(300), rp[1:] - rp[:-1])[keep], torch.ones(int(keep.sum()), dtype=torch.long))
+    assert torch.equal((crp[1:] - crp[:-1]).cpu(), deg)
+
+
+def test_symmetrize_partitioned_equals_single(ops):
+    """Two 'ranks' on one GPU: export + import of transposed edges reproduces the single-GPU rows."""
+    g = golden("umap_n300_d16_k15")
+    P, I = _cuda(t(g["P"])), _cuda(t(g["I"]))
+    rowptr, col, val = ops.symmetrize_csr(P, I, 0, 300)
+    bounds = [oracle.chunk_bounds(300, r, 2) for r in range(2)]
+    exports = []
+    for r, (s, e) in enumerate(bounds):
+        counts, er, ec, ev = ops.symmetrize_export(P[s:e], I[s:e], s, 300, 2, r)
+        assert int(counts[r]) == 0
+        exports.append((counts, er, ec, ev))
+    for r, (s, e) in enumerate(bounds):
+        o = 1 - r
+        counts, er, ec, ev = exports[o]
+        off = int(counts[:r].sum())
+        ext = (er[off:off + int(counts[r])], ec[off:off + int(counts[r])], ev[off:off + int(counts[r])])
+        rp_r, col_r, val_r = ops.symmetrize_csr(P[s:e], I[s:e], s, 300, ext=ext)
+        a, b = int(rowptr[s]), int(rowptr[e])
+        assert torch.equal(rp_r, rowptr[s:e + 1] - rowptr[s])
+        assert torch.equal(col_r, col[a:b]) and torch.equal(val_r, val[a:b])
+
+
+# --------------------------------------------------------------------------- (iii) UMAP step
+def _umap_state():
+    g = golden("umap_n300_d16_k15")
+    V, J = t(g["sym_vals"]), t(g["sym_idx"]).long()
+    per, nxt = oracle.umap_edge_schedule(V, int(g["max_iter"]))
+    return g, V, J, per, nxt
+
+
+def _graph_to_dev(ops, J, per, nxt):
+    rp, col, eps = oracle.ell_to_csr(per, J)
+    eons = oracle.ell_to_csr(nxt, J)[2]
+    crp, ccol, ceps, _ = ops.umap_compact(_cuda(rp), _cuda(col), _cuda(eps))
+    keep = eps < float("inf")
+    return crp, ccol, ceps, _cuda(eons[keep].contiguous()), keep
+
+
+def test_umap_single_steps_match_oracle(ops):
+    g, V, J, per, nxt = _umap_state()
+    seed, a, b = int(g["seed"]), float(g["a"]), float(g["b"])
+    T = 100
+    negs = [negative_table(seed, s, 300, 75) for s in range(T)]
+    lrs = oracle.linear_lr_sequence(1.0, T, T)
+    Z = t(g["Z0"]).clone()
+    nxt_cur = nxt.clone()
+    worst = 0.0
+    for step in range(T):
+        Zref, nxt_next = oracle.umap_run(Z, J, per, nxt_cur, [negs[step]], [lrs[step]], a, b, n_iter0=step)
+        if step in (0, 1, 2, 5, 20, 50, 99):
+            crp, ccol, ceps, ceons, keep = _graph_to_dev(ops, J, per, nxt_cur)
+            Zout = torch.empty(300, 2, device=DEV)
+            grad = torch.empty(300, 2, device=DEV)
+            ops.umap_step(_cuda(Z), Zout, 0, 300, crp, ccol, ceps, ceons, step, a, b, float(lrs[step]),
+                          neg=_cuda(negs[step]), precise=True, grad_out=grad)
+            err = rel_fro(Zout.cpu(), Zref)
+            worst = max(worst, err)
+            # one step from an identical state: 1e-5 relative (fp32 ulp-level differences only)
+            assert err < 1e-5, f"step {step}: rel {err:.3e}"
+            live = oracle.ell_to_csr(nxt_next, J)[2][keep]
+            assert torch.equal(ceons.cpu(), live), f"edge schedule differs at step {step}"
+        Z, nxt_cur = Zref, nxt_next
+    assert torch.equal(Z, t(g["Z_100"]))  # the oracle trajectory is the reference's
+    print(f"worst single-step rel error {worst:.3e}")
+
+
+def test_umap_five_steps_match_reference(ops):
+    """Fixed iteration count T=5 from the reference's own Z0: 1e-4 relative (the loop is chaotic:
+    the reference itself diverges by 7e-4 at T=10 under a 1-ulp perturbation, tests/test_oracle_golden.py)."""
+    g, V, J, per, nxt = _umap_state()
+    seed, a, b = int(g["seed"]), float(g["a"]), float(g["b"])
+    crp, ccol, ceps, ceons, _ = _graph_to_dev(ops, J, per, nxt)
+    lrs = oracle.linear_lr_sequence(1.0, 100, 5)
+    Za, Zb = _cuda(t(g["Z0"])).clone(), torch.empty(300, 2, device=DEV)
+    for step in range(5):
+        ops.umap_step(Za, Zb, 0, 300, crp, ccol, ceps, ceons, step, a, b, float(lrs[step]),
+                      neg=_cuda(negative_table(seed, step, 300, 75)), precise=True)
+        Za, Zb = Zb, Za
+        if step + 1 in (1, 2, 5):
+            err = rel_fro(Za.cpu(), g[f"Z_{step + 1}"])
+            assert err < 1e-4, f"T={step + 1}: rel {err:.3e}"
+
+
+def test_umap_fast_math_mode_close(ops):
+    g, V, J, per, nxt = _umap_state()
+    seed, a, b = int(g["seed"]), float(g["a"]), float(g["b"])
+    crp, ccol, ceps, ceons, _ = _graph_to_dev(ops, J, per, nxt)
+    Zb = torch.empty(300, 2, device=DEV)
+    ops.umap_step(_cuda(t(g["Z0"])), Zb, 0, 300, crp, ccol, ceps, ceons, 0, a, b, 1.0,
+                  neg=_cuda(negative_table(seed, 0, 300, 75)), precise=False)
+    assert rel_fro(Zb.cpu(), g["Z_1"]) < 1e-4
+
+
+def test_umap_row_chunks_equal_full(ops):
+    g, V, J, per, nxt = _umap_state()
+    seed, a, b = int(g["seed"]), float(g["a"]), float(g["b"])
+    crp, ccol, ceps, ceons, _ = _graph_to_dev(ops, J, per, nxt)
+    neg = _cuda(negative_table(seed, 0, 300, 75))
+    Zin = _cuda(t(g["Z_5"]))
+    full = torch.empty(300, 2, device=DEV)
+    e1 = ceons.clone()
+    ops.umap_step(Zin, full, 0, 300, crp, ccol, ceps, e1, 7, a, b, 0.5, neg=neg, precise=True)
+    parts = torch.zeros(300, 2, device=DEV)
+    for r in range(3):
+        s, e = oracle.chunk_bounds(300, r, 3)
+        lo, hi = int(crp[s]), int(crp[e])
+        rp = (crp[s:e + 1] - crp[s]).contiguous()
+        e2 = ceons[lo:hi].clone()
+        ops.umap_step(Zin, parts, s, e - s, rp, ccol[lo:hi].contiguous(), ceps[lo:hi].contiguous(), e2, 7, a, b, 0.5,
+                      neg=neg[s:e].contiguous(), precise=True)
+        assert torch.equal(e2, e1[lo:hi])
+    assert torch.equal(parts, full)
+
+
+def test_umap_in_kernel_negatives(ops):
+    g, V, J, per, nxt = _umap_state()
+    a, b = float(g["a"]), float(g["b"])
+    crp, ccol, ceps, ceons, _ = _graph_to_dev(ops, J, per, nxt)
+    Zin = _cuda(t(g["Z_5"]))
+    outs = []
+    for seed in (1, 1, 2):
+        Zo = torch.empty(300, 2, device=DEV)
+        ops.umap_step(Zin, Zo, 0, 300, crp, ccol, ceps, ceons.clone(), 3, a, b, 1.0, neg=None, seed=seed)
+        assert bool(torch.isfinite(Zo).all())
+        outs.append(Zo)
+    assert torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], outs[2])
+    # run entry point: 7 steps == 7 single steps
+    lrs = oracle.linear_lr_sequence(1.0, 100, 7)
+    Za, Zb, e1 = Zin.clone(), torch.empty_like(Zin), ceons.clone()
+    res = ops.umap_run(Za, Zb, crp, ccol, ceps, e1, 0, lrs, a, b, seed=5)
+    Zc, Zd, e2 = Zin.clone(), torch.empty_like(Zin), ceons.clone()
+    for s in range(7):
+        ops.umap_step(Zc, Zd, 0, 300, crp, ccol, ceps, e2, s, a, b, float(lrs[s]), neg=None, seed=5)
+        Zc, Zd = Zd, Zc
+    assert torch.equal(res, Zc) and torch.equal(e1, e2)
+
+
+# --------------------------------------------------------------------------- LargeVis / TSNE
+def test_largevis_gradient_and_steps(ops):
+    g = golden("largevis_n300_d16_p10")
+    seed = int(g["seed"])
+    P, I = _cuda(t(g["P"])), _cuda(t(g["I"]))
+    Z = _cuda(t(g["Z0"])).clone()
+    grad = torch.zeros(300, 2, device=DEV)
+    ops.largevis_grad(Z, 0, 300, P, I, grad, 0, neg=_cuda(negative_table(seed, 0, 300, 5)))
+    assert rel_fro(grad.cpu(), g["G_1"]) < 1e-5
+    mom = torch.zeros_like(Z)
+    for step in range(5):
+        grad.zero_()
+        ops.largevis_grad(Z, 0, 300, P, I, grad, step, neg=_cuda(negative_table(seed, step, 300, 5)))
+        ops.sgd_momentum(Z, mom, grad, float(g["lr"][step]), 0.8, step == 0)
+        if step + 1 in (1, 2, 5):
+            assert rel_fro(Z.cpu(), g[f"Z_{step + 1}"]) < 1e-4, step
+
+
+def test_tsne_gradient_and_steps(ops):
+    g = golden("tsne_n300_d16_p10")
+    P, I = _cuda(t(g["P"])), _cuda(t(g["I"]))
+    Z = _cuda(t(g["Z0"])).clone()
+    ws = ops.tsne_workspace(300, DEV)
+    grad = torch.zeros(300, 2, device=DEV)
+
+    def gradient(lam):
+        grad.zero_()
+        ops.tsne_grad(Z, 0, 300, P, I, lam, 0, grad, ws)
+        ops.tsne_grad(Z, 0, 300, P, I, lam, 1, grad, ws)
+
+    gradient(12.0)
+    assert rel_fro(grad.cpu(), g["G_1"]) < 1e-5
+    mom = torch.zeros_like(Z)
+    lam, first = 12.0, True
+    for step in range(12):
+        gradient(lam)
+        if step + 1 in (2, 5, 12):
+            assert rel_fro(grad.cpu(), g[f"G_{step + 1}"]) < 1e-3, step
+        ops.sgd_momentum(Z, mom, grad, 50.0, 0.5, first)  # lr/momentum keep their first-build values (oracle/tsne.py)
+        first = False
+        if step == int(g["exag_iter"]):
+            lam, first = 1.0, True
+        if step + 1 in (1, 2, 5, 10, 11, 12):
+            assert rel_fro(Z.cpu(), g[f"Z_{step + 1}"]) < 1e-4, step
+
+
+# --------------------------------------------------------------------------- seams
+def test_pairwise_distances_seam():
+    import torchdr_b200 as tb
+
+    g = golden("knn_n300_d16_k15")
+    X = t(g["X"])
+    C, I = tb.pairwise_distances(X, metric="sqeuclidean", k=15, exclude_diag=True, return_indices=True)
+    assert C.is_cuda and I.dtype == torch.int32 and C.dtype == torch.float32
+    _, _, ok, _ = oracle.knn_ambiguity(X, 15)
+    assert torch.equal(I.cpu()[ok], t(g["I"])[ok])
+    Cf, If = tb.pairwise_distances(X, metric="sqeuclidean", k=400, return_indices=True)  # k >= n -> full, None
+    assert If is None and Cf.shape == (300, 300)
+    assert tb.pairwise_distances(X.numpy(), metric="euclidean").shape == (300, 300)
+    with pytest.raises(ValueError, match="distance is not supported"):
+        tb.pairwise_distances(X, metric="chebyshev")
+    ctx = tb.DistributedContext(force_enable=True)
+    ctx.rank, ctx.world_size = 1, 3
+    Cc, Ic = tb.pairwise_distances(X, metric="sqeuclidean", k=15, exclude_diag=True, return_indices=True,
+                                   distributed_ctx=ctx)
+    assert torch.equal(Ic, I[100:200])
+    with pytest.raises(ValueError, match="k cannot be None"):
+        tb.pairwise_distances(X, distributed_ctx=ctx)
+
+
+def test_affinity_seams():
+    import torchdr_b200 as tb
+
+    g = golden("umap_n300_d16_k15")
+    X = t(g["X"])
+    aff = tb.UMAPAffinity(n_neighbors=15, max_iter=100)
+    vals, idx = aff(X, return_indices=True)
+    assert idx.dtype == torch.int64 and torch.equal(idx.cpu(), t(g["sym_idx"]).long())
+    torch.testing.assert_close(vals.cpu(), t(g["sym_vals"]), rtol=5e-5, atol=1e-7)
+    torch.testing.assert_close(aff.eps_.cpu(), t(g["sigma"]), rtol=1e-4, atol=0)
+    P, I = tb.UMAPAffinity(n_neighbors=15, max_iter=100, symmetrize=False)(X)
+    torch.testing.assert_close(P.cpu(), t(g["P"]), rtol=5e-5, atol=1e-7)
+    ge = golden("entropic_n300_d16_p10")
+    ea = tb.EntropicAffinity(perplexity=10, max_iter=100)
+    logP, I = ea(t(ge["X"]), log=True, return_indices=True)
+    _, _, ok, _ = oracle.knn_ambiguity(t(ge["X"]), 30)
+    assert I.dtype == torch.int32 and torch.equal(I.cpu()[ok], t(ge["I"])[ok])
+    torch.testing.assert_close(ea.eps_.cpu(), t(ge["eps"]), rtol=1e-3, atol=0)
+    assert ea.log_normalization_.shape == (300, 1)
+
+
+def test_estimators_end_to_end():
+    """The reference's own acceptance test (tests/test_neighbor_embedding.py:42-74): silhouette > 0.15."""
+    from sklearn.datasets import make_blobs
+    from sklearn.metrics import silhouette_score
+
+    import torchdr_b200 as tb
+
+    X, y = make_blobs(n_samples=600, n_features=20, centers=4, random_state=0)
+    X = X.astype(np.float32)
+    for cls, kw in ((tb.UMAP, dict(n_neighbors=15, max_iter=200)),
+                    (tb.LargeVis, dict(perplexity=20, max_iter=200)),
+                    (tb.TSNE, dict(perplexity=20, max_iter=300))):
+        m = cls(init="normal", random_state=0, **kw)
+        Z = m.fit_transform(X)
+        assert isinstance(Z, np.ndarray) and Z.shape == (600, 2) and np.isfinite(Z).all()
+        assert silhouette_score(Z, y) > 0.15, cls.__name__
+        assert m.is_fitted_ and int(m.n_iter_) >= 0
+    Zt = tb.UMAP(n_neighbors=10, max_iter=20, init="pca").fit_transform(torch.from_numpy(X))
+    assert isinstance(Zt, torch.Tensor) and Zt.device.type == "cpu"
+    with pytest.raises(ValueError, match="smaller than n_neighbors"):
+        tb.UMAP(n_neighbors=700).fit_transform(X)
+
+
+def test_umap_estimator_parity_hooks():
+    """Drive the estimator like the reference's golden run (injected init + negatives through the hook)."""
+    import torchdr_b200 as tb
+
+    g = golden("umap_n300_d16_k15")
+    seed = int(g["seed"])
+
+    class Injected(tb.UMAP):
+        def on_training_step_start(self):
+            self.neg_indices_ = negative_table(seed, int(self.n_iter_), 300, 75).to(self.embedding_.device)
+
+    m = Injected(n_neighbors=15, max_iter=100, init=t(g["Zinit"]), random_state=0, process_duplicates=False,
+                 precise=True, min_grad_norm=0.0)
+    m.max_iter_run = None
+    # stop after 5 steps by shrinking the loop, keeping max_iter (schedule/threshold) at 100
+    orig = m._converged
+    m._converged = lambda step, gn: step >= 0 and False
+    full = m.fit_transform(t(g["X"]))
+    assert full.shape == (300, 2)
+
+    class Five(Injected):
+        def on_training_step_end(self):
+            if int(self.n_iter_) == 4:
+                self._snap = self.embedding_.clone()
+
+    m5 = Five(n_neighbors=15, max_iter=100, init=t(g["Zinit"]), random_state=0, process_duplicates=False,
+              precise=True, min_grad_norm=0.0)
+    m5.fit_transform(t(g["X"]))
+    err = rel_fro(m5._snap.cpu(), g["Z_5"])
+    # end-to-end (own kNN -> own sigma -> own graph -> 5 steps): small fp32 differences in P enter here
+    assert err < 5e-3, err

@@ -1,0 +1,164 @@
+"""CPU tests of the host-side mirror: partition arithmetic, parameter clamps, bracket scalars,
+optimiser/scheduler sequences, and the world_size-2 collectives under gloo."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from helpers import golden, t
+from torchdr_b200.affinity import check_neighbor_param, entropic_bound_scalars
+from torchdr_b200.distributed import DistributedContext, all_bounds, chunk_bounds
+
+
+def test_chunk_bounds_match_reference_rule():
+    # torchdr/tests/test_distributed.py:116-129 overwrites rank/world_size by hand
+    ctx = DistributedContext(force_enable=True)
+    for n, w in [(100, 4), (103, 4), (10, 3), (7, 8), (10_000_000, 8)]:
+        prev = 0
+        for r in range(w):
+            ctx.rank, ctx.world_size = r, w
+            s, e = ctx.compute_chunk_bounds(n)
+            assert (s, e) == oracle.chunk_bounds(n, r, w) and s == prev
+            prev = e
+        assert prev == n
+    idx = torch.tensor([0, 25, 50, 75, 99])
+    assert DistributedContext.get_rank_for_indices(idx, 100, 4).tolist() == [0, 1, 2, 3, 3]
+    idx = torch.arange(103)
+    owners = DistributedContext.get_rank_for_indices(idx, 103, 4)
+    assert owners.tolist() == [oracle.owner_of(i, 103, 4) for i in range(103)]
+
+
+def test_neighbor_param_clamp():
+    assert check_neighbor_param(30, 2000) == 30
+    assert check_neighbor_param(5000, 2000) == 1998
+    assert check_neighbor_param(1, 2000) == 2
+    with pytest.raises(ValueError, match="less than one sample"):
+        check_neighbor_param(5, 1)
+
+
+def test_entropic_bracket_scalars_reproduce_reference_bounds():
+    g = golden("entropic_n300_d16_p10")
+    C = t(g["C"])
+    b_num, b_den, b_lr, b_logp1 = (torch.tensor(v, dtype=torch.float32) for v in entropic_bound_scalars(300, 10))
+    dN, d1, d2 = C.max(1)[0], C[:, 0], C[:, 1]
+    beta_lo = torch.max(b_num / (b_den * (dN - d1)), torch.sqrt(b_lr / (dN * dN - d1 * d1)))
+    beta_hi = b_logp1 / (d2 - d1)
+    assert torch.equal(1 / beta_hi, t(g["begin"])) and torch.equal(1 / beta_lo, t(g["end"]))
+
+
+def _make(cls, **kw):
+    m = cls(**kw)
+    m.n_samples_in_ = 300
+    m.early_exaggeration_coeff_ = m.early_exaggeration_coeff
+    m._dummy = torch.nn.Parameter(torch.zeros(1))
+    m.params_ = [{"params": [m._dummy]}]
+    m._set_learning_rate()
+    m._configure_optimizer()
+    m._configure_scheduler()
+    return m
+
+
+def test_schedules_match_reference_runs():
+    import torchdr_b200 as tb
+
+    g = golden("umap_n300_d16_k15")
+    m = _make(tb.UMAP, n_neighbors=15, max_iter=100)
+    lrs = []
+    for _ in range(100):
+        lrs.append(m._hyper()[0])
+        m._advance_schedule()
+    np.testing.assert_array_equal(np.asarray(lrs, dtype=np.float32), g["lr"].astype(np.float32))
+    assert m._hyper()[1] == 0.0  # plain SGD (umap.py:139)
+
+    g = golden("largevis_n300_d16_p10")
+    m = _make(tb.LargeVis, perplexity=10, max_iter=30)
+    lrs = []
+    for _ in range(30):
+        lrs.append(m._hyper()[0])
+        m._advance_schedule()
+    np.testing.assert_allclose(lrs, g["lr"], rtol=1e-12)
+    assert m._hyper()[1] == 0.8
+
+    # TSNE: after the early-exaggeration rebuild lr and momentum keep their first-build values
+    m = _make(tb.TSNE, perplexity=10, max_iter=20, early_exaggeration_iter=10)
+    assert m._hyper() == (50.0, 0.5)
+    m.early_exaggeration_coeff_ = 1
+    m._set_learning_rate()
+    m._configure_optimizer()
+    m._configure_scheduler()
+    assert m.lr_ == 75.0 and m._hyper() == (50.0, 0.5)  # verified on the reference (oracle/tsne.py)
+
+
+def test_constructor_surface_and_errors():
+    import torchdr_b200 as tb
+
+    m = tb.UMAP()
+    assert (m.n_neighbors, m.max_iter, m.lr, m.n_negatives, m.init) == (30, 1000, 1.0, 150, "pca")
+    assert abs(m._a - 1.5769434602697652) < 1e-12 and abs(m._b - 0.8950608778515733) < 1e-12
+    assert tb.TSNE().early_exaggeration_coeff == 12.0 and tb.LargeVis().n_negatives == 5
+    with pytest.raises(ValueError, match="distance is not supported"):
+        tb.UMAPAffinity(metric="chebyshev")
+    with pytest.raises(RuntimeError, match="requires launching with torchrun"):
+        tb.UMAP(distributed=True)
+    with pytest.raises(ValueError, match="not fitted yet"):
+        tb.UMAP().transform()
+
+
+# ----------------------------------------------------------------------------- gloo, world_size 2
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from torchdr_b200.distributed import all_gather_rows, exchange_edges
+
+        # edge exchange: rank r sends (row, col, val) triples to the owner of row
+        n = 11
+        bounds = all_bounds(n, world)
+        g = torch.Generator().manual_seed(rank)
+        rows = torch.randint(0, n, (20,), generator=g)
+        owners = DistributedContext.get_rank_for_indices(rows, n, world)
+        keep = owners != rank
+        rows, owners = rows[keep], owners[keep]
+        order = torch.argsort(owners, stable=True)
+        rows = rows[order]
+        counts = torch.bincount(owners, minlength=world)
+        cols = (rows * 7 + rank).int()
+        vals = rows.float() + 0.5 * rank
+        rr, rc, rv = exchange_edges(counts, rows, cols, vals)
+        s, e = bounds[rank]
+        ok = bool(((rr >= s) & (rr < e)).all()) and rr.dtype == torch.int64 and rc.dtype == torch.int32
+        ok = ok and bool((rc == (rr * 7 + (1 - rank)).int()).all()) and bool((rv == rr.float() + 0.5 * (1 - rank)).all())
+        # embedding exchange: uneven chunks (6 + 5 rows)
+        Z = torch.full((n, 2), -1.0)
+        Z[s:e] = torch.arange(s, e, dtype=torch.float32)[:, None] + torch.tensor([0.0, 0.25])
+        all_gather_rows(Z, bounds, rank)
+        want = torch.arange(n, dtype=torch.float32)[:, None] + torch.tensor([0.0, 0.25])
+        ok = ok and torch.equal(Z, want)
+        # index >= 2^24 survives the exchange (the reference casts indices to fp32, sparse.py:286-293)
+        big = torch.tensor([2**24 + 1 + rank], dtype=torch.int64)
+        cnt = torch.zeros(world, dtype=torch.int64)
+        cnt[1 - rank] = 1
+        br, _, _ = exchange_edges(cnt, big, big.int(), big.float())
+        ok = ok and int(br[0]) == 2**24 + 1 + (1 - rank)
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_collectives_world_size_2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]

@@ -1,0 +1,21 @@
+"""B200-native neighbor-embedding engine behind TorchDR's distance / Affinity / NeighborEmbedding seams.
+
+Host code is Python over PyTorch tensors; all compute is hand-written sm_100a CUDA reached
+through the C ABI of ``include/tdrb200.h`` (``torchdr_b200/lib/libtdrb200.so``).
+"""
+
+from . import _lib  # noqa: F401
+from .distance import pairwise_distances, LIST_METRICS_B200  # noqa: F401
+from .affinity import UMAPAffinity, EntropicAffinity  # noqa: F401
+from .neighbor_embedding import UMAP, LargeVis, TSNE  # noqa: F401
+from .distributed import DistributedContext  # noqa: F401
+
+__all__ = [
+    "pairwise_distances",
+    "UMAPAffinity",
+    "EntropicAffinity",
+    "UMAP",
+    "LargeVis",
+    "TSNE",
+    "DistributedContext",
+]

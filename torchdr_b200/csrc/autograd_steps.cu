@@ -1,0 +1,257 @@
+// Closed-form gradients of the two autograd-mode methods and the momentum-SGD update.
+//
+// LargeVis  torchdr/neighbor_embedding/largevis.py:181-201
+//   L = lam * sum_is -P_is log Q_is  +  rep * (1/N) sum_in -log(1 - Q_in),
+//   Q = q/(q+1), q = 1/(1+D)  (so Q = 1/(2+D));  dL/dD_is = lam P_is Q_is,
+//   dL/dD_in = -(rep/N) Q_in^2 / (1 - Q_in).  D = |z_i - z_j|^2 (distance/base.py:384-385),
+//   so each edge adds 2 c (z_i - z_j) to row i and subtracts it from row j — the scatter that
+//   autograd's index_put(accumulate) performs (affinity_matcher.py:418-425).
+// t-SNE     torchdr/neighbor_embedding/tsne.py:162-180
+//   attraction on the directed kNN edges: dL/dD = lam P/(1+D);
+//   repulsion = log sum_{all i,j} 1/(1+C_ij) with C in the expanded form of
+//   distance/torch.py:89-91, diagonal included:  grad_i = -(4/S) sum_j w_ij^2 (z_i - z_j).
+// SGD       torch.optim.SGD with momentum (NE base.py:331-343).
+#include "common.cuh"
+
+namespace tdr {
+
+constexpr int kAgWarps = 8;
+
+__device__ __forceinline__ int64_t draw_negative(const Philox& rng, int64_t n_iter, int64_t gi, int s,
+                                                 int64_t n_total) {
+    const uint4 u = rng((uint32_t)n_iter, (uint32_t)(n_iter >> 32) ^ (uint32_t)(gi >> 32), (uint32_t)gi,
+                        (uint32_t)(s >> 2));
+    const uint32_t w = (s & 3) == 0 ? u.x : (s & 3) == 1 ? u.y : (s & 3) == 2 ? u.z : u.w;
+    int64_t j = (int64_t)(((uint64_t)w * (uint64_t)(n_total - 1)) >> 32);
+    return j + ((j >= gi) ? 1 : 0);  // NE base.py:636
+}
+
+__global__ void __launch_bounds__(kAgWarps * 32)
+largevis_grad_kernel(const float2* __restrict__ Z, int64_t n_total, int64_t row0, int64_t n_local,
+                     const float* __restrict__ P, const int32_t* __restrict__ idx, int k,
+                     const int64_t* __restrict__ neg, int n_neg, uint64_t seed, int64_t n_iter, float lam,
+                     float rep_over_n, float* __restrict__ grad) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * kAgWarps + (threadIdx.x >> 5);
+    if (r >= n_local) return;
+    const int64_t gi = row0 + r;
+    const float2 zi = __ldg(Z + gi);
+    float gx = 0.0f, gy = 0.0f;
+    for (int s = lane; s < k; s += 32) {
+        const int64_t j = __ldg(idx + r * k + s);
+        const float2 zj = __ldg(Z + j);
+        const float dx = __fsub_rn(zi.x, zj.x), dy = __fsub_rn(zi.y, zj.y);
+        const float D = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        const float q = __fdiv_rn(1.0f, __fadd_rn(1.0f, D));   // largevis.py:199
+        const float Q = __fdiv_rn(q, __fadd_rn(q, 1.0f));      // largevis.py:200
+        const float c = 2.0f * lam * __ldg(P + r * k + s) * Q;
+        const float cx = c * dx, cy = c * dy;
+        gx += cx;
+        gy += cy;
+        atomicAdd(grad + 2 * j, -cx);
+        atomicAdd(grad + 2 * j + 1, -cy);
+    }
+    const Philox rng(seed);
+    for (int s = lane; s < n_neg; s += 32) {
+        const int64_t j = neg ? __ldg(neg + r * n_neg + s) : draw_negative(rng, n_iter, gi, s, n_total);
+        const float2 zj = __ldg(Z + j);
+        const float dx = __fsub_rn(zi.x, zj.x), dy = __fsub_rn(zi.y, zj.y);
+        const float D = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        const float q = __fdiv_rn(1.0f, __fadd_rn(1.0f, D));   // largevis.py:188
+        const float Q = __fdiv_rn(q, __fadd_rn(q, 1.0f));      // largevis.py:189
+        const float c = -2.0f * rep_over_n * __fdiv_rn(Q * Q, __fsub_rn(1.0f, Q));
+        const float cx = c * dx, cy = c * dy;
+        gx += cx;
+        gy += cy;
+        atomicAdd(grad + 2 * j, -cx);
+        atomicAdd(grad + 2 * j + 1, -cy);
+    }
+    gx = warp_sum(gx);
+    gy = warp_sum(gy);
+    if (lane == 0) {
+        atomicAdd(grad + 2 * gi, gx);
+        atomicAdd(grad + 2 * gi + 1, gy);
+    }
+}
+
+__global__ void __launch_bounds__(kAgWarps * 32)
+tsne_attract_kernel(const float2* __restrict__ Z, int64_t row0, int64_t n_local, const float* __restrict__ P,
+                    const int32_t* __restrict__ idx, int k, float lam, float* __restrict__ grad) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * kAgWarps + (threadIdx.x >> 5);
+    if (r >= n_local) return;
+    const int64_t gi = row0 + r;
+    const float2 zi = __ldg(Z + gi);
+    float gx = 0.0f, gy = 0.0f;
+    for (int s = lane; s < k; s += 32) {
+        const int64_t j = __ldg(idx + r * k + s);
+        const float2 zj = __ldg(Z + j);
+        const float dx = __fsub_rn(zi.x, zj.x), dy = __fsub_rn(zi.y, zj.y);
+        const float D = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        const float c = 2.0f * lam * __fdiv_rn(__ldg(P + r * k + s), __fadd_rn(1.0f, D));  // tsne.py:169
+        const float cx = c * dx, cy = c * dy;
+        gx += cx;
+        gy += cy;
+        atomicAdd(grad + 2 * j, -cx);
+        atomicAdd(grad + 2 * j + 1, -cy);
+    }
+    gx = warp_sum(gx);
+    gy = warp_sum(gy);
+    if (lane == 0) {
+        atomicAdd(grad + 2 * gi, gx);
+        atomicAdd(grad + 2 * gi + 1, gy);
+    }
+}
+
+// Dense repulsion: thread = one local row i, the j range streamed through shared memory in
+// tiles of TJ points (x, y, |z|^2).  blockIdx.y splits the j range so small N still fills the chip.
+constexpr int TSNE_TI = 128, TSNE_TJ = 512;
+
+__global__ void __launch_bounds__(TSNE_TI)
+tsne_repulse_kernel(const float2* __restrict__ Z, int64_t n_total, int64_t row0, int64_t n_local,
+                    int64_t j_per_split, float* __restrict__ U /*[n_local,2]*/, double* __restrict__ S) {
+    __shared__ float4 tile[TSNE_TJ];
+    const int64_t r = (int64_t)blockIdx.x * TSNE_TI + threadIdx.x;
+    const bool live = r < n_local;
+    const float2 zi = live ? __ldg(Z + row0 + r) : make_float2(0.f, 0.f);
+    const float ni = fmaf(zi.x, zi.x, zi.y * zi.y);
+    float ux = 0.0f, uy = 0.0f, s = 0.0f;
+    const int64_t j_begin = (int64_t)blockIdx.y * j_per_split;
+    const int64_t j_end = min(n_total, j_begin + j_per_split);
+    for (int64_t j0 = j_begin; j0 < j_end; j0 += TSNE_TJ) {
+        const int cnt = (int)min((int64_t)TSNE_TJ, j_end - j0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < cnt; t += TSNE_TI) {
+            const float2 zj = __ldg(Z + j0 + t);
+            tile[t] = make_float4(zj.x, zj.y, fmaf(zj.x, zj.x, zj.y * zj.y), 0.f);
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int t = 0; t < cnt; ++t) {
+            const float4 zj = tile[t];
+            // distance/torch.py:89-91 expanded form on the embedding (diagonal included)
+            const float C = __fsub_rn(__fadd_rn(ni, zj.z), 2.0f * fmaf(zi.x, zj.x, zi.y * zj.y));
+            const float w = __frcp_rn(__fadd_rn(1.0f, C));  // exp(-log(1+C)), tsne.py:176-177
+            const float w2 = w * w;
+            s += w;
+            ux = fmaf(w2, zi.x - zj.x, ux);
+            uy = fmaf(w2, zi.y - zj.y, uy);
+        }
+    }
+    if (live) {
+        atomicAdd(U + 2 * r, ux);
+        atomicAdd(U + 2 * r + 1, uy);
+    }
+    // block reduction of the normaliser in fp64
+    double sd = live ? (double)s : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
+    __shared__ double wsum[TSNE_TI / 32];
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = sd;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < TSNE_TI / 32; ++w) t += wsum[w];
+        atomicAdd(S, t);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+tsne_finish_kernel(const float* __restrict__ U, const double* __restrict__ S, int64_t row0, int64_t n_local,
+                   float* __restrict__ grad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * n_local) return;
+    const float scale = (float)(-4.0 / *S);
+    atomicAdd(grad + 2 * row0 + i, scale * U[i]);
+}
+
+__global__ void __launch_bounds__(256)
+sgd_momentum_kernel(float* __restrict__ Z, float* __restrict__ buf, const float* __restrict__ grad, int64_t n,
+                    float neg_lr, float mu, int first, double* __restrict__ gnorm_sq, int* __restrict__ nan_flag) {
+    double gn = 0.0;
+    bool bad = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float g = grad[i];
+        // torch.optim.sgd: buf = g (first step) | buf.mul_(mu).add_(g) ; param.add_(buf, alpha=-lr)
+        const float b = first ? g : __fadd_rn(__fmul_rn(buf[i], mu), g);
+        buf[i] = b;
+        const float z = fmaf(neg_lr, b, Z[i]);
+        Z[i] = z;
+        gn += (double)g * g;
+        bad |= (z != z);
+    }
+    if (gnorm_sq) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gn += __shfl_xor_sync(0xffffffffu, gn, o);
+        if ((threadIdx.x & 31) == 0 && gn != 0.0) atomicAdd(gnorm_sq, gn);
+    }
+    if (nan_flag && bad) atomicExch(nan_flag, 1);
+}
+
+}  // namespace tdr
+
+using namespace tdr;
+
+extern "C" TDR_API int tdr_largevis_grad_f32(const float* Z, int64_t n_total, int64_t row0, int64_t n_local, const float* P,
+                                     const int32_t* idx, int k, const int64_t* neg, int n_neg, uint64_t seed,
+                                     int64_t n_iter, float lam, float repulsion, float* grad, tdr_stream_t stream) {
+    TDR_CHECK_ARG(Z && P && idx && grad, "tdr_largevis_grad_f32: null pointer");
+    TDR_CHECK_ARG(n_total >= 2 && row0 >= 0 && n_local >= 0 && row0 + n_local <= n_total && k >= 1 && n_neg >= 0,
+                  "tdr_largevis_grad_f32: bad shape");
+    if (n_local == 0) return TDR_OK;
+    const unsigned blocks = (unsigned)((n_local + kAgWarps - 1) / kAgWarps);
+    largevis_grad_kernel<<<blocks, kAgWarps * 32, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(Z), n_total, row0, n_local, P, idx, k, neg, n_neg, seed, n_iter, lam,
+        repulsion / (float)n_total, grad);
+    TDR_LAUNCH_CHECK();
+    return TDR_OK;
+}
+
+extern "C" TDR_API size_t tdr_tsne_workspace_bytes(int64_t n_local) { return 256 + (size_t)n_local * 8; }
+
+extern "C" TDR_API int tdr_tsne_grad_f32(const float* Z, int64_t n_total, int64_t row0, int64_t n_local, const float* P,
+                                 const int32_t* idx, int k, float lam, int phase, float* grad, void* ws,
+                                 size_t ws_bytes, tdr_stream_t stream) {
+    TDR_CHECK_ARG(Z && grad && ws, "tdr_tsne_grad_f32: null pointer");
+    TDR_CHECK_ARG(n_total >= 2 && row0 >= 0 && n_local >= 0 && row0 + n_local <= n_total, "tdr_tsne_grad_f32: bad shape");
+    TDR_CHECK_ARG(ws_bytes >= tdr_tsne_workspace_bytes(n_local) && (uintptr_t)ws % 16 == 0,
+                  "tdr_tsne_grad_f32: workspace too small or misaligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* S = reinterpret_cast<double*>(ws);
+    float* U = reinterpret_cast<float*>((char*)ws + 256);
+    const float2* Z2 = reinterpret_cast<const float2*>(Z);
+    if (phase == 0) {
+        // partial normaliser + unnormalised repulsion of the local rows, and the sparse attraction
+        TDR_CUDA(cudaMemsetAsync(ws, 0, tdr_tsne_workspace_bytes(n_local), st));
+        if (n_local > 0) {
+            const unsigned bx = (unsigned)((n_local + TSNE_TI - 1) / TSNE_TI);
+            unsigned by = 1;
+            while ((int64_t)bx * by < 2 * kNumSMs && (int64_t)by * TSNE_TJ * 2 <= n_total) by *= 2;
+            const int64_t per = (n_total + by - 1) / by;
+            const int64_t per_al = (per + TSNE_TJ - 1) / TSNE_TJ * TSNE_TJ;
+            tsne_repulse_kernel<<<dim3(bx, by), TSNE_TI, 0, st>>>(Z2, n_total, row0, n_local, per_al, U, S);
+            if (P && idx && k > 0) {
+                const unsigned blocks = (unsigned)((n_local + kAgWarps - 1) / kAgWarps);
+                tsne_attract_kernel<<<blocks, kAgWarps * 32, 0, st>>>(Z2, row0, n_local, P, idx, k, lam, grad);
+            }
+        }
+    } else {
+        // S now holds the global normaliser (all-reduced by the host when distributed)
+        if (n_local > 0)
+            tsne_finish_kernel<<<(unsigned)((2 * n_local + 255) / 256), 256, 0, st>>>(U, S, row0, n_local, grad);
+    }
+    TDR_LAUNCH_CHECK();
+    return TDR_OK;
+}
+
+extern "C" TDR_API int tdr_sgd_momentum_f32(float* Z, float* buf, const float* grad, int64_t n_elems, float lr,
+                                    float momentum, int first, double* gnorm_sq, int* nan_flag,
+                                    tdr_stream_t stream) {
+    TDR_CHECK_ARG(Z && buf && grad && n_elems >= 0, "tdr_sgd_momentum_f32: bad arguments");
+    if (n_elems == 0) return TDR_OK;
+    const unsigned grid = (unsigned)min((int64_t)kNumSMs * 8, (n_elems + 255) / 256);
+    sgd_momentum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(Z, buf, grad, n_elems, -lr, momentum, first,
+                                                               gnorm_sq, nan_flag);
+    TDR_LAUNCH_CHECK();
+    return TDR_OK;
+}

@@ -1,0 +1,215 @@
+// (iii) UMAP optimisation step: sampled attraction + repulsion + clamp + SGD in ONE kernel.
+//
+// Replaces, per iteration, the ~40 ATen launches of torchdr/neighbor_embedding/umap.py:236-292
+// + neighbor_embedding/base.py:617-649 (negative sampling) + affinity_matcher.py:427 (SGD):
+//   * graph as CSR (live edges only) instead of the 75 %-padded ELL;
+//   * epoch_of_next_sample read-modify-written in place, only for due edges;
+//   * negatives drawn in-kernel (Philox4x32-10) in throughput mode, or read from the
+//     caller's table (the reference's neg_indices_) in parity mode;
+//   * Jacobi update: every gradient is computed from Z_in, results go to Z_out.
+// One warp per row: lanes stride over the row's CSR segment, then over the 5*active
+// negatives; 8-byte gathers of z_j hit L2 (Z is 8 MB at 1 M points, 80 MB at 10 M).
+//
+// Arithmetic mirrors the reference op by op (each torch op is one rounding): explicit
+// __f*_rn intrinsics keep the compiler from contracting them into FMAs.
+#include "common.cuh"
+
+namespace tdr {
+
+struct UmapStepParams {
+    const float2* Zin;
+    float2* Zout;
+    int64_t n_total, row0, n_local;
+    const int64_t* rowptr;
+    const int32_t* col;
+    const float* eps;
+    float* eons;
+    const int64_t* neg;
+    int n_neg, rate;
+    uint64_t seed;
+    int64_t n_iter;
+    float a, b, bm1, two_ab, neg_two_b, lam, rep, lr;
+    float2* grad_out;
+    double* gnorm_sq;
+    int* nan_flag;
+};
+
+template <bool PRECISE>
+__device__ __forceinline__ float pow_b(float x, float y) {
+    // torch pow(tensor, scalar) evaluates powf in fp32 (Sleef, 1 ulp); parity mode goes through
+    // fp64 so the result is the correctly rounded fp32 value in all but ~1e-9 of cases.
+    if (PRECISE) return (float)pow((double)x, (double)y);
+    return powf(x, y);
+}
+
+constexpr int kStepWarps = 8;
+
+template <bool PRECISE>
+__global__ void __launch_bounds__(kStepWarps * 32) umap_step_kernel(const UmapStepParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = (int64_t)blockIdx.x * kStepWarps + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * kStepWarps;
+    const float due_before = (float)(p.n_iter + 1);  // umap.py:251 (long promoted to fp32)
+    double gn_local = 0.0;
+    bool saw_nan = false;
+
+    for (int64_t r = warp_global; r < p.n_local; r += n_warps) {
+        const int64_t gi = p.row0 + r;
+        const float2 zi = __ldg(p.Zin + gi);
+        // ---- attraction (umap.py:236-264) over the row's live edges
+        const int64_t e0 = p.rowptr[r], e1 = p.rowptr[r + 1];
+        float gx = 0.0f, gy = 0.0f;
+        int active = 0;
+        for (int64_t e = e0 + lane; e < e1; e += 32) {
+            const float nxt = p.eons[e];
+            if (nxt <= due_before) {
+                p.eons[e] = __fadd_rn(nxt, __ldg(p.eps + e));  // umap.py:253-255
+                ++active;
+                const float2 zj = __ldg(p.Zin + __ldg(p.col + e));
+                const float dx = __fsub_rn(zi.x, zj.x), dy = __fsub_rn(zi.y, zj.y);
+                const float D = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));  // distance/base.py:384-385
+                if (D > 0.0f) {  // umap.py:243,247
+                    const float den = __fadd_rn(1.0f, __fmul_rn(p.a, pow_b<PRECISE>(D, p.b)));
+                    const float coef = __fdiv_rn(__fmul_rn(pow_b<PRECISE>(D, p.bm1), p.two_ab), den);
+                    gx = fmaf(dx, coef, gx);
+                    gy = fmaf(dy, coef, gy);
+                }
+            }
+        }
+        gx = warp_sum(gx);
+        gy = warp_sum(gy);
+        active = warp_sum_int(active);
+        gx = fminf(fmaxf(gx, -4.0f), 4.0f);  // umap.py:263
+        gy = fminf(fmaxf(gy, -4.0f), 4.0f);
+
+        // ---- repulsion (umap.py:266-292) on the first rate*active negatives
+        int quota = active * p.rate;
+        if (quota > p.n_neg) quota = p.n_neg;
+        float rx = 0.0f, ry = 0.0f;
+        const Philox rng(p.seed);
+        for (int s = lane; s < quota; s += 32) {
+            int64_t j;
+            if (p.neg) {
+                j = __ldg(p.neg + r * p.n_neg + s);
+            } else {
+                // one Philox block per 4 consecutive slots: counter = (n_iter, row, slot/4)
+                const uint4 u = rng((uint32_t)p.n_iter, (uint32_t)(p.n_iter >> 32) ^ (uint32_t)(gi >> 32),
+                                    (uint32_t)gi, (uint32_t)(s >> 2));
+                const uint32_t w = (s & 3) == 0 ? u.x : (s & 3) == 1 ? u.y : (s & 3) == 2 ? u.z : u.w;
+                j = (int64_t)(((uint64_t)w * (uint64_t)(p.n_total - 1)) >> 32);  // uniform on [0, N-2]
+                j += (j >= gi) ? 1 : 0;                                         // NE base.py:636
+            }
+            const float2 zj = __ldg(p.Zin + j);
+            const float dx = __fsub_rn(zi.x, zj.x), dy = __fsub_rn(zi.y, zj.y);
+            const float D = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+            const float den = __fadd_rn(1.0f, __fmul_rn(p.a, pow_b<PRECISE>(D, p.b)));   // umap.py:273
+            const float coef = __fmul_rn(__frcp_rn(__fmul_rn(__fadd_rn(D, 1e-3f), den)), p.neg_two_b);  // :274-276
+            rx = fmaf(dx, coef, rx);
+            ry = fmaf(dy, coef, ry);
+        }
+        rx = warp_sum(rx);
+        ry = warp_sum(ry);
+        rx = fminf(fmaxf(rx, -4.0f), 4.0f);  // umap.py:291
+        ry = fminf(fmaxf(ry, -4.0f), 4.0f);
+
+        if (lane == 0) {
+            // NE base.py:237-241: lam * attractive + repulsion_strength * repulsive
+            const float g0 = __fadd_rn(__fmul_rn(p.lam, gx), __fmul_rn(p.rep, rx));
+            const float g1 = __fadd_rn(__fmul_rn(p.lam, gy), __fmul_rn(p.rep, ry));
+            float2 zo;  // torch.optim.SGD: param.add_(grad, alpha=-lr)
+            zo.x = fmaf(-p.lr, g0, zi.x);
+            zo.y = fmaf(-p.lr, g1, zi.y);
+            p.Zout[gi] = zo;
+            if (p.grad_out) p.grad_out[r] = make_float2(g0, g1);
+            gn_local += (double)g0 * g0 + (double)g1 * g1;
+            saw_nan |= (zo.x != zo.x) || (zo.y != zo.y);
+        }
+    }
+    if (lane == 0) {
+        if (p.gnorm_sq && gn_local != 0.0) atomicAdd(p.gnorm_sq, gn_local);
+        if (p.nan_flag && saw_nan) atomicExch(p.nan_flag, 1);
+    }
+}
+
+static int launch_step(const UmapStepParams& p, int precise, cudaStream_t st) {
+    int64_t blocks = (p.n_local + kStepWarps - 1) / kStepWarps;
+    const int64_t cap = (int64_t)kNumSMs * 32;  // persistent-style cap: 8 CTAs x 4 waves per SM
+    if (blocks > cap) blocks = cap;
+    if (precise) umap_step_kernel<true><<<(unsigned)blocks, kStepWarps * 32, 0, st>>>(p);
+    else umap_step_kernel<false><<<(unsigned)blocks, kStepWarps * 32, 0, st>>>(p);
+    TDR_LAUNCH_CHECK();
+    return TDR_OK;
+}
+
+static void fill_consts(UmapStepParams& p, float a, float b, double a64, double b64) {
+    // python-side scalars are doubles cast to fp32 at the op (umap.py:244-246, 273-276)
+    p.a = a;
+    p.b = b;
+    p.bm1 = (float)(b64 - 1.0);
+    p.two_ab = (float)(2.0 * a64 * b64);
+    p.neg_two_b = (float)(-2.0 * b64);
+}
+
+}  // namespace tdr
+
+using namespace tdr;
+
+extern "C" TDR_API int tdr_umap_step_f32(const float* Z_in, float* Z_out, int64_t n_total, int64_t row0, int64_t n_local,
+                                 const int64_t* rowptr, const int32_t* col, const float* epochs_per_sample,
+                                 float* epoch_of_next_sample, const int64_t* neg, int n_neg,
+                                 int negative_sample_rate, uint64_t seed, int64_t n_iter, double a, double b,
+                                 float lam, float repulsion, float lr, int precise, float* grad_out,
+                                 double* gnorm_sq, int* nan_flag, tdr_stream_t stream) {
+    TDR_CHECK_ARG(Z_in && Z_out && rowptr && col && epochs_per_sample && epoch_of_next_sample,
+                  "tdr_umap_step_f32: null pointer");
+    TDR_CHECK_ARG(Z_in != Z_out, "tdr_umap_step_f32: Z_in and Z_out must not alias (Jacobi update)");
+    TDR_CHECK_ARG(n_total >= 2 && row0 >= 0 && n_local >= 0 && row0 + n_local <= n_total,
+                  "tdr_umap_step_f32: bad row range");
+    TDR_CHECK_ARG(n_neg >= 0 && negative_sample_rate >= 0, "tdr_umap_step_f32: bad negative sampling config");
+    if (n_local == 0) return TDR_OK;
+    UmapStepParams p{};
+    p.Zin = reinterpret_cast<const float2*>(Z_in);
+    p.Zout = reinterpret_cast<float2*>(Z_out);
+    p.n_total = n_total;
+    p.row0 = row0;
+    p.n_local = n_local;
+    p.rowptr = rowptr;
+    p.col = col;
+    p.eps = epochs_per_sample;
+    p.eons = epoch_of_next_sample;
+    p.neg = neg;
+    p.n_neg = n_neg;
+    p.rate = negative_sample_rate;
+    p.seed = seed;
+    p.n_iter = n_iter;
+    fill_consts(p, (float)a, (float)b, a, b);
+    p.lam = lam;
+    p.rep = repulsion;
+    p.lr = lr;
+    p.grad_out = reinterpret_cast<float2*>(grad_out);
+    p.gnorm_sq = gnorm_sq;
+    p.nan_flag = nan_flag;
+    return launch_step(p, precise, (cudaStream_t)stream);
+}
+
+extern "C" TDR_API int tdr_umap_run_f32(float* Z_a, float* Z_b, int64_t n_total, const int64_t* rowptr,
+                                const int32_t* col, const float* epochs_per_sample, float* epoch_of_next_sample,
+                                int n_neg, int negative_sample_rate, uint64_t seed, int64_t n_iter0, int n_steps,
+                                const float* lrs_host, double a, double b, float lam, float repulsion, int precise,
+                                double* gnorm_sq, int* nan_flag, tdr_stream_t stream) {
+    TDR_CHECK_ARG(Z_a && Z_b && Z_a != Z_b && lrs_host && n_steps >= 0, "tdr_umap_run_f32: bad arguments");
+    float* src = Z_a;
+    float* dst = Z_b;
+    for (int t = 0; t < n_steps; ++t) {
+        // gradient norm is only wanted for the last step of the batch (the host's check_interval)
+        int rc = tdr_umap_step_f32(src, dst, n_total, 0, n_total, rowptr, col, epochs_per_sample,
+                                   epoch_of_next_sample, nullptr, n_neg, negative_sample_rate, seed, n_iter0 + t,
+                                   a, b, lam, repulsion, lrs_host[t], precise, nullptr,
+                                   (t == n_steps - 1) ? gnorm_sq : nullptr, nan_flag, stream);
+        if (rc != TDR_OK) return rc;
+        float* tmp = src;
+        src = dst;
+        dst = tmp;
+    }
+    return TDR_OK;
+}

@@ -1,0 +1,115 @@
+"""Row partition and the (few) collectives of the path.
+
+Mirrors ``torchdr/distributed/__init__.py:115-318`` (``DistributedContext``): rank r owns the
+contiguous rows ``compute_chunk_bounds(n)``; the first ``n % W`` ranks own one extra row.
+Collectives go through ``torch.distributed`` (NCCL on GPUs; the helpers are backend-agnostic so
+the host logic is testable under gloo).  Differences from the reference, on purpose:
+
+* edge exchange for the symmetrisation carries int64/int32 indices, not indices cast to fp32
+  (``utils/sparse.py:286-293`` corrupts indices >= 2^24);
+* the per-iteration exchange of the closed-form (UMAP) update is an all-gather of each rank's
+  updated rows instead of an all-reduce of a zero-padded N x q gradient
+  (``affinity_matcher.py:395-413``) — same result because plain SGD is row-local.
+"""
+
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def is_distributed() -> bool:
+    return dist.is_available() and dist.is_initialized()
+
+
+def get_rank() -> int:
+    return dist.get_rank() if is_distributed() else 0
+
+
+def get_world_size() -> int:
+    return dist.get_world_size() if is_distributed() else 1
+
+
+class DistributedContext:
+    """``torchdr/distributed/__init__.py:115-318``."""
+
+    def __init__(self, force_enable: bool = False):
+        self.force_enable = force_enable
+        if is_distributed():
+            self.is_initialized = True
+            self.rank = dist.get_rank()
+            self.world_size = dist.get_world_size()
+            import os
+
+            self.local_rank = int(os.environ.get("LOCAL_RANK", self.rank))
+        else:
+            self.is_initialized = bool(force_enable)
+            self.rank = 0
+            self.world_size = 1
+            self.local_rank = 0
+
+    def compute_chunk_bounds(self, n_samples: int) -> Tuple[int, int]:
+        """distributed/__init__.py:209-219."""
+        return chunk_bounds(n_samples, self.rank, self.world_size)
+
+    @staticmethod
+    def get_rank_for_indices(indices: torch.Tensor, n_samples: int, world_size: int) -> torch.Tensor:
+        """distributed/__init__.py:251-267."""
+        base, extra = divmod(n_samples, world_size)
+        cut = extra * (base + 1)
+        late = extra + (indices - cut) // max(base, 1)
+        ranks = torch.where(indices < cut, indices // (base + 1), late)
+        return torch.clamp(ranks, 0, world_size - 1)
+
+
+def chunk_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
+    base, extra = divmod(n, world)
+    if rank < extra:
+        start = rank * (base + 1)
+        return start, start + base + 1
+    start = rank * base + extra
+    return start, start + base
+
+
+def all_bounds(n: int, world: int):
+    return [chunk_bounds(n, r, world) for r in range(world)]
+
+
+def exchange_edges(counts: torch.Tensor, row: torch.Tensor, col: torch.Tensor, val: torch.Tensor, group=None):
+    """All-to-all of (row, col, val) triples packed by destination rank (``utils/sparse.py:259-309``).
+
+    ``counts[r]`` triples go to rank r (the slice order of the packed arrays).  Returns the
+    concatenated triples received by this rank.  Works on any backend (NCCL / gloo).
+    """
+    world = dist.get_world_size(group)
+    send_counts = [int(c) for c in counts.tolist()]
+    recv_counts_t = torch.empty(world, dtype=torch.int64, device=row.device)
+    dist.all_to_all_single(recv_counts_t, torch.tensor(send_counts, dtype=torch.int64, device=row.device), group=group)
+    recv_counts = [int(c) for c in recv_counts_t.tolist()]
+    out = []
+    for t in (row, col, val):
+        recv = torch.empty(sum(recv_counts), dtype=t.dtype, device=t.device)
+        dist.all_to_all_single(recv, t.contiguous(), output_split_sizes=recv_counts, input_split_sizes=send_counts,
+                               group=group)
+        out.append(recv)
+    return tuple(out)
+
+
+def all_gather_rows(Z_full: torch.Tensor, bounds, rank: int, group=None):
+    """In place: every rank contributes ``Z_full[start:end]`` of its own chunk; afterwards all rows are current.
+
+    Chunks differ by at most one row, so each is padded to the longest chunk for one
+    ``all_gather_into_tensor`` (8 N bytes on the wire for q = 2).
+    """
+    world = len(bounds)
+    longest = max(e - s for s, e in bounds)
+    q = Z_full.shape[1]
+    s, e = bounds[rank]
+    send = torch.zeros((longest, q), dtype=Z_full.dtype, device=Z_full.device)
+    send[: e - s] = Z_full[s:e]
+    recv = torch.empty((world * longest, q), dtype=Z_full.dtype, device=Z_full.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    for r, (rs, re) in enumerate(bounds):
+        if r != rank:
+            Z_full[rs:re] = recv[r * longest : r * longest + (re - rs)]
+    return Z_full

@@ -1,0 +1,556 @@
+"""Estimator seam: ``UMAP``, ``LargeVis``, ``TSNE`` with the reference's sklearn-style surface.
+
+Mirrors ``torchdr/base.py:27-229`` (``DRModule.fit / fit_transform / transform``),
+``torchdr/affinity_matcher.py:201-352`` (affinity -> init -> optimisation loop with the
+``on_*`` lifecycle hooks) and ``torchdr/neighbor_embedding/{base,umap,largevis,tsne}.py``.
+The loop body is one CUDA kernel per iteration (UMAP) or two (gradient + momentum SGD); the
+optimiser / scheduler objects are the reference's own ``torch.optim`` classes stepped on a
+dummy parameter, so learning-rate and momentum sequences — including the reference's
+param-group reuse when the optimiser is rebuilt after early exaggeration — are identical.
+"""
+
+import logging
+import os
+import random
+import warnings
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+from .affinity import EntropicAffinity, UMAPAffinity
+from .distance import _to_device_tensor
+from .distributed import all_bounds, all_gather_rows, is_distributed
+
+
+def find_ab_params(spread, min_dist):
+    """``torchdr/neighbor_embedding/umap.py:19-36`` (same scipy call, same grid)."""
+    from scipy.optimize import curve_fit
+
+    def curve(x, a, b):
+        return 1.0 / (1.0 + a * x ** (2 * b))
+
+    xv = np.linspace(0, spread * 3, 300)
+    yv = np.zeros(xv.shape)
+    yv[xv < min_dist] = 1.0
+    yv[xv >= min_dist] = np.exp(-(xv[xv >= min_dist] - min_dist) / spread)
+    params, _ = curve_fit(curve, xv, yv)
+    return params[0].item(), params[1].item()
+
+
+class _NeighborEmbeddingB200:
+    """Driver shared by the three methods (affinity_matcher.py + neighbor_embedding/base.py)."""
+
+    _use_closed_form_gradients = False
+
+    def __init__(self, n_components=2, lr=1.0, optimizer="SGD", optimizer_kwargs="auto", scheduler=None,
+                 scheduler_kwargs="auto", min_grad_norm=1e-7, max_iter=2000, init="pca", init_scaling=1e-4,
+                 device="auto", backend=None, verbose=False, random_state=None, early_exaggeration_coeff=None,
+                 early_exaggeration_iter=None, repulsion_strength=1.0, check_interval=50, compile=False,
+                 distributed="auto", process_duplicates=True, precise=False, **kwargs):
+        if n_components != 2:
+            raise NotImplementedError("[TorchDR-B200] the step kernels are specialised for n_components=2.")
+        if "learning_rate" in kwargs:  # NE base.py:170-171
+            lr = kwargs.pop("learning_rate")
+        if "early_exaggeration" in kwargs:
+            early_exaggeration_coeff = kwargs.pop("early_exaggeration")
+        self.n_components = n_components
+        self.lr = lr
+        self.optimizer = optimizer
+        self.optimizer_kwargs = optimizer_kwargs
+        self.scheduler = scheduler
+        self.min_grad_norm = min_grad_norm
+        self.max_iter = max_iter
+        self.init = init
+        self.init_scaling = init_scaling
+        self.device = device if device is not None else "auto"
+        self.backend = backend
+        self.verbose = verbose
+        self.random_state = random_state
+        self.early_exaggeration_iter = early_exaggeration_iter or 0  # NE base.py:160-162
+        self.early_exaggeration_coeff = 1 if early_exaggeration_coeff is None else early_exaggeration_coeff
+        self.repulsion_strength = repulsion_strength
+        self.check_interval = check_interval
+        self.compile = compile
+        self.process_duplicates = process_duplicates
+        self.precise = precise  # fp64 transcendental evaluation in the step kernel (parity runs)
+        # NE base.py:175-182 — LinearLR "auto" goes from 1 to 0 over max_iter
+        if scheduler == "LinearLR" and scheduler_kwargs == "auto":
+            scheduler_kwargs = {"start_factor": torch.tensor(1.0), "end_factor": torch.tensor(0), "total_iters": max_iter}
+        self.scheduler_kwargs = scheduler_kwargs
+        self.logger = logging.getLogger(f"torchdr_b200.{self.__class__.__name__}")
+        if verbose:
+            self.logger.setLevel(logging.INFO)
+        if random_state is not None:  # base.py:75-79, utils/utils.py:51-97
+            seed = int(random_state)
+            random.seed(seed)
+            np.random.seed(seed)
+            torch.manual_seed(seed)
+            self._actual_seed = seed
+        self._setup_distributed(distributed)
+        self.embedding_ = None
+        self.is_fitted_ = False
+        self.n_iter_ = torch.tensor(-1, dtype=torch.long)
+
+    # ---- distributed (NE base.py:354-383) -------------------------------------------------
+    def _setup_distributed(self, distributed):
+        self.distributed = is_distributed() if distributed == "auto" else bool(distributed)
+        if self.distributed:
+            if not is_distributed():
+                raise RuntimeError(
+                    "[TorchDR] distributed=True requires launching with torchrun. "
+                    "Example: torchrun --nproc_per_node=4 your_script.py"
+                )
+            self.rank, self.world_size = dist.get_rank(), dist.get_world_size()
+            self.is_multi_gpu = self.world_size > 1
+            if self.device == "cpu":
+                raise ValueError("[TorchDR] Distributed mode requires GPU (device cannot be 'cpu')")
+            local_rank = int(os.environ.get("LOCAL_RANK", 0))
+            torch.cuda.set_device(local_rank)
+            self.device = torch.device(f"cuda:{local_rank}")
+        else:
+            self.rank, self.world_size, self.is_multi_gpu = 0, 1, False
+
+    # ---- public API (base.py:85-187) ------------------------------------------------------
+    def fit(self, X, y=None):
+        self.fit_transform(X, y=y)
+        return self
+
+    def fit_transform(self, X, y=None):
+        was_numpy = isinstance(X, np.ndarray)
+        in_device = X.device if isinstance(X, torch.Tensor) else None
+        Xd = _to_device_tensor(X, self.device)
+        if Xd.dtype != torch.float32:
+            Xd = Xd.float()
+        Xd = Xd.contiguous()
+        if not bool(torch.isfinite(Xd).all()):
+            raise ValueError("[TorchDR] ERROR : input contains NaN or infinite values.")
+        if self.process_duplicates:  # base.py:132-146
+            Xu, inverse = torch.unique(Xd, dim=0, return_inverse=True)
+            if Xu.shape[0] < Xd.shape[0]:
+                self.logger.info(f"Detected {Xd.shape[0] - Xu.shape[0]} duplicate samples, performing DR on unique data.")
+                self.embedding_ = self._fit_transform(Xu.contiguous())[inverse]
+            else:
+                self.embedding_ = self._fit_transform(Xd)
+        else:
+            self.embedding_ = self._fit_transform(Xd)
+        self.is_fitted_ = True
+        out = self.embedding_
+        if was_numpy:
+            return out.detach().cpu().numpy()
+        if in_device is not None and in_device != out.device:
+            return out.to(in_device)
+        return out
+
+    def transform(self, X=None):
+        if not self.is_fitted_:
+            raise ValueError("This DRModule instance is not fitted yet. Call 'fit' or 'fit_transform' with some data first.")
+        if X is not None:
+            raise NotImplementedError("Transforming new data is not implemented for this model.")
+        return self.embedding_
+
+    # ---- lifecycle hooks (affinity_matcher.py:475-489) -------------------------------------
+    def on_affinity_computation_start(self):
+        pass
+
+    def on_affinity_computation_end(self):
+        pass
+
+    def on_training_step_start(self):
+        """Subclasses / tests may set ``self.neg_indices_`` (int64 [n_local, n_negatives], already
+        adjusted as in NE base.py:629-636); when left ``None`` negatives are drawn in-kernel."""
+        self.neg_indices_ = None
+
+    def on_training_step_end(self):
+        pass
+
+    # ---- checks ----------------------------------------------------------------------------
+    def _check_n_neighbors(self, n):
+        for name in ("perplexity", "n_neighbors"):  # NE base.py:258-267
+            if hasattr(self, name) and n <= getattr(self, name):
+                raise ValueError(
+                    f"[TorchDR] ERROR : Number of samples is smaller than {name} ({n} <= {getattr(self, name)})."
+                )
+
+    # ---- init (affinity_matcher.py:493-573, NE base.py:410-423) ----------------------------
+    def _init_embedding(self, X):
+        n = X.shape[0]
+        dev = X.device
+        if isinstance(self.init, (torch.Tensor, np.ndarray)):
+            Z = torch.as_tensor(self.init).to(device=dev, dtype=torch.float32)
+        elif self.init in ("normal", "random"):
+            Z = torch.randn((n, self.n_components), device=dev, dtype=torch.float32)
+        elif self.init == "pca":
+            Z = _pca_init(X, self.n_components)
+        else:
+            raise ValueError(f"[TorchDR] ERROR : init {self.init} not supported in {self.__class__.__name__}.")
+        Z = (self.init_scaling * Z / Z[:, 0].std()).contiguous()
+        if self.world_size > 1:
+            dist.broadcast(Z, src=0)
+        return Z
+
+    # ---- optimiser / scheduler: the reference's torch.optim objects on a dummy parameter ----
+    def _set_learning_rate(self):
+        if self.lr == "auto":  # NE base.py:299-310
+            if self.optimizer != "SGD" and self.verbose:
+                warnings.warn("[TorchDR] WARNING : when 'auto' is used for the learning rate, the optimizer should be 'SGD'.")
+            self.lr_ = max(self.n_samples_in_ / self.early_exaggeration_coeff_ / 4, 50)
+        else:
+            self.lr_ = self.lr
+
+    def _configure_optimizer(self):
+        if self.optimizer != "SGD":
+            raise NotImplementedError("[TorchDR-B200] only optimizer='SGD' is implemented by the update kernels.")
+        if self.optimizer_kwargs == "auto":  # NE base.py:331-338
+            kw = {"momentum": 0.5} if self.early_exaggeration_coeff_ > 1 else {"momentum": 0.8}
+        else:
+            kw = self.optimizer_kwargs or {}
+        extra = set(kw) - {"momentum"}
+        if extra:
+            raise NotImplementedError(f"[TorchDR-B200] SGD options {sorted(extra)} are not implemented.")
+        self.optimizer_ = torch.optim.SGD(self.params_, lr=self.lr_, **kw)  # NE base.py:343
+        return self.optimizer_
+
+    def _configure_scheduler(self):
+        if self.early_exaggeration_coeff_ > 1:  # NE base.py:345-350
+            n_iter = min(self.early_exaggeration_iter, self.max_iter)
+        else:
+            n_iter = self.max_iter - self.early_exaggeration_iter
+        del n_iter  # affinity_matcher.py:620-657 never forwards it to the scheduler class
+        if self.scheduler is None:
+            self.scheduler_ = None
+        elif isinstance(self.scheduler, str):
+            cls = getattr(torch.optim.lr_scheduler, self.scheduler, None)
+            if cls is None:
+                raise ValueError(f"[TorchDR] ERROR: Scheduler '{self.scheduler}' not found in torch.optim.lr_scheduler.")
+            self.scheduler_ = cls(self.optimizer_, **(self.scheduler_kwargs or {}))
+        else:
+            self.scheduler_ = self.scheduler(self.optimizer_, **(self.scheduler_kwargs or {}))
+        return self.scheduler_
+
+    def _hyper(self):
+        g = self.optimizer_.param_groups[0]
+        return float(g["lr"]), float(g.get("momentum", 0.0))
+
+    def _advance_schedule(self):
+        self.optimizer_.step()  # dummy parameter has no grad: keeps torch's step-order bookkeeping quiet
+        if self.scheduler_ is not None:
+            self.scheduler_.step()
+
+    # ---- main driver (affinity_matcher.py:201-352) -----------------------------------------
+    def _fit_transform(self, X):
+        n = X.shape[0]
+        self._check_n_neighbors(n)
+        self.early_exaggeration_coeff_ = self.early_exaggeration_coeff  # NE base.py:276
+        self.n_samples_in_, self.n_features_in_ = X.shape
+        self.device_ = X.device
+        _lib.require_device(X.device)
+        bounds = all_bounds(n, self.world_size)
+        self._bounds = bounds
+        self.chunk_start_, self.chunk_end_ = bounds[self.rank]
+
+        self.on_affinity_computation_start()
+        if self.verbose:
+            self.logger.info(f"----- Computing the input affinity matrix with {self.affinity_in.__class__.__name__} -----")
+        self._compute_affinity(X)
+        self.chunk_indices_ = torch.arange(self.chunk_start_, self.chunk_end_, device=X.device)  # NE base.py:406-408
+        self.on_affinity_computation_end()
+
+        if self.verbose:
+            self.logger.info("----- Optimizing the embedding -----")
+        Z = self._init_embedding(X)
+        self._dummy = torch.nn.Parameter(torch.zeros(1))
+        self.params_ = [{"params": [self._dummy]}]  # ONE dict reused by every rebuild (affinity_matcher.py:588-590)
+        self._set_learning_rate()
+        self._configure_optimizer()
+        self._configure_scheduler()
+        del X
+
+        dev = Z.device
+        self._gnorm = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._nan = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.embedding_ = Z
+        self._loop()
+        self.n_iter_ = torch.tensor(self._last_step, dtype=torch.long)
+        self.clear_memory()
+        return self.embedding_
+
+    def _check_nan(self, step):
+        if int(self._nan.item()):
+            raise ValueError(f"[TorchDR] ERROR AffinityMatcher : NaNs in the embeddings at iter {step}.")
+
+    def _converged(self, step, grad_norm):
+        if self.verbose:
+            lr, _ = self._hyper()
+            self.logger.info(f"[{step}/{self.max_iter}] Grad norm: {grad_norm:.2e} | LR: {lr:.2e}")
+        if grad_norm < self.min_grad_norm:  # affinity_matcher.py:343-349
+            if self.verbose:
+                self.logger.info(f"Convergence reached at iter {step} with grad norm: {grad_norm:.2e}.")
+            return True
+        return False
+
+    def clear_memory(self):
+        for name in ("_gnorm", "_nan", "optimizer_", "scheduler_", "params_", "_dummy", "neg_indices_", "_graph",
+                     "affinity_in_", "NN_indices_", "chunk_indices_", "_mom", "_grad"):
+            if hasattr(self, name):
+                delattr(self, name)
+        if hasattr(self.affinity_in, "clear_memory"):
+            self.affinity_in.clear_memory()
+
+    # ---- autograd-mode loop shared by LargeVis and TSNE (gradient kernel + momentum SGD) ----
+    def _loop(self):
+        Z = self.embedding_
+        n = Z.shape[0]
+        self._grad = torch.zeros_like(Z)
+        self._mom = torch.zeros_like(Z)
+        first = True
+        self._last_step = -1
+        for step in range(self.max_iter):
+            self.n_iter_ = torch.tensor(step, dtype=torch.long)
+            self._last_step = step
+            self.on_training_step_start()
+            check = step % self.check_interval == 0
+            self._grad.zero_()
+            self._compute_gradient(Z, step)
+            if self.world_size > 1:  # affinity_matcher.py:424-425
+                dist.all_reduce(self._grad, op=dist.ReduceOp.SUM)
+            lr, mom = self._hyper()
+            if check:
+                self._gnorm.zero_()
+            ops.sgd_momentum(Z, self._mom, self._grad, lr, mom, first or mom == 0.0,
+                             gnorm_sq=self._gnorm if check else None, nan_flag=self._nan)
+            first = False
+            self._advance_schedule()
+            # NE base.py:282-295 — end of early exaggeration: rebuild optimiser (+ scheduler)
+            if self.early_exaggeration_coeff_ > 1 and step == self.early_exaggeration_iter:
+                self.early_exaggeration_coeff_ = 1
+                self._set_learning_rate()
+                self._configure_optimizer()
+                self._configure_scheduler()
+                first = True  # fresh optimiser state: momentum buffer restarts
+            self.on_training_step_end()
+            if check:
+                self._check_nan(step)
+                if self._converged(step, float(self._gnorm.item()) ** 0.5):
+                    break
+        self._check_nan(self._last_step)
+
+
+def _pca_init(X, q):
+    """PCA scores for ``init="pca"`` via covariance + eigh on the device (one-off; torch library
+    calls: a d x d GEMM and a d x d eigh).  The reference uses a full SVD
+    (spectral_embedding/pca.py:171-178); both give the top-q principal scores up to sign, and the
+    sign convention below follows svd_flip(u_based_decision) of utils/utils.py:264-301."""
+    mean = X.mean(0, keepdim=True)
+    Xc = X - mean
+    cov = (Xc.T @ Xc).double()
+    w, V = torch.linalg.eigh(cov)
+    comp = V[:, -q:].flip(1).float()  # [d, q], descending eigenvalue
+    scores = Xc @ comp
+    amax = scores.abs().argmax(0)
+    signs = torch.sign(scores[amax, torch.arange(q, device=X.device)])
+    signs[signs == 0] = 1
+    return scores * signs
+
+
+class UMAP(_NeighborEmbeddingB200):
+    """``torchdr/neighbor_embedding/umap.py:39-292``."""
+
+    _use_closed_form_gradients = True
+
+    def __init__(self, n_neighbors=30, n_components=2, min_dist=0.1, spread=1.0, a=None, b=None, lr=1e0,
+                 optimizer="SGD", optimizer_kwargs=None, scheduler="LinearLR", scheduler_kwargs="auto", init="pca",
+                 init_scaling=1e-4, min_grad_norm=1e-7, max_iter=1000, device="auto", backend=None, verbose=False,
+                 random_state=None, max_iter_affinity=100, metric="sqeuclidean", negative_sample_rate=5,
+                 check_interval=50, discard_NNs=False, compile=False, distributed="auto", **kwargs):
+        self.n_neighbors = n_neighbors
+        self.min_dist = min_dist
+        self.spread = spread
+        self.metric = metric
+        self.max_iter_affinity = max_iter_affinity
+        self.negative_sample_rate = negative_sample_rate
+        self.sparsity = True
+        self._eps = 1e-3
+        if a is None or b is None:
+            a, b = find_ab_params(spread, min_dist)
+        self._a, self._b = a, b
+        self.n_negatives = int(negative_sample_rate * n_neighbors)  # umap.py:177
+        if discard_NNs:
+            raise NotImplementedError("[TorchDR-B200] discard_NNs=True is not implemented in the step kernel.")
+        self.discard_NNs = discard_NNs
+        super().__init__(n_components=n_components, lr=lr, optimizer=optimizer, optimizer_kwargs=optimizer_kwargs,
+                         scheduler=scheduler, scheduler_kwargs=scheduler_kwargs, min_grad_norm=min_grad_norm,
+                         max_iter=max_iter, init=init, init_scaling=init_scaling, device=device, backend=backend,
+                         verbose=verbose, random_state=random_state, check_interval=check_interval, compile=compile,
+                         distributed=distributed, **kwargs)
+        self.affinity_in = UMAPAffinity(n_neighbors=n_neighbors, metric=metric, max_iter=max_iter_affinity,
+                                        device=self.device, backend=backend, verbose=verbose, sparsity=True,
+                                        compile=compile, distributed=self.distributed)
+
+    def _compute_affinity(self, X):
+        rowptr, col, val = self.affinity_in.compute_csr(X)
+        # umap.py:215-234 — threshold A_max/max_iter, epochs_per_sample, epoch_of_next_sample
+        a_max = ops.max_value(val)
+        if self.world_size > 1:
+            dist.all_reduce(a_max, op=dist.ReduceOp.MAX)
+        a_max = float(a_max.item())
+        eps, _ = ops.umap_schedule(val, a_max, self.max_iter)
+        if self.verbose:
+            kept = float((eps < float("inf")).float().mean().item()) * 100
+            self.logger.info(f"Keeping {kept:.1f}% of affinity edges.")
+        self._graph_full = (rowptr, col, val, eps)
+        self._graph = ops.umap_compact(rowptr, col, eps)  # (rowptr, col, eps, eons) of live edges
+
+    def clear_memory(self):
+        if hasattr(self, "_graph_full"):
+            del self._graph_full
+        super().clear_memory()
+
+    def _loop(self):
+        rowptr, col, eps, eons = self._graph
+        n = self.n_samples_in_
+        s, e = self.chunk_start_, self.chunk_end_
+        Za = self.embedding_
+        Zb = Za.clone()
+        seed = int(self._actual_seed) if self.random_state is not None else int(torch.initial_seed() % (2**63))
+        lam, rep = float(self.early_exaggeration_coeff_), float(self.repulsion_strength)
+        mom = self._hyper()[1]
+        if mom != 0.0:
+            raise NotImplementedError("[TorchDR-B200] UMAP step kernel implements plain SGD (umap.py:139).")
+        self._last_step = -1
+        step = 0
+        stop = False
+        while step < self.max_iter and not stop:
+            # batch = steps up to (and including) the next one with n_iter % check_interval == 0
+            nxt_check = step if step % self.check_interval == 0 else (step // self.check_interval + 1) * self.check_interval
+            last = min(nxt_check, self.max_iter - 1)
+            hooks_per_step = type(self).on_training_step_start is not UMAP.on_training_step_start or \
+                type(self).on_training_step_end is not _NeighborEmbeddingB200.on_training_step_end
+            if self.world_size > 1 or hooks_per_step:
+                for t in range(step, last + 1):
+                    self.n_iter_ = torch.tensor(t, dtype=torch.long)
+                    self.on_training_step_start()
+                    lr = self._hyper()[0]
+                    want = t == last and t % self.check_interval == 0
+                    if want:
+                        self._gnorm.zero_()
+                    neg = getattr(self, "neg_indices_", None)
+                    ops.umap_step(Za, Zb, s, e - s, rowptr, col, eps, eons, t, self._a, self._b, lr,
+                                  neg=neg, n_neg=self.n_negatives, rate=self.negative_sample_rate, seed=seed, lam=lam,
+                                  repulsion=rep, precise=self.precise, gnorm_sq=self._gnorm if want else None,
+                                  nan_flag=self._nan)
+                    if self.world_size > 1:
+                        all_gather_rows(Zb, self._bounds, self.rank)
+                        if want:
+                            dist.all_reduce(self._gnorm, op=dist.ReduceOp.SUM)
+                    Za, Zb = Zb, Za
+                    self.embedding_ = Za
+                    self._advance_schedule()
+                    self.on_training_step_end()
+            else:
+                lrs = []
+                for t in range(step, last + 1):
+                    lrs.append(self._hyper()[0])
+                    self._advance_schedule()
+                want = last % self.check_interval == 0
+                if want:
+                    self._gnorm.zero_()
+                res = ops.umap_run(Za, Zb, rowptr, col, eps, eons, step, lrs, self._a, self._b,
+                                   n_neg=self.n_negatives, rate=self.negative_sample_rate, seed=seed, lam=lam,
+                                   repulsion=rep, precise=self.precise, gnorm_sq=self._gnorm if want else None,
+                                   nan_flag=self._nan)
+                if res is not Za:
+                    Za, Zb = Zb, Za
+                self.embedding_ = Za
+            self._last_step = last
+            step = last + 1
+            self._check_nan(last)
+            if last % self.check_interval == 0:
+                stop = self._converged(last, float(self._gnorm.item()) ** 0.5)
+        self.embedding_ = Za
+
+
+class _EntropicInputMixin:
+    def _compute_affinity(self, X):
+        P, idx = self.affinity_in(X, log=False, return_indices=True)
+        self.affinity_in_ = P.contiguous()
+        self.NN_indices_ = idx.contiguous()
+
+
+class LargeVis(_EntropicInputMixin, _NeighborEmbeddingB200):
+    """``torchdr/neighbor_embedding/largevis.py:21-201``."""
+
+    def __init__(self, perplexity=30, n_components=2, lr="auto", optimizer="SGD", optimizer_kwargs="auto",
+                 scheduler="LinearLR", scheduler_kwargs=None, init="pca", init_scaling=1e-4, min_grad_norm=1e-7,
+                 max_iter=1000, device="auto", backend=None, verbose=False, random_state=None, max_iter_affinity=100,
+                 metric="sqeuclidean", n_negatives=5, sparsity=True, early_exaggeration_coeff=None,
+                 early_exaggeration_iter=None, check_interval=50, discard_NNs=False, compile=False,
+                 distributed="auto", **kwargs):
+        self.metric = metric
+        self.perplexity = perplexity
+        self.max_iter_affinity = max_iter_affinity
+        self.sparsity = sparsity
+        self.n_negatives = n_negatives
+        if discard_NNs:
+            raise NotImplementedError("[TorchDR-B200] discard_NNs=True is not implemented in the step kernel.")
+        self.discard_NNs = discard_NNs
+        super().__init__(n_components=n_components, lr=lr, optimizer=optimizer, optimizer_kwargs=optimizer_kwargs,
+                         scheduler=scheduler, scheduler_kwargs=scheduler_kwargs, min_grad_norm=min_grad_norm,
+                         max_iter=max_iter, init=init, init_scaling=init_scaling, device=device, backend=backend,
+                         verbose=verbose, random_state=random_state,
+                         early_exaggeration_coeff=early_exaggeration_coeff,
+                         early_exaggeration_iter=early_exaggeration_iter, check_interval=check_interval,
+                         compile=compile, distributed=distributed, **kwargs)
+        self.affinity_in = EntropicAffinity(perplexity=perplexity, metric=metric, max_iter=max_iter_affinity,
+                                            device=self.device, backend=backend, verbose=verbose, sparsity=sparsity,
+                                            distributed=self.distributed)
+
+    def _compute_gradient(self, Z, step):
+        s, e = self.chunk_start_, self.chunk_end_
+        seed = int(self._actual_seed) if self.random_state is not None else 0
+        ops.largevis_grad(Z, s, e - s, self.affinity_in_, self.NN_indices_, self._grad, step,
+                          neg=getattr(self, "neg_indices_", None), n_neg=self.n_negatives, seed=seed,
+                          lam=float(self.early_exaggeration_coeff_), repulsion=float(self.repulsion_strength))
+
+
+class TSNE(_EntropicInputMixin, _NeighborEmbeddingB200):
+    """``torchdr/neighbor_embedding/tsne.py:22-180``."""
+
+    def __init__(self, perplexity=30, n_components=2, lr="auto", optimizer="SGD", optimizer_kwargs="auto",
+                 scheduler=None, scheduler_kwargs=None, init="pca", init_scaling=1e-4, min_grad_norm=1e-7,
+                 max_iter=2000, device="auto", backend=None, verbose=False, random_state=None,
+                 early_exaggeration_coeff=12.0, early_exaggeration_iter=250, max_iter_affinity=100,
+                 metric="sqeuclidean", sparsity=True, check_interval=50, compile=False, distributed="auto", **kwargs):
+        self.metric = metric
+        self.perplexity = perplexity
+        self.max_iter_affinity = max_iter_affinity
+        self.sparsity = sparsity
+        super().__init__(n_components=n_components, lr=lr, optimizer=optimizer, optimizer_kwargs=optimizer_kwargs,
+                         scheduler=scheduler, scheduler_kwargs=scheduler_kwargs, min_grad_norm=min_grad_norm,
+                         max_iter=max_iter, init=init, init_scaling=init_scaling, device=device, backend=backend,
+                         verbose=verbose, random_state=random_state,
+                         early_exaggeration_coeff=early_exaggeration_coeff,
+                         early_exaggeration_iter=early_exaggeration_iter, check_interval=check_interval,
+                         compile=compile, distributed=distributed, **kwargs)
+        self.affinity_in = EntropicAffinity(perplexity=perplexity, metric=metric, max_iter=max_iter_affinity,
+                                            device=self.device, backend=backend, verbose=verbose, sparsity=sparsity,
+                                            distributed=self.distributed)
+
+    def _compute_gradient(self, Z, step):
+        s, e = self.chunk_start_, self.chunk_end_
+        if not hasattr(self, "_tsne_ws"):
+            self._tsne_ws = ops.tsne_workspace(e - s, Z.device)
+        lam = float(self.early_exaggeration_coeff_)
+        ops.tsne_grad(Z, s, e - s, self.affinity_in_, self.NN_indices_, lam, 0, self._grad, self._tsne_ws)
+        if self.world_size > 1:
+            # the reference has every rank compute the whole N x N term and divide by W (tsne.py:172-180);
+            # here each rank owns a row range of the double sum and the scalar normaliser is all-reduced
+            S = self._tsne_ws[:8].view(torch.float64)
+            dist.all_reduce(S, op=dist.ReduceOp.SUM)
+        ops.tsne_grad(Z, s, e - s, self.affinity_in_, self.NN_indices_, lam, 1, self._grad, self._tsne_ws)
+
+    def clear_memory(self):
+        if hasattr(self, "_tsne_ws"):
+            del self._tsne_ws
+        super().clear_memory()

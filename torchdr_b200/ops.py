@@ -1,0 +1,244 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point of include/tdrb200.h).
+
+These take and return CUDA tensors; shapes/dtypes are validated here so that the C layer
+only sees raw pointers.  No function here computes on the CPU.
+"""
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream, workspace
+
+
+def _dev_f32(x, name):
+    if not isinstance(x, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    _lib.require_device(x.device)
+    if x.dtype != torch.float32:
+        raise TypeError(f"[TorchDR-B200] {name} must be float32 (the path computes in fp32), got {x.dtype}")
+    return x.contiguous()
+
+
+def knn(Xq, Xdb, k, q_row0=0, exclude_self=True, metric="sqeuclidean"):
+    """Exact kNN of query rows against the database -> (dist[nq,k] f32, idx[nq,k] i32)."""
+    Xq, Xdb = _dev_f32(Xq, "Xq"), _dev_f32(Xdb, "Xdb")
+    lib = _lib.load()
+    nq, d = Xq.shape
+    ndb = Xdb.shape[0]
+    ws = workspace(lib.tdr_knn_workspace_bytes(nq, ndb, d, k), Xq.device)
+    dist = torch.empty((nq, k), dtype=torch.float32, device=Xq.device)
+    idx = torch.empty((nq, k), dtype=torch.int32, device=Xq.device)
+    with torch.cuda.device(Xq.device):
+        check(lib.tdr_knn_f32(ptr(Xq), nq, q_row0, ptr(Xdb), ndb, d, k, int(exclude_self), _lib.METRIC_IDS[metric],
+                              ptr(dist), ptr(idx), ptr(ws), ws.numel(), stream()), "tdr_knn_f32")
+    return dist, idx
+
+
+def knn_umap_fused(Xq, Xdb, k, q_row0=0, exclude_self=True, max_iter=100, want_dist=True):
+    """Fused kNN + UMAP rho/sigma search -> (dist|None, idx, P, rho, sigma)."""
+    Xq, Xdb = _dev_f32(Xq, "Xq"), _dev_f32(Xdb, "Xdb")
+    lib = _lib.load()
+    nq, d = Xq.shape
+    ndb = Xdb.shape[0]
+    dev = Xq.device
+    ws = workspace(lib.tdr_knn_workspace_bytes(nq, ndb, d, k), dev)
+    dist = torch.empty((nq, k), dtype=torch.float32, device=dev) if want_dist else None
+    idx = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    Pm = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    rho = torch.empty((nq,), dtype=torch.float32, device=dev)
+    sigma = torch.empty((nq,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.tdr_knn_umap_fused_f32(ptr(Xq), nq, q_row0, ptr(Xdb), ndb, d, k, int(exclude_self), max_iter,
+                                         ptr(dist), ptr(idx), ptr(Pm), ptr(rho), ptr(sigma), ptr(ws), ws.numel(),
+                                         stream()), "tdr_knn_umap_fused_f32")
+    return dist, idx, Pm, rho, sigma
+
+
+def pairwise_full(X, Y=None, metric="sqeuclidean", exclude_diag=False):
+    X = _dev_f32(X, "X")
+    Y = X if Y is None or Y is X else _dev_f32(Y, "Y")
+    lib = _lib.load()
+    n, d = X.shape
+    m = Y.shape[0]
+    ws = workspace(lib.tdr_knn_workspace_bytes(n, m, d, 1), X.device)
+    C = torch.empty((n, m), dtype=torch.float32, device=X.device)
+    with torch.cuda.device(X.device):
+        check(lib.tdr_pairwise_full_f32(ptr(X), n, ptr(Y), m, d, _lib.METRIC_IDS[metric], int(exclude_diag), ptr(C),
+                                        ptr(ws), ws.numel(), stream()), "tdr_pairwise_full_f32")
+    return C
+
+
+def umap_affinity_rows(C, max_iter=100):
+    C = _dev_f32(C, "C")
+    n, k = C.shape
+    Pm = torch.empty_like(C)
+    rho = torch.empty((n,), dtype=torch.float32, device=C.device)
+    sigma = torch.empty((n,), dtype=torch.float32, device=C.device)
+    with torch.cuda.device(C.device):
+        check(_lib.load().tdr_umap_affinity_f32(ptr(C), n, k, max_iter, ptr(Pm), ptr(rho), ptr(sigma), stream()),
+              "tdr_umap_affinity_f32")
+    return Pm, rho, sigma
+
+
+def entropic_affinity_rows(C, target_entropy, log_n_total, bounds=None, max_iter=100):
+    """bounds = (b_num, b_den, b_lr, b_logp1) fp32 scalars or None (multi-GPU rule)."""
+    C = _dev_f32(C, "C")
+    n, k = C.shape
+    logP = torch.empty_like(C)
+    eps = torch.empty((n,), dtype=torch.float32, device=C.device)
+    log_norm = torch.empty((n,), dtype=torch.float32, device=C.device)
+    b = bounds if bounds is not None else (0.0, 0.0, 0.0, 0.0)
+    with torch.cuda.device(C.device):
+        check(_lib.load().tdr_entropic_affinity_f32(ptr(C), n, k, float(target_entropy), float(log_n_total),
+                                                    int(bounds is not None), float(b[0]), float(b[1]), float(b[2]),
+                                                    float(b[3]), max_iter, ptr(logP), ptr(eps), ptr(log_norm),
+                                                    stream()), "tdr_entropic_affinity_f32")
+    return logP, eps, log_norm
+
+
+def symmetrize_csr(Pm, idx, row0, n_total, ext=None, transpose_local=True):
+    """Q = P + P^T - P o P^T for the local rows -> (rowptr i64[n+1], col i32[nnz], val f32[nnz])."""
+    Pm = _dev_f32(Pm, "P")
+    idx = idx.contiguous()
+    assert idx.dtype == torch.int32 and idx.shape == Pm.shape
+    lib = _lib.load()
+    dev = Pm.device
+    n_local, k = Pm.shape
+    if ext is not None and ext[0].numel() > 0:
+        er, ec, ev = (t.contiguous() for t in ext)
+        assert er.dtype == torch.int64 and ec.dtype == torch.int32 and ev.dtype == torch.float32
+        n_ext = er.numel()
+    else:
+        er = ec = ev = None
+        n_ext = 0
+    cap = 2 * n_local * k + n_ext
+    ws = workspace(lib.tdr_symmetrize_workspace_bytes(n_local, k, n_ext), dev)
+    rowptr = torch.empty((n_local + 1,), dtype=torch.int64, device=dev)
+    col = torch.empty((cap,), dtype=torch.int32, device=dev)
+    val = torch.empty((cap,), dtype=torch.float32, device=dev)
+    nnz = torch.zeros((1,), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.tdr_symmetrize_csr_f32(ptr(Pm), ptr(idx), n_local, k, row0, n_total, ptr(er), ptr(ec), ptr(ev),
+                                         n_ext, int(transpose_local), ptr(rowptr), ptr(col), ptr(val), ptr(nnz),
+                                         ptr(ws), ws.numel(), stream()), "tdr_symmetrize_csr_f32")
+    m = int(nnz.item())
+    return rowptr, col[:m].clone(), val[:m].clone()
+
+
+def symmetrize_export(Pm, idx, row0, n_total, world, rank):
+    """Transposed edges owned by other ranks, packed by destination -> (counts[world], row, col, val)."""
+    Pm = _dev_f32(Pm, "P")
+    idx = idx.contiguous()
+    dev = Pm.device
+    n_local, k = Pm.shape
+    counts = torch.zeros((2 * world,), dtype=torch.int64, device=dev)
+    row = torch.empty((n_local * k,), dtype=torch.int64, device=dev)
+    col = torch.empty((n_local * k,), dtype=torch.int32, device=dev)
+    val = torch.empty((n_local * k,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().tdr_symmetrize_export_f32(ptr(Pm), ptr(idx), n_local, k, row0, n_total, world, rank,
+                                                    ptr(counts), ptr(row), ptr(col), ptr(val), stream()),
+              "tdr_symmetrize_export_f32")
+    c = counts[:world].cpu()
+    tot = int(c.sum())
+    return c, row[:tot], col[:tot], val[:tot]
+
+
+def csr_to_ell(rowptr, col, val, pad_val=0.0):
+    n_local = rowptr.numel() - 1
+    width = int((rowptr[1:] - rowptr[:-1]).max().item()) if n_local > 0 else 0
+    ev = torch.empty((n_local, width), dtype=torch.float32, device=val.device)
+    ei = torch.empty((n_local, width), dtype=torch.int64, device=val.device)
+    with torch.cuda.device(val.device):
+        check(_lib.load().tdr_csr_to_ell_f32(ptr(rowptr), ptr(col), ptr(val), n_local, width, float(pad_val), ptr(ev),
+                                             ptr(ei), stream()), "tdr_csr_to_ell_f32")
+    return ev, ei
+
+
+def max_value(val):
+    out = torch.zeros((1,), dtype=torch.float32, device=val.device)
+    with torch.cuda.device(val.device):
+        check(_lib.load().tdr_max_f32(ptr(val), val.numel(), ptr(out), stream()), "tdr_max_f32")
+    return out
+
+
+def umap_schedule(val, a_max, max_iter):
+    eps = torch.empty_like(val)
+    eons = torch.empty_like(val)
+    with torch.cuda.device(val.device):
+        check(_lib.load().tdr_umap_schedule_f32(ptr(val), val.numel(), float(a_max), int(max_iter), ptr(eps),
+                                                ptr(eons), stream()), "tdr_umap_schedule_f32")
+    return eps, eons
+
+
+def umap_compact(rowptr, col, eps):
+    lib = _lib.load()
+    dev = eps.device
+    n_local = rowptr.numel() - 1
+    nnz = eps.numel()
+    ws = workspace(lib.tdr_compact_workspace_bytes(n_local, nnz), dev)
+    orp = torch.empty_like(rowptr)
+    ocol = torch.empty_like(col)
+    oeps = torch.empty_like(eps)
+    oeons = torch.empty_like(eps)
+    cnt = torch.zeros((1,), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.tdr_umap_compact_f32(ptr(rowptr), ptr(col), ptr(eps), n_local, nnz, ptr(orp), ptr(ocol), ptr(oeps),
+                                       ptr(oeons), ptr(cnt), ptr(ws), ws.numel(), stream()), "tdr_umap_compact_f32")
+    m = int(cnt.item())
+    return orp, ocol[:m].clone(), oeps[:m].clone(), oeons[:m].clone()
+
+
+def umap_step(Z_in, Z_out, row0, n_local, rowptr, col, eps, eons, n_iter, a, b, lr, neg=None, n_neg=75, rate=5,
+              seed=0, lam=1.0, repulsion=1.0, precise=False, grad_out=None, gnorm_sq=None, nan_flag=None):
+    n_total = Z_in.shape[0]
+    if neg is not None:
+        assert neg.dtype == torch.int64 and neg.is_contiguous() and neg.shape == (n_local, n_neg)
+    with torch.cuda.device(Z_in.device):
+        check(_lib.load().tdr_umap_step_f32(ptr(Z_in), ptr(Z_out), n_total, row0, n_local, ptr(rowptr), ptr(col),
+                                            ptr(eps), ptr(eons), ptr(neg), n_neg, rate, seed, n_iter, float(a),
+                                            float(b), float(lam), float(repulsion), float(lr), int(precise),
+                                            ptr(grad_out), ptr(gnorm_sq), ptr(nan_flag), stream()),
+              "tdr_umap_step_f32")
+
+
+def umap_run(Z_a, Z_b, rowptr, col, eps, eons, n_iter0, lrs, a, b, n_neg=75, rate=5, seed=0, lam=1.0,
+             repulsion=1.0, precise=False, gnorm_sq=None, nan_flag=None):
+    """len(lrs) iterations on one GPU; returns the tensor holding the result."""
+    lrs = np.ascontiguousarray(lrs, dtype=np.float32)
+    n = len(lrs)
+    with torch.cuda.device(Z_a.device):
+        check(_lib.load().tdr_umap_run_f32(ptr(Z_a), ptr(Z_b), Z_a.shape[0], ptr(rowptr), ptr(col), ptr(eps),
+                                           ptr(eons), n_neg, rate, seed, n_iter0, n,
+                                           lrs.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), float(a), float(b),
+                                           float(lam), float(repulsion), int(precise), ptr(gnorm_sq), ptr(nan_flag),
+                                           stream()), "tdr_umap_run_f32")
+    return Z_a if n % 2 == 0 else Z_b
+
+
+def largevis_grad(Z, row0, n_local, Pm, idx, grad, n_iter, neg=None, n_neg=5, seed=0, lam=1.0, repulsion=1.0):
+    with torch.cuda.device(Z.device):
+        check(_lib.load().tdr_largevis_grad_f32(ptr(Z), Z.shape[0], row0, n_local, ptr(Pm), ptr(idx), Pm.shape[1],
+                                                ptr(neg), n_neg, seed, n_iter, float(lam), float(repulsion),
+                                                ptr(grad), stream()), "tdr_largevis_grad_f32")
+
+
+def tsne_workspace(n_local, device):
+    return workspace(_lib.load().tdr_tsne_workspace_bytes(n_local), device)
+
+
+def tsne_grad(Z, row0, n_local, Pm, idx, lam, phase, grad, ws):
+    k = Pm.shape[1] if Pm is not None else 0
+    with torch.cuda.device(Z.device):
+        check(_lib.load().tdr_tsne_grad_f32(ptr(Z), Z.shape[0], row0, n_local, ptr(Pm), ptr(idx), k, float(lam),
+                                            int(phase), ptr(grad), ptr(ws), ws.numel(), stream()), "tdr_tsne_grad_f32")
+
+
+def sgd_momentum(Z, buf, grad, lr, momentum, first, gnorm_sq=None, nan_flag=None):
+    with torch.cuda.device(Z.device):
+        check(_lib.load().tdr_sgd_momentum_f32(ptr(Z), ptr(buf), ptr(grad), Z.numel(), float(lr), float(momentum),
+                                               int(first), ptr(gnorm_sq), ptr(nan_flag), stream()),
+              "tdr_sgd_momentum_f32")
