@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py — UMAP iters/sec (and the fused kNN+sigma "affinity kernel" throughput) on B200.
+
+Contract (driver): ``python bench.py --gpus N --steps K --warmup W`` (under torchrun for N>1)
+prints ONE JSON line from rank 0.  ``--impl reference`` times the CPU restatement of the
+reference path (oracle/, kind "port") on a bounded sample instead.
+
+Workload (BASELINE.json configs[1]): UMAP n_neighbors=15 on 1 M x 128 synthetic clustered points
+(the reference benchmark's generator, benchmarks/faiss/run_benchmark.py:127-146).  A *step* is
+one UMAP optimisation iteration over all points; the graph (kNN -> sigma/rho -> symmetrise ->
+edge schedule) is built once, untimed, through the same C-ABI calls.  Strong scaling: the point
+set is fixed and rows are sharded across ranks; after every iteration the updated rows are
+all-gathered (NCCL).
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+K_NEIGHBORS = 15
+N_NEG = 75          # umap.py:177: negative_sample_rate * n_neighbors
+MAX_ITER = 500      # iteration budget of the schedule (the reference's UMAP benchmark uses 500)
+E2E_ITERS = 500
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
+
+
+# ----------------------------------------------------------------------------- data
+def clustered(n, d, device, seed=42):
+    """benchmarks/faiss/run_benchmark.py:127-146: min(1000, n//100) Gaussian clusters,
+    centres randn*10, points centre + randn*0.5, cluster blocks contiguous."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    nc = max(1, min(1000, n // 100))
+    centers = torch.randn(nc, d, generator=g, device=device) * 10
+    per = n // nc
+    lab = torch.arange(n, device=device) // per
+    lab.clamp_(max=nc - 1)
+    X = centers[lab] + torch.randn(n, d, generator=g, device=device) * 0.5
+    return X.float().contiguous()
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=10)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle port)
+def cpu_reference(steps, warmup, n_total, d, sample_n=20000, knn_queries=2048, verbose=False):
+    """Reference path restated on CPU (oracle/, torch CPU ops like the reference's backend=None).
+
+    Bounded sample: the full pipeline on `sample_n` points of the same generator; the loop rate is
+    per-iteration over sample_n points and is scaled by sample_n / n_total (the iteration is O(N));
+    the kNN stage is O(N^2 D) and is timed as `knn_queries` query rows against a database of
+    sample_n rows, then scaled by (n_total/knn_queries) * (n_total/sample_n).  Extrapolated
+    figures are labelled as such in `sample`."""
+    import oracle
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    X = clustered(sample_n, d, "cpu")
+    t0 = time.perf_counter()
+    C, I = oracle.knn_chunked(X, K_NEIGHBORS, block=4096)
+    t_knn_sample = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    oracle.knn_chunked(X, K_NEIGHBORS, block=knn_queries, q_start=0, q_end=knn_queries)
+    t_knn_q = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    P, rho, sigma = oracle.umap_affinity_rows(C, K_NEIGHBORS, max_iter=100)
+    V, J = oracle.symmetrize_ell(P, I)
+    per, nxt = oracle.umap_edge_schedule(V, MAX_ITER)
+    t_aff = time.perf_counter() - t0
+    a, b = oracle.find_ab()
+    g = torch.Generator().manual_seed(0)
+    Z = torch.randn(sample_n, 2, generator=g)
+    Z = 1e-4 * Z / Z[:, 0].std()
+    lrs = oracle.linear_lr_sequence(1.0, MAX_ITER, steps + warmup)
+    me = torch.arange(sample_n)
+
+    def one(t, Z, nxt):
+        neg = torch.randint(0, sample_n - 1, (sample_n, N_NEG), generator=g)
+        neg = oracle.adjust_negatives(neg, me)
+        G = oracle.umap_step(Z, J, per, nxt, neg, t, a, b)
+        return Z.add(G, alpha=-float(lrs[t]))
+
+    for t in range(warmup):
+        Z = one(t, Z, nxt)
+    t0 = time.perf_counter()
+    for t in range(warmup, warmup + steps):
+        Z = one(t, Z, nxt)
+    t_loop = time.perf_counter() - t0
+    its_sample = steps / t_loop
+    its_full = its_sample * sample_n / n_total
+    knn_full_s = t_knn_q * (n_total / knn_queries) * (n_total / sample_n)
+    aff_full_s = t_aff * n_total / sample_n
+    e2e_full = E2E_ITERS / (knn_full_s + aff_full_s + E2E_ITERS / its_full)
+    return {
+        "value": its_full, "unit": "iters/s", "cores": cores, "kind": "port",
+        "sample": (f"oracle (torch-CPU restatement of backend=None) on {sample_n}x{d} clustered points: loop "
+                   f"{its_sample:.2f} it/s measured over {steps} iters, scaled x{sample_n}/{n_total} (O(N) per "
+                   f"iteration, extrapolated); kNN {t_knn_sample:.1f}s at {sample_n} rows, {t_knn_q:.2f}s for "
+                   f"{knn_queries} queries -> {knn_full_s:.0f}s extrapolated to {n_total} rows; affinity+graph "
+                   f"{t_aff:.1f}s -> {aff_full_s:.0f}s extrapolated"),
+        "e2e_value": e2e_full, "loop_its_sample": its_sample, "knn_full_s_extrapolated": knn_full_s,
+        "ms_per_step": 1e3 * t_loop / steps * n_total / sample_n,
+    }
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def build_graph(X, rank, world, max_iter):
+    """Untimed setup through the product path: fused kNN + sigma/rho, symmetrise, schedule, compact."""
+    import torch.distributed as dist
+
+    from torchdr_b200 import ops
+    from torchdr_b200.distributed import all_bounds, exchange_edges
+
+    n = X.shape[0]
+    bounds = all_bounds(n, world)
+    s, e = bounds[rank]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    dist_, idx, P, rho, sigma = ops.knn_umap_fused(X[s:e], X, K_NEIGHBORS, q_row0=s, want_dist=False)
+    ev1.record()
+    torch.cuda.synchronize()
+    knn_ms = ev0.elapsed_time(ev1)
+    ext = None
+    if world > 1:
+        counts, er, ec, ev = ops.symmetrize_export(P, idx, s, n, world, rank)
+        ext = exchange_edges(counts, er, ec, ev)
+    rowptr, col, val = ops.symmetrize_csr(P, idx, s, n, ext=ext)
+    a_max = ops.max_value(val)
+    if world > 1:
+        dist.all_reduce(a_max, op=dist.ReduceOp.MAX)
+    eps, _ = ops.umap_schedule(val, float(a_max.item()), max_iter)
+    graph = ops.umap_compact(rowptr, col, eps)
+    return graph, bounds, knn_ms, int(val.numel())
+
+
+def gpu_arm(args):
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from torchdr_b200 import UMAP, _lib, ops
+    from torchdr_b200.distributed import all_gather_rows
+    from torchdr_b200.neighbor_embedding import find_ab_params
+
+    _lib.require_device(dev)
+    n, d, K, W = args.points, args.dim, args.steps, max(args.warmup, 3)
+    X = clustered(n, d, dev)
+    (rowptr, col, eps, eons), bounds, knn_ms, nnz_sym = build_graph(X, rank, world, MAX_ITER)
+    s, e = bounds[rank]
+    a, b = find_ab_params(1.0, 0.1)
+    g = torch.Generator(device=dev).manual_seed(0)
+    Z = torch.randn(n, 2, generator=g, device=dev)
+    Za = (1e-4 * Z / Z[:, 0].std()).contiguous()
+    Zb = Za.clone()
+    # learning rates of the reference schedule (LinearLR 1 -> 0 over MAX_ITER), host-side scalars
+    lr_all = np.asarray([1.0 * (1.0 - t / MAX_ITER) for t in range(W + K)], dtype=np.float32)
+    stats = torch.zeros(2, dtype=torch.int64, device=dev)
+    nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def run(t0, count, Za, Zb, stats_t):
+        if world == 1:
+            res = ops.umap_run(Za, Zb, rowptr, col, eps, eons, t0, lr_all[t0:t0 + count], a, b, n_neg=N_NEG,
+                               seed=1234, nan_flag=nan_flag, stats=stats_t)
+            return (res, Zb if res is Za else Za)
+        for t in range(t0, t0 + count):
+            ops.umap_step(Za, Zb, s, e - s, rowptr, col, eps, eons, t, a, b, float(lr_all[t]), neg=None,
+                          n_neg=N_NEG, seed=1234, nan_flag=nan_flag, stats=stats_t)
+            all_gather_rows(Zb, bounds, rank)
+            Za, Zb = Zb, Za
+        return Za, Zb
+
+    Za, Zb = run(0, W, Za, Zb, None)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        ev0.record()
+        Za, Zb = run(W, K, Za, Zb, stats)
+        ev1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    st = stats.clone().double()
+    nnz_live = torch.tensor([float(col.numel())], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(st, op=dist.ReduceOp.SUM)
+        dist.all_reduce(nnz_live, op=dist.ReduceOp.SUM)
+    assert int(nan_flag.item()) == 0, "NaN in the embedding"
+    assert bool(torch.isfinite(Za).all())
+    total_ms = float(ms.item())
+    ms_per_step = total_ms / K
+    value = 1e3 / ms_per_step
+
+    # ---- roofline of the step kernel (algorithmic bytes) -------------
+    act, negs = float(st[0]) / K, float(st[1]) / K
+    nnz = float(nnz_live.item())
+    alg_bytes = 16.0 * n + 8.0 * (n + world) + 4.0 * nnz + act * (4 + 4 + 8 + 4) + negs * 8.0
+    peak, peak_src = FALLBACK_HBM_GBS, "fallback"
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        peak_src = "measured"
+    except Exception:
+        pass
+    kernel_ms = ms_per_step  # N=1: the timed region contains only the K step-kernel launches
+    achieved = alg_bytes / world / (kernel_ms * 1e-3) / 1e9 if world == 1 else alg_bytes / world / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    roofline = {"bound": "hbm", "kernel": "umap_step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes / world,
+                "note": "per-GPU; at N>1 the per-step time also contains the NCCL all-gather"}
+    aff_bytes = 4.0 * n * d / 1 + n / world * K_NEIGHBORS * 8.0 + 8.0 * n / world
+    affinity = {"kernel": "knn_tile_kernel<FUSED>", "ms": knn_ms, "algorithmic_bytes": aff_bytes,
+                "gbs": aff_bytes / (knn_ms * 1e-3) / 1e9,
+                "tflops_2nnd": 2.0 * (n / world) * n * d / (knn_ms * 1e-3) / 1e12,
+                "note": "compute-bound by construction (SURVEY 8d); fp32 FFMA mainloop"}
+
+    out = None
+    if rank == 0:
+        out = {
+            "metric": "UMAP iters/sec (1 M x 128, n_neighbors=15); affinity-kernel GB/s in `affinity_kernel`",
+            "value": value, "unit": "iters/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"UMAP n_neighbors={K_NEIGHBORS} on {n}x{d} clustered synthetic (BASELINE configs[1])",
+                       "points": n, "dim": d, "n_negatives": N_NEG, "schedule_max_iter": MAX_ITER,
+                       "negatives": "in-kernel Philox4x32-10", "parallelism": f"rows sharded x{world}",
+                       "l2": "per-iteration working set (CSR edge state %.0f MB) exceeds the 126 MB L2; no flush" %
+                             (nnz * 12 / 1e6 / world)},
+            "roofline": roofline, "affinity_kernel": affinity,
+            "gpu_launches": K if world == 1 else K,
+            "clocks": clk.summary(),
+            "graph": {"nnz_symmetrised": nnz_sym, "nnz_live": nnz, "sampled_edges_per_iter": act,
+                      "negatives_per_iter": negs},
+        }
+    del X
+    return out, (rank, world, dev)
+
+
+def e2e_arm(args, dev):
+    """fit_transform through the public estimator on HOST memory: H2D of X, kNN, sigma search, graph,
+    E2E_ITERS iterations, D2H of the embedding — all inside the timed region."""
+    from torchdr_b200 import UMAP
+
+    n, d = args.points, args.dim
+    Xh = clustered(n, d, dev).cpu().pin_memory().numpy()
+    torch.cuda.synchronize()
+    m = UMAP(n_neighbors=K_NEIGHBORS, max_iter=E2E_ITERS, init="normal", random_state=0, process_duplicates=False)
+    m.fit_transform(Xh[:20000])  # warm-up of allocator / library load
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    Z = m.fit_transform(Xh)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    assert Z.shape == (n, 2) and np.isfinite(Z).all()
+    return {"value": E2E_ITERS / dt, "unit": "iters/s", "h2d_bytes_per_step": Xh.nbytes / E2E_ITERS,
+            "d2h_bytes_per_step": Z.nbytes / E2E_ITERS, "seconds": dt, "iters": E2E_ITERS,
+            "note": "UMAP(n_neighbors=15, max_iter=500, init='normal').fit_transform(numpy X): "
+                    "iters / wall time incl. H2D, exact kNN, sigma search, symmetrise, loop, D2H"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--points", type=int, default=1_000_000)
+    ap.add_argument("--dim", type=int, default=128)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = min(args.steps, 20)
+        r = cpu_reference(steps, min(args.warmup, 3), args.points, args.dim)
+        line = {
+            "impl": "reference",
+            "metric": "UMAP iters/sec (1 M x 128, n_neighbors=15); affinity-kernel GB/s in `affinity_kernel`",
+            "value": r["value"], "unit": "iters/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3),
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"UMAP n_neighbors={K_NEIGHBORS} on {args.points}x{args.dim} clustered synthetic "
+                                   "(BASELINE configs[1])", "points": args.points, "dim": args.dim},
+            "cpu_baseline": {"value": r["value"], "unit": "iters/s", "cores": r["cores"], "kind": r["kind"],
+                             "sample": r["sample"]},
+            "e2e": {"value": r["e2e_value"], "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return
+
+    out, (rank, world, dev) = gpu_arm(args)
+    if rank == 0:
+        if not args.no_e2e and world == 1:
+            out["e2e"] = e2e_arm(args, dev)
+        elif not args.no_e2e:
+            out["e2e"] = None
+        if world == 1 and not args.no_cpu:
+            r = cpu_reference(10, 2, args.points, args.dim)
+            out["cpu_baseline"] = {"value": r["value"], "unit": "iters/s", "cores": r["cores"], "kind": r["kind"],
+                                   "sample": r["sample"], "e2e_value": r["e2e_value"]}
+        print(json.dumps(out))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

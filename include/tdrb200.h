@@ -65,6 +65,11 @@ TDR_API int tdr_knn_f32(const float* Xq, int64_t nq, int64_t q_row0,
                 float* out_dist /*[nq,k]*/, int32_t* out_idx /*[nq,k]*/,
                 void* ws, size_t ws_bytes, tdr_stream_t stream);
 
+/* Kernel selection for the two kNN entry points: 0 = auto, 1 = fp32 SIMT kernel,
+ * 2 = tcgen05 tensor-core kernel (fp16 hi/lo split, d <= 128, k <= 32).  Process-wide; meant
+ * for tests and profiling.  The environment variable TDR_KNN_PATH seeds it at load time. */
+TDR_API int tdr_knn_set_path(int path);
+
 /* Full matrix C[n,m] (k=None path, distance/torch.py:81-116).  Y may equal X.
  * Workspace: tdr_knn_workspace_bytes(n, m, d, 1). */
 TDR_API int tdr_pairwise_full_f32(const float* X, int64_t n, const float* Y, int64_t m, int d,
@@ -162,7 +167,8 @@ TDR_API int tdr_umap_compact_f32(const int64_t* rowptr, const int32_t* col, cons
  * precise != 0 evaluates pow in fp64 (parity mode).
  * grad_out (nullable) [n_local,2] receives the gradient; gnorm_sq (nullable,
  * device double) accumulates ||g||^2; nan_flag (nullable, device int) is set
- * if a NaN is written (check_NaNs, affinity_matcher.py:315). */
+ * if a NaN is written (check_NaNs, affinity_matcher.py:315); stats (nullable, device
+ * uint64[2]) accumulates the number of sampled edges and of negatives used. */
 TDR_API int tdr_umap_step_f32(const float* Z_in, float* Z_out, int64_t n_total, int64_t row0, int64_t n_local,
                       const int64_t* rowptr, const int32_t* col,
                       const float* epochs_per_sample, float* epoch_of_next_sample,
@@ -170,7 +176,7 @@ TDR_API int tdr_umap_step_f32(const float* Z_in, float* Z_out, int64_t n_total, 
                       uint64_t seed, int64_t n_iter,
                       double a, double b, float lam, float repulsion, float lr,
                       int precise, float* grad_out, double* gnorm_sq, int* nan_flag,
-                      tdr_stream_t stream);
+                      uint64_t* stats, tdr_stream_t stream);
 
 /* n_steps single-GPU iterations ping-ponging Z_a <-> Z_b (in-kernel negatives);
  * lrs is a HOST array [n_steps].  The result is in Z_a if n_steps is even, else Z_b. */
@@ -180,7 +186,8 @@ TDR_API int tdr_umap_run_f32(float* Z_a, float* Z_b, int64_t n_total,
                      int n_neg, int negative_sample_rate, uint64_t seed, int64_t n_iter0,
                      int n_steps, const float* lrs_host,
                      double a, double b, float lam, float repulsion,
-                     int precise, double* gnorm_sq, int* nan_flag, tdr_stream_t stream);
+                     int precise, double* gnorm_sq, int* nan_flag, uint64_t* stats,
+                     tdr_stream_t stream);
 
 /* LargeVis gradient (largevis.py:181-201 differentiated): accumulates into
  * grad[n_total,2] (zeroed by the caller) with atomics — the autograd scatter of

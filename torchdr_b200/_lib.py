@@ -45,9 +45,9 @@ SIGNATURES = {
     "tdr_compact_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "tdr_umap_compact_f32": (c_int, [P, P, P, c_int64, c_int64, P, P, P, P, P, P, c_size_t, P]),
     "tdr_umap_step_f32": (c_int, [P, P, c_int64, c_int64, c_int64, P, P, P, P, P, c_int, c_int, c_uint64, c_int64,
-                                  c_double, c_double, c_float, c_float, c_float, c_int, P, P, P, P]),
+                                  c_double, c_double, c_float, c_float, c_float, c_int, P, P, P, P, P]),
     "tdr_umap_run_f32": (c_int, [P, P, c_int64, P, P, P, P, c_int, c_int, c_uint64, c_int64, c_int,
-                                 ctypes.POINTER(c_float), c_double, c_double, c_float, c_float, c_int, P, P, P]),
+                                 ctypes.POINTER(c_float), c_double, c_double, c_float, c_float, c_int, P, P, P, P]),
     "tdr_largevis_grad_f32": (c_int, [P, c_int64, c_int64, c_int64, P, P, c_int, P, c_int, c_uint64, c_int64,
                                       c_float, c_float, P, P]),
     "tdr_tsne_workspace_bytes": (c_size_t, [c_int64]),

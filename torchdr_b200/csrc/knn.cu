@@ -13,6 +13,9 @@
 // MODE_FUSED : + UMAP rho/sigma search on the finished rows (rowsearch.cuh) — the
 //              "fused distance + sigma-bisection" kernel of BASELINE.json config 2
 // MODE_FULL  : one (query tile, db tile) per CTA, writes the dense C tile (k=None path)
+#include <stdlib.h>
+
+#include <algorithm>
 #include <type_traits>
 
 #include "rowsearch.cuh"
@@ -24,6 +27,18 @@ constexpr int LDS = BM + 4;  // padded leading dimension of the K-major smem til
 constexpr int QCAP = 16;     // per-row candidate queue
 
 enum { MODE_KNN = 0, MODE_FUSED = 1, MODE_FULL = 2 };
+
+// knn_tc.cu
+bool knn_tc_supported(int d, int k);
+size_t knn_tc_workspace_bytes(int64_t nq, int64_t ndb, int d, bool same);
+int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb, int64_t ndb, int d, int k,
+                  bool same, int exclude_self, int metric, int fused, int max_iter, float* out_dist, int32_t* out_idx,
+                  float* P, float* rho, float* sigma, void* ws, size_t ws_bytes, cudaStream_t st);
+// 0 = auto, 1 = SIMT fp32 kernel, 2 = tcgen05 kernel (tests / profiling); env TDR_KNN_PATH seeds it
+static int g_knn_path = [] {
+    const char* e = getenv("TDR_KNN_PATH");
+    return e ? atoi(e) : 1;
+}();
 
 struct KnnParams {
     const float* Xq;   // [nq, ld]
@@ -466,6 +481,16 @@ static int knn_common(int mode, const float* Xq, int64_t nq, int64_t q_row0, con
     TDR_CHECK_ARG(metric == TDR_METRIC_SQEUCLIDEAN || metric == TDR_METRIC_EUCLIDEAN,
                   "[TorchDR] ERROR : metric id %d is not supported.", metric);
     if (nq == 0) return TDR_OK;
+    // tensor-core path (knn_tc.cu) when the tile shapes allow it; the SIMT kernel below otherwise
+    if (g_knn_path != 1 && knn_tc_supported(d, k) && (g_knn_path == 2 || g_knn_path == 0)) {
+        const bool inside = (Xq == Xdb + q_row0 * d) && q_row0 + nq <= ndb;
+        return knn_tc_launch(Xq, nq, q_row0, Xdb, ndb, d, k, inside, exclude_self, metric, mode == MODE_FUSED,
+                             max_iter, out_dist, out_idx, P, rho, sigma, ws, ws_bytes, st);
+    }
+    if (g_knn_path == 2) {
+        set_error("knn: tensor-core path forced but unsupported for d=%d k=%d", d, k);
+        return TDR_E_UNSUPPORTED;
+    }
     const bool same = (Xq == Xdb && nq == ndb);
     Prepared pr;
     int rc = prepare(Xq, nq, Xdb, ndb, d, same, ws, ws_bytes, st, &pr);
@@ -498,9 +523,16 @@ static int knn_common(int mode, const float* Xq, int64_t nq, int64_t q_row0, con
 using namespace tdr;
 
 extern "C" TDR_API size_t tdr_knn_workspace_bytes(int64_t nq, int64_t ndb, int d, int k) {
-    (void)k;
-    // conservative: assume distinct query / database buffers
-    return prepare_bytes(nq, ndb, d, false) + 256;
+    // conservative: assume distinct query / database buffers; covers both kernel paths
+    size_t b = prepare_bytes(nq, ndb, d, false) + 256;
+    if (knn_tc_supported(d, k)) b = std::max(b, knn_tc_workspace_bytes(nq, ndb, d, false) + 256);
+    return b;
+}
+
+extern "C" TDR_API int tdr_knn_set_path(int path) {
+    TDR_CHECK_ARG(path >= 0 && path <= 2, "tdr_knn_set_path: 0 = auto, 1 = SIMT fp32, 2 = tcgen05");
+    g_knn_path = path;
+    return TDR_OK;
 }
 
 extern "C" TDR_API int tdr_knn_f32(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb, int64_t ndb, int d,

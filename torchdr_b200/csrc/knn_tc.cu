@@ -1,0 +1,516 @@
+// (i) Exact kNN on the 5th-gen tensor cores: tcgen05.mma (kind::f16) + TMEM + TMA, sm_100a.
+//
+// The only dense contraction of the path is the -2 X Y^T term of torchdr/distance/torch.py:89-91.
+// fp32 accuracy is kept by an error-compensated split: every input is pre-scaled by a power of
+// two s (so |x s| < 2^10) and written as x s = hi + lo with hi, lo in fp16 (11 significant bits
+// each, 22 together).  Three MMA passes give  hi.hi  (exact products, accumulated in one TMEM
+// accumulator) and  hi.lo + lo.hi  (2^-11 smaller, a second accumulator); the dropped lo.lo term
+// is 2^-22 relative — below the fp32 rounding of the reference's own sgemm.  fp16 MMAs run at
+// the full 16-bit tensor rate, i.e. 3 passes cost what 1.5 TF32 passes would.
+//
+// One CTA (256 threads, 1 per SM) owns 128 query rows: their hi/lo tiles stay resident in
+// shared memory (TMA, 128B swizzle) for the whole sweep over the database, which streams through
+// a ring of TMA stages in 128-row tiles.  Warp 0 = TMA producer, warp 1 = MMA issuer (one
+// thread), warp 2 = TMEM allocator, warps 4-7 = epilogue: thread t owns TMEM lane t = query row
+// t, reads its 128 accumulator columns with tcgen05.ld, forms the distance and compares it with
+// its row's running k-th best held in a register; the rare survivor is insertion-sorted into the
+// row's list in shared memory.  Two accumulator stages (2 x 256 TMEM columns) overlap the MMAs of
+// tile t+1 with the filter of tile t.  MODE_FUSED runs the UMAP rho/sigma search (rowsearch.cuh)
+// on the finished rows before they leave the SM.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <type_traits>
+
+#include "rowsearch.cuh"
+
+namespace tdr {
+namespace tc {
+
+constexpr int BM = 128, BN = 128, KATOM = 64;  // 64 fp16 = one 128-byte swizzle row
+constexpr int NT = 256;
+constexpr int TILE_BYTES = BM * KATOM * 2;  // 16 KB: one [128 x 64] fp16 box
+constexpr int MAX_ATOMS = 2;                // d <= 128
+constexpr int MAX_K = 32;                   // top-k lists in shared memory next to 192 KB of tiles
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled [rows x 64 fp16] tile: SBO = 8 rows * 128 B, version 1 (sm_100), layout 2 (SW128)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// kind::f16, A/B = F16 (0), D = F32 (1), both K-major, N = 128, M = 128
+constexpr uint32_t kInstrDesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+// ------------------------------------------------------------------ pre-pass: scale + fp16 split
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ X, int64_t n, int* __restrict__ out_bits) {
+    float m = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(X[i]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_int(m));
+}
+
+__device__ __forceinline__ int scale_exponent(float absmax) {
+    if (!(absmax > 0.0f) || absmax == INFINITY) return 0;
+    return 9 - ilogbf(absmax);  // absmax * 2^e in [2^9, 2^10)
+}
+
+__global__ void __launch_bounds__(256)
+split_kernel(const float* __restrict__ X, int64_t n, int d, int dp, const int* __restrict__ absmax_bits,
+             __half* __restrict__ hi, __half* __restrict__ lo) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * dp) return;
+    const int64_t r = i / dp;
+    const int c = (int)(i - r * dp);
+    float v = 0.0f;
+    if (c < d) v = ldexpf(X[r * d + c], scale_exponent(__int_as_float(*absmax_bits)));
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    lo[i] = __float2half_rn(v - __half2float(h));
+}
+
+// norms in fp64 -> fp32; entries beyond n (up to the 128-padded length) are +inf so padded columns never qualify
+__global__ void __launch_bounds__(256) sqnorm_pad_kernel(const float* __restrict__ X, int64_t n, int64_t n_pad, int d,
+                                                         float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n_pad) return;
+    if (row >= n) {
+        if (lane == 0) out[row] = INFINITY;
+        return;
+    }
+    const float* x = X + row * d;
+    double s = 0.0;
+    for (int j = lane; j < d; j += 32) s = fma((double)x[j], (double)x[j], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[row] = (float)s;
+}
+
+// Sorted insert into a thread-private list in shared memory; equal distances keep index order
+// because columns arrive in ascending index.  Rare (~k ln(N/k) calls per row per sweep): kept
+// out of line so the 128-column filter loop stays small.
+__device__ __noinline__ float list_insert(float* my_d, int* my_i, int k, float dist, int col) {
+    int p = k - 1;
+    while (p > 0 && my_d[p - 1] > dist) {
+        my_d[p] = my_d[p - 1];
+        my_i[p] = my_i[p - 1];
+        --p;
+    }
+    my_d[p] = dist;
+    my_i[p] = col;
+    return my_d[k - 1];
+}
+
+// ------------------------------------------------------------------ main kernel
+struct Params {
+    int64_t nq, ndb, q_row0;  // q_row0: global id of query row 0 (self exclusion)
+    int64_t q_tile_row0;      // row of query 0 inside the query split arrays
+    const float* qn;
+    const float* dbn;  // padded to a multiple of 128 with +inf
+    const int* absmax_bits;
+    int k, kpad, atoms, stages;
+    int exclude_self, metric, fused, max_iter;
+    float* out_dist;
+    int32_t* out_idx;
+    float* P;
+    float* rho;
+    float* sigma;
+};
+
+__global__ void __launch_bounds__(NT, 1)
+knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
+              const __grid_constant__ CUtensorMap map_db_hi, const __grid_constant__ CUtensorMap map_db_lo,
+              const Params prm) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int atoms = prm.atoms, stages = prm.stages, k = prm.k, kpad = prm.kpad;
+    const int a_bytes = atoms * 2 * TILE_BYTES;  // hi + lo
+    unsigned char* a_tiles = smem;                    // [atoms][hi, lo][16 KB]
+    unsigned char* b_tiles = smem + a_bytes;          // [stages][atoms][hi, lo][16 KB]
+    float* ld_s = reinterpret_cast<float*>(b_tiles + (size_t)stages * a_bytes);  // [128][kpad]
+    int* li_s = reinterpret_cast<int*>(ld_s + BM * kpad);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(li_s + BM * kpad);
+    // barrier slots: 0 a_full | 1..S full | 1+S..2S empty | 2S+1, 2S+2 tmem_full | 2S+3, 2S+4 tmem_empty
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 5);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t q0 = (int64_t)blockIdx.x * BM;
+    const int64_t n_tiles = (prm.ndb + BN - 1) / BN;
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    const int B_FULL = 1, B_EMPTY = 1 + stages, T_FULL = 1 + 2 * stages, T_EMPTY = 3 + 2 * stages;
+
+    if (warp == 1 && lane == 0) {
+        mbar_init(BAR(0), 1);
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(BAR(B_FULL + s), 1);
+            mbar_init(BAR(B_EMPTY + s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(BAR(T_FULL + s), 1);
+            mbar_init(BAR(T_EMPTY + s), 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    for (int i = tid; i < BM * kpad; i += NT) {
+        ld_s[i] = INFINITY;
+        li_s[i] = 0x7fffffff;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            mbar_expect_tx(BAR(0), (uint32_t)a_bytes);
+            for (int a = 0; a < atoms; ++a) {
+                tma_load_2d(smem_u32(a_tiles + (a * 2 + 0) * TILE_BYTES), &map_q_hi, BAR(0), a * KATOM,
+                            (int)(prm.q_tile_row0 + q0));
+                tma_load_2d(smem_u32(a_tiles + (a * 2 + 1) * TILE_BYTES), &map_q_lo, BAR(0), a * KATOM,
+                            (int)(prm.q_tile_row0 + q0));
+            }
+            for (int64_t t = 0; t < n_tiles; ++t) {
+                const int s = (int)(t % stages);
+                const uint32_t ph = (uint32_t)((t / stages) & 1);
+                mbar_wait(BAR(B_EMPTY + s), ph ^ 1u);
+                mbar_expect_tx(BAR(B_FULL + s), (uint32_t)a_bytes);
+                unsigned char* dst = b_tiles + (size_t)s * a_bytes;
+                for (int a = 0; a < atoms; ++a) {
+                    tma_load_2d(smem_u32(dst + (a * 2 + 0) * TILE_BYTES), &map_db_hi, BAR(B_FULL + s), a * KATOM, (int)(t * BN));
+                    tma_load_2d(smem_u32(dst + (a * 2 + 1) * TILE_BYTES), &map_db_lo, BAR(B_FULL + s), a * KATOM, (int)(t * BN));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            mbar_wait(BAR(0), 0);
+            for (int64_t t = 0; t < n_tiles; ++t) {
+                const int s = (int)(t % stages);
+                const uint32_t ph = (uint32_t)((t / stages) & 1);
+                const int as = (int)(t & 1);
+                const uint32_t aph = (uint32_t)((t >> 1) & 1);
+                mbar_wait(BAR(T_EMPTY + as), aph ^ 1u);
+                mbar_wait(BAR(B_FULL + s), ph);
+                tc_fence_after();
+                const uint32_t d_big = tmem_base + (uint32_t)(as * 256);
+                const uint32_t d_small = d_big + 128u;
+                const unsigned char* bt = b_tiles + (size_t)s * a_bytes;
+                for (int a = 0; a < atoms; ++a) {
+                    const uint64_t a_hi = make_smem_desc(smem_u32(a_tiles + (a * 2 + 0) * TILE_BYTES));
+                    const uint64_t a_lo = make_smem_desc(smem_u32(a_tiles + (a * 2 + 1) * TILE_BYTES));
+                    const uint64_t b_hi = make_smem_desc(smem_u32(bt + (a * 2 + 0) * TILE_BYTES));
+                    const uint64_t b_lo = make_smem_desc(smem_u32(bt + (a * 2 + 1) * TILE_BYTES));
+#pragma unroll
+                    for (int kk = 0; kk < KATOM / 16; ++kk) {
+                        const uint64_t adv = (uint64_t)(kk * 2);  // 16 fp16 = 32 B -> +2 in the >>4 address field
+                        const uint32_t acc = (a | kk) ? 1u : 0u;
+                        tc_mma_f16(d_big, a_hi + adv, b_hi + adv, kInstrDesc, acc);
+                        tc_mma_f16(d_small, a_hi + adv, b_lo + adv, kInstrDesc, acc);
+                        tc_mma_f16(d_small, a_lo + adv, b_hi + adv, kInstrDesc, 1u);
+                    }
+                }
+                tc_commit(BAR(B_EMPTY + s));   // smem stage reusable once these MMAs retire
+                tc_commit(BAR(T_FULL + as));   // accumulators ready for the epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: thread = query row =====================
+        const int row = tid - 128;  // == TMEM lane; warp (4..7) % 4 selects lanes 32*(warp-4)..+31
+        const int64_t gq = q0 + row;
+        const int64_t self = prm.q_row0 + gq;
+        const float qn = gq < prm.nq ? __ldg(prm.qn + gq) : 0.0f;
+        const int e = scale_exponent(__int_as_float(__ldg(prm.absmax_bits)));
+        const float inv_s2 = ldexpf(1.0f, -2 * e);
+        float* my_d = ld_s + row * kpad;
+        int* my_i = li_s + row * kpad;
+        float tau = INFINITY;
+        const uint32_t lane_addr = (uint32_t)((warp - 4) * 32) << 16;
+        for (int64_t t = 0; t < n_tiles; ++t) {
+            const int as = (int)(t & 1);
+            const uint32_t aph = (uint32_t)((t >> 1) & 1);
+            mbar_wait(BAR(T_FULL + as), aph);
+            tc_fence_after();
+            const int col0 = (int)(t * BN);
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t big[32], small[32];
+                tc_ld32(tmem_base + lane_addr + (uint32_t)(as * 256 + c), big);
+                tc_ld32(tmem_base + lane_addr + (uint32_t)(as * 256 + 128 + c), small);
+                tc_ld_wait();
+#pragma unroll
+                for (int j4 = 0; j4 < 32; j4 += 4) {
+                    const float4 nb = __ldg(reinterpret_cast<const float4*>(prm.dbn + col0 + c + j4));
+                    const float nbv[4] = {nb.x, nb.y, nb.z, nb.w};
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = j4 + jj;
+                        const float dot = __fmul_rn(__fadd_rn(__uint_as_float(big[j]), __uint_as_float(small[j])), inv_s2);
+                        float dist = __fsub_rn(__fadd_rn(qn, nbv[jj]), 2.0f * dot);  // torch.py:89-91
+                        if (prm.metric == TDR_METRIC_EUCLIDEAN) dist = sqrtf(fmaxf(dist, 0.0f));
+                        if (dist < tau) {
+                            const int col = col0 + c + j;
+                            if (!(prm.exclude_self && (int64_t)col == self)) tau = list_insert(my_d, my_i, k, dist, col);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(BAR(T_EMPTY + as));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+
+    // ---- write back; fused: rho/sigma search on the finished rows (all 8 warps, 16 rows each) ----
+    for (int rr = 0; rr < 16; ++rr) {
+        const int row = warp * 16 + rr;
+        const int64_t gr = q0 + row;
+        if (gr >= prm.nq) continue;
+        const float* ldr = ld_s + row * kpad;
+        const int* lir = li_s + row * kpad;
+        if (lane < k) {
+            if (prm.out_dist) prm.out_dist[gr * k + lane] = ldr[lane];
+            prm.out_idx[gr * k + lane] = lir[lane];
+        }
+        if (prm.fused) {
+            UmapRow<1> u;  // k <= 32
+            u.k = k;
+            u.lane = lane;
+            u.target = log2f((float)k);
+            u.c[0] = u.valid(0) ? ldr[lane] : INFINITY;
+            u.init();
+            const float s = u.solve(prm.max_iter);
+            if (u.valid(0)) prm.P[gr * k + lane] = u.p(0, s);
+            if (lane == 0) {
+                prm.rho[gr] = u.rho;
+                prm.sigma[gr] = s;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap* m, const __half* base, int64_t rows, int dp) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable");
+        return TDR_E_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)dp, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)dp * 2};
+    cuuint32_t box[2] = {(cuuint32_t)KATOM, (cuuint32_t)BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with code %d", (int)r);
+        return TDR_E_CUDA;
+    }
+    return TDR_OK;
+}
+
+}  // namespace tc
+
+bool knn_tc_supported(int d, int k) { return d <= tc::MAX_ATOMS * tc::KATOM && k <= tc::MAX_K; }
+
+size_t knn_tc_workspace_bytes(int64_t nq, int64_t ndb, int d, bool same) {
+    const int dp = (int)align_up((size_t)d, tc::KATOM);
+    const int64_t ndb_pad = (int64_t)align_up((size_t)ndb, 128);
+    const int64_t nq_pad = (int64_t)align_up((size_t)nq, 128);
+    size_t b = 256;                                        // absmax
+    b += align_up((size_t)ndb_pad * 4, 256);               // dbn (padded with +inf)
+    b += 2 * align_up((size_t)ndb * dp * 2, 256);          // db hi, lo
+    if (!same) {
+        b += align_up((size_t)nq_pad * 4, 256);
+        b += 2 * align_up((size_t)nq * dp * 2, 256);
+    }
+    return b;
+}
+
+// `same`: the query rows are rows [q_row0, q_row0+nq) of the database buffer itself.
+int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb, int64_t ndb, int d, int k,
+                  bool same, int exclude_self, int metric, int fused, int max_iter, float* out_dist, int32_t* out_idx,
+                  float* P, float* rho, float* sigma, void* ws, size_t ws_bytes, cudaStream_t st) {
+    using namespace tc;
+    const size_t need = knn_tc_workspace_bytes(nq, ndb, d, same);
+    if (!ws || ws_bytes < need || (uintptr_t)ws % 256) {
+        set_error("knn (tensor-core path) workspace: need %zu bytes (256-aligned), got %zu", need, ws_bytes);
+        return TDR_E_WORKSPACE;
+    }
+    const int dp = (int)align_up((size_t)d, KATOM);
+    const int atoms = dp / KATOM;
+    const int64_t ndb_pad = (int64_t)align_up((size_t)ndb, 128);
+    const int64_t nq_pad = (int64_t)align_up((size_t)nq, 128);
+    char* p = (char*)ws;
+    int* absmax = (int*)p;
+    p += 256;
+    float* dbn = (float*)p;
+    p += align_up((size_t)ndb_pad * 4, 256);
+    __half* db_hi = (__half*)p;
+    p += align_up((size_t)ndb * dp * 2, 256);
+    __half* db_lo = (__half*)p;
+    p += align_up((size_t)ndb * dp * 2, 256);
+    float* qn = dbn + (same ? q_row0 : 0);
+    __half *q_hi = db_hi, *q_lo = db_lo;
+    if (!same) {
+        qn = (float*)p;
+        p += align_up((size_t)nq_pad * 4, 256);
+        q_hi = (__half*)p;
+        p += align_up((size_t)nq * dp * 2, 256);
+        q_lo = (__half*)p;
+    }
+    TDR_CUDA(cudaMemsetAsync(absmax, 0, 4, st));
+    const unsigned rgrid = (unsigned)std::min<int64_t>((int64_t)kNumSMs * 16, (ndb * d + 255) / 256);
+    absmax_kernel<<<rgrid, 256, 0, st>>>(Xdb, ndb * d, absmax);
+    if (!same) {
+        const unsigned qgrid = (unsigned)std::min<int64_t>((int64_t)kNumSMs * 16, (nq * d + 255) / 256);
+        absmax_kernel<<<qgrid, 256, 0, st>>>(Xq, nq * d, absmax);
+    }
+    split_kernel<<<(unsigned)((ndb * dp + 255) / 256), 256, 0, st>>>(Xdb, ndb, d, dp, absmax, db_hi, db_lo);
+    sqnorm_pad_kernel<<<(unsigned)((ndb_pad + 7) / 8), 256, 0, st>>>(Xdb, ndb, ndb_pad, d, dbn);
+    if (!same) {
+        split_kernel<<<(unsigned)((nq * dp + 255) / 256), 256, 0, st>>>(Xq, nq, d, dp, absmax, q_hi, q_lo);
+        sqnorm_pad_kernel<<<(unsigned)((nq_pad + 7) / 8), 256, 0, st>>>(Xq, nq, nq_pad, d, qn);
+    }
+    TDR_LAUNCH_CHECK();
+
+    CUtensorMap mq_hi, mq_lo, mdb_hi, mdb_lo;
+    int rc;
+    const int64_t q_rows = same ? ndb : nq;
+    if ((rc = make_map(&mq_hi, q_hi, q_rows, dp)) || (rc = make_map(&mq_lo, q_lo, q_rows, dp)) ||
+        (rc = make_map(&mdb_hi, db_hi, ndb, dp)) || (rc = make_map(&mdb_lo, db_lo, ndb, dp)))
+        return rc;
+
+    Params prm{};
+    prm.nq = nq;
+    prm.ndb = ndb;
+    prm.q_row0 = q_row0;
+    prm.q_tile_row0 = same ? q_row0 : 0;
+    prm.qn = qn;
+    prm.dbn = dbn;
+    prm.absmax_bits = absmax;
+    prm.k = k;
+    prm.kpad = k;
+    prm.atoms = atoms;
+    prm.exclude_self = exclude_self;
+    prm.metric = metric;
+    prm.fused = fused;
+    prm.max_iter = max_iter;
+    prm.out_dist = out_dist;
+    prm.out_idx = out_idx;
+    prm.P = P;
+    prm.rho = rho;
+    prm.sigma = sigma;
+    const size_t stage_bytes = (size_t)atoms * 2 * TILE_BYTES;
+    const size_t fixed = stage_bytes + (size_t)BM * k * 8 + 512 + 1024;
+    int stages = (int)((227 * 1024 - fixed) / stage_bytes);
+    if (stages > 6) stages = 6;
+    if (stages < 2) {
+        set_error("knn (tensor-core path): shared memory budget exceeded");
+        return TDR_E_UNSUPPORTED;
+    }
+    prm.stages = stages;
+    const size_t smem = fixed + (size_t)stages * stage_bytes;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TDR_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    knn_tc_kernel<<<(unsigned)((nq + BM - 1) / BM), NT, smem, st>>>(mq_hi, mq_lo, mdb_hi, mdb_lo, prm);
+    TDR_LAUNCH_CHECK();
+    return TDR_OK;
+}
+
+}  // namespace tdr

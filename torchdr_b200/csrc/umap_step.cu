@@ -32,6 +32,7 @@ struct UmapStepParams {
     float2* grad_out;
     double* gnorm_sq;
     int* nan_flag;
+    unsigned long long* stats;  // [0] += sampled edges, [1] += negatives used (roofline accounting)
 };
 
 template <bool PRECISE>
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(kStepWarps * 32) umap_step_kernel(const UmapSt
     const float due_before = (float)(p.n_iter + 1);  // umap.py:251 (long promoted to fp32)
     double gn_local = 0.0;
     bool saw_nan = false;
+    unsigned long long n_act = 0, n_neg_used = 0;
 
     for (int64_t r = warp_global; r < p.n_local; r += n_warps) {
         const int64_t gi = p.row0 + r;
@@ -85,6 +87,8 @@ __global__ void __launch_bounds__(kStepWarps * 32) umap_step_kernel(const UmapSt
         // ---- repulsion (umap.py:266-292) on the first rate*active negatives
         int quota = active * p.rate;
         if (quota > p.n_neg) quota = p.n_neg;
+        n_act += active;
+        n_neg_used += quota;
         float rx = 0.0f, ry = 0.0f;
         const Philox rng(p.seed);
         for (int s = lane; s < quota; s += 32) {
@@ -128,6 +132,10 @@ __global__ void __launch_bounds__(kStepWarps * 32) umap_step_kernel(const UmapSt
     if (lane == 0) {
         if (p.gnorm_sq && gn_local != 0.0) atomicAdd(p.gnorm_sq, gn_local);
         if (p.nan_flag && saw_nan) atomicExch(p.nan_flag, 1);
+        if (p.stats) {
+            atomicAdd(p.stats, n_act);
+            atomicAdd(p.stats + 1, n_neg_used);
+        }
     }
 }
 
@@ -159,7 +167,7 @@ extern "C" TDR_API int tdr_umap_step_f32(const float* Z_in, float* Z_out, int64_
                                  float* epoch_of_next_sample, const int64_t* neg, int n_neg,
                                  int negative_sample_rate, uint64_t seed, int64_t n_iter, double a, double b,
                                  float lam, float repulsion, float lr, int precise, float* grad_out,
-                                 double* gnorm_sq, int* nan_flag, tdr_stream_t stream) {
+                                 double* gnorm_sq, int* nan_flag, uint64_t* stats, tdr_stream_t stream) {
     TDR_CHECK_ARG(Z_in && Z_out && rowptr && col && epochs_per_sample && epoch_of_next_sample,
                   "tdr_umap_step_f32: null pointer");
     TDR_CHECK_ARG(Z_in != Z_out, "tdr_umap_step_f32: Z_in and Z_out must not alias (Jacobi update)");
@@ -189,6 +197,7 @@ extern "C" TDR_API int tdr_umap_step_f32(const float* Z_in, float* Z_out, int64_
     p.grad_out = reinterpret_cast<float2*>(grad_out);
     p.gnorm_sq = gnorm_sq;
     p.nan_flag = nan_flag;
+    p.stats = reinterpret_cast<unsigned long long*>(stats);
     return launch_step(p, precise, (cudaStream_t)stream);
 }
 
@@ -196,7 +205,7 @@ extern "C" TDR_API int tdr_umap_run_f32(float* Z_a, float* Z_b, int64_t n_total,
                                 const int32_t* col, const float* epochs_per_sample, float* epoch_of_next_sample,
                                 int n_neg, int negative_sample_rate, uint64_t seed, int64_t n_iter0, int n_steps,
                                 const float* lrs_host, double a, double b, float lam, float repulsion, int precise,
-                                double* gnorm_sq, int* nan_flag, tdr_stream_t stream) {
+                                double* gnorm_sq, int* nan_flag, uint64_t* stats, tdr_stream_t stream) {
     TDR_CHECK_ARG(Z_a && Z_b && Z_a != Z_b && lrs_host && n_steps >= 0, "tdr_umap_run_f32: bad arguments");
     float* src = Z_a;
     float* dst = Z_b;
@@ -205,7 +214,7 @@ extern "C" TDR_API int tdr_umap_run_f32(float* Z_a, float* Z_b, int64_t n_total,
         int rc = tdr_umap_step_f32(src, dst, n_total, 0, n_total, rowptr, col, epochs_per_sample,
                                    epoch_of_next_sample, nullptr, n_neg, negative_sample_rate, seed, n_iter0 + t,
                                    a, b, lam, repulsion, lrs_host[t], precise, nullptr,
-                                   (t == n_steps - 1) ? gnorm_sq : nullptr, nan_flag, stream);
+                                   (t == n_steps - 1) ? gnorm_sq : nullptr, nan_flag, stats, stream);
         if (rc != TDR_OK) return rc;
         float* tmp = src;
         src = dst;

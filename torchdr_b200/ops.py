@@ -193,7 +193,7 @@ def umap_compact(rowptr, col, eps):
 
 
 def umap_step(Z_in, Z_out, row0, n_local, rowptr, col, eps, eons, n_iter, a, b, lr, neg=None, n_neg=75, rate=5,
-              seed=0, lam=1.0, repulsion=1.0, precise=False, grad_out=None, gnorm_sq=None, nan_flag=None):
+              seed=0, lam=1.0, repulsion=1.0, precise=False, grad_out=None, gnorm_sq=None, nan_flag=None, stats=None):
     n_total = Z_in.shape[0]
     if neg is not None:
         assert neg.dtype == torch.int64 and neg.is_contiguous() and neg.shape == (n_local, n_neg)
@@ -201,12 +201,12 @@ def umap_step(Z_in, Z_out, row0, n_local, rowptr, col, eps, eons, n_iter, a, b, 
         check(_lib.load().tdr_umap_step_f32(ptr(Z_in), ptr(Z_out), n_total, row0, n_local, ptr(rowptr), ptr(col),
                                             ptr(eps), ptr(eons), ptr(neg), n_neg, rate, seed, n_iter, float(a),
                                             float(b), float(lam), float(repulsion), float(lr), int(precise),
-                                            ptr(grad_out), ptr(gnorm_sq), ptr(nan_flag), stream()),
+                                            ptr(grad_out), ptr(gnorm_sq), ptr(nan_flag), ptr(stats), stream()),
               "tdr_umap_step_f32")
 
 
 def umap_run(Z_a, Z_b, rowptr, col, eps, eons, n_iter0, lrs, a, b, n_neg=75, rate=5, seed=0, lam=1.0,
-             repulsion=1.0, precise=False, gnorm_sq=None, nan_flag=None):
+             repulsion=1.0, precise=False, gnorm_sq=None, nan_flag=None, stats=None):
     """len(lrs) iterations on one GPU; returns the tensor holding the result."""
     lrs = np.ascontiguousarray(lrs, dtype=np.float32)
     n = len(lrs)
@@ -215,7 +215,7 @@ def umap_run(Z_a, Z_b, rowptr, col, eps, eons, n_iter0, lrs, a, b, n_neg=75, rat
                                            ptr(eons), n_neg, rate, seed, n_iter0, n,
                                            lrs.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), float(a), float(b),
                                            float(lam), float(repulsion), int(precise), ptr(gnorm_sq), ptr(nan_flag),
-                                           stream()), "tdr_umap_run_f32")
+                                           ptr(stats), stream()), "tdr_umap_run_f32")
     return Z_a if n % 2 == 0 else Z_b
 
 
