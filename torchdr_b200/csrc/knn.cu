@@ -37,7 +37,7 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
 // 0 = auto, 1 = SIMT fp32 kernel, 2 = tcgen05 kernel (tests / profiling); env TDR_KNN_PATH seeds it
 static int g_knn_path = [] {
     const char* e = getenv("TDR_KNN_PATH");
-    return e ? atoi(e) : 1;
+    return e ? atoi(e) : 0;
 }();
 
 struct KnnParams {

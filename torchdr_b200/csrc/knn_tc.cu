@@ -92,7 +92,21 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
-__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait::ld with the destination registers as in/out operands, so that no use of them can be
+// scheduled above the wait
+__device__ __forceinline__ void tc_ld_wait(uint32_t (&a)[32], uint32_t (&b)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]),
+                   "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]), "+r"(a[16]),
+                   "+r"(a[17]), "+r"(a[18]), "+r"(a[19]), "+r"(a[20]), "+r"(a[21]), "+r"(a[22]), "+r"(a[23]), "+r"(a[24]),
+                   "+r"(a[25]), "+r"(a[26]), "+r"(a[27]), "+r"(a[28]), "+r"(a[29]), "+r"(a[30]), "+r"(a[31]), "+r"(b[0]),
+                   "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]), "+r"(b[8]), "+r"(b[9]),
+                   "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15]), "+r"(b[16]), "+r"(b[17]),
+                   "+r"(b[18]), "+r"(b[19]), "+r"(b[20]), "+r"(b[21]), "+r"(b[22]), "+r"(b[23]), "+r"(b[24]), "+r"(b[25]),
+                   "+r"(b[26]), "+r"(b[27]), "+r"(b[28]), "+r"(b[29]), "+r"(b[30]), "+r"(b[31])
+                 :
+                 : "memory");
+}
 
 // K-major, 128B-swizzled [rows x 64 fp16] tile: SBO = 8 rows * 128 B, version 1 (sm_100), layout 2 (SW128)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
@@ -148,19 +162,34 @@ __global__ void __launch_bounds__(256) sqnorm_pad_kernel(const float* __restrict
     if (lane == 0) out[row] = (float)s;
 }
 
-// Sorted insert into a thread-private list in shared memory; equal distances keep index order
-// because columns arrive in ascending index.  Rare (~k ln(N/k) calls per row per sweep): kept
-// out of line so the 128-column filter loop stays small.
-__device__ __noinline__ float list_insert(float* my_d, int* my_i, int k, float dist, int col) {
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t a) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_s32(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// Sorted insert into a thread-private list in shared memory (shared-space addresses); equal
+// distances keep index order because columns arrive in ascending index.  Rare (~k ln(N/k) calls
+// per row per sweep): kept out of line so the filter loop stays small.
+__device__ __noinline__ float list_insert(uint32_t my_d, uint32_t my_i, int k, float dist, int col) {
     int p = k - 1;
-    while (p > 0 && my_d[p - 1] > dist) {
-        my_d[p] = my_d[p - 1];
-        my_i[p] = my_i[p - 1];
+    while (p > 0) {
+        const float v = lds_f32(my_d + 4u * (uint32_t)(p - 1));
+        if (!(v > dist)) break;
+        sts_f32(my_d + 4u * (uint32_t)p, v);
+        sts_s32(my_i + 4u * (uint32_t)p, lds_s32(my_i + 4u * (uint32_t)(p - 1)));
         --p;
     }
-    my_d[p] = dist;
-    my_i[p] = col;
-    return my_d[k - 1];
+    sts_f32(my_d + 4u * (uint32_t)p, dist);
+    sts_s32(my_i + 4u * (uint32_t)p, col);
+    return lds_f32(my_d + 4u * (uint32_t)(k - 1));
 }
 
 // ------------------------------------------------------------------ main kernel
@@ -285,45 +314,72 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
         }
     } else if (warp >= 4) {
         // ===================== epilogue: thread = query row =====================
+        // One warp per scheduler, so latency is hidden by instruction-level parallelism: the 32
+        // distances of a TMEM chunk are formed as independent chains (2 FADD + 1 FFMA + 1 FMNMX each),
+        // only their minimum is compared with the row's running k-th best, and the next chunk's
+        // tcgen05.ld is in flight meanwhile.  The per-element test runs only when that minimum wins.
         const int row = tid - 128;  // == TMEM lane; warp (4..7) % 4 selects lanes 32*(warp-4)..+31
         const int64_t gq = q0 + row;
-        const int64_t self = prm.q_row0 + gq;
+        const int64_t self = prm.exclude_self ? prm.q_row0 + gq : -1;
         const float qn = gq < prm.nq ? __ldg(prm.qn + gq) : 0.0f;
         const int e = scale_exponent(__int_as_float(__ldg(prm.absmax_bits)));
-        const float inv_s2 = ldexpf(1.0f, -2 * e);
-        float* my_d = ld_s + row * kpad;
-        int* my_i = li_s + row * kpad;
+        const float neg2s = -2.0f * ldexpf(1.0f, -2 * e);  // power of two: the FFMA below rounds once, like sub(add, 2*dot)
+        const uint32_t my_d = smem_u32(ld_s + row * kpad), my_i = smem_u32(li_s + row * kpad);
         float tau = INFINITY;
         const uint32_t lane_addr = (uint32_t)((warp - 4) * 32) << 16;
+
+        auto filter = [&](uint32_t(&big)[32], uint32_t(&small)[32], int col_base) {
+            float m0 = INFINITY, m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;
+#pragma unroll
+            for (int j4 = 0; j4 < 32; j4 += 4) {
+                const float4 nb = __ldg(reinterpret_cast<const float4*>(prm.dbn + col_base + j4));
+                // torch.py:89-91: (|x|^2 + |y|^2) - 2 x.y
+                const float d0 = fmaf(__fadd_rn(__uint_as_float(big[j4 + 0]), __uint_as_float(small[j4 + 0])), neg2s, __fadd_rn(qn, nb.x));
+                const float d1 = fmaf(__fadd_rn(__uint_as_float(big[j4 + 1]), __uint_as_float(small[j4 + 1])), neg2s, __fadd_rn(qn, nb.y));
+                const float d2 = fmaf(__fadd_rn(__uint_as_float(big[j4 + 2]), __uint_as_float(small[j4 + 2])), neg2s, __fadd_rn(qn, nb.z));
+                const float d3 = fmaf(__fadd_rn(__uint_as_float(big[j4 + 3]), __uint_as_float(small[j4 + 3])), neg2s, __fadd_rn(qn, nb.w));
+                big[j4 + 0] = __float_as_uint(d0);
+                big[j4 + 1] = __float_as_uint(d1);
+                big[j4 + 2] = __float_as_uint(d2);
+                big[j4 + 3] = __float_as_uint(d3);
+                m0 = fminf(m0, d0);
+                m1 = fminf(m1, d1);
+                m2 = fminf(m2, d2);
+                m3 = fminf(m3, d3);
+            }
+            if (fminf(fminf(m0, m1), fminf(m2, m3)) < tau) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float dist = __uint_as_float(big[j]);
+                    if (dist < tau && (int64_t)(col_base + j) != self) tau = list_insert(my_d, my_i, k, dist, col_base + j);
+                }
+            }
+        };
+
         for (int64_t t = 0; t < n_tiles; ++t) {
             const int as = (int)(t & 1);
             const uint32_t aph = (uint32_t)((t >> 1) & 1);
             mbar_wait(BAR(T_FULL + as), aph);
             tc_fence_after();
             const int col0 = (int)(t * BN);
-#pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
-                uint32_t big[32], small[32];
-                tc_ld32(tmem_base + lane_addr + (uint32_t)(as * 256 + c), big);
-                tc_ld32(tmem_base + lane_addr + (uint32_t)(as * 256 + 128 + c), small);
-                tc_ld_wait();
-#pragma unroll
-                for (int j4 = 0; j4 < 32; j4 += 4) {
-                    const float4 nb = __ldg(reinterpret_cast<const float4*>(prm.dbn + col0 + c + j4));
-                    const float nbv[4] = {nb.x, nb.y, nb.z, nb.w};
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int j = j4 + jj;
-                        const float dot = __fmul_rn(__fadd_rn(__uint_as_float(big[j]), __uint_as_float(small[j])), inv_s2);
-                        float dist = __fsub_rn(__fadd_rn(qn, nbv[jj]), 2.0f * dot);  // torch.py:89-91
-                        if (prm.metric == TDR_METRIC_EUCLIDEAN) dist = sqrtf(fmaxf(dist, 0.0f));
-                        if (dist < tau) {
-                            const int col = col0 + c + j;
-                            if (!(prm.exclude_self && (int64_t)col == self)) tau = list_insert(my_d, my_i, k, dist, col);
-                        }
-                    }
-                }
-            }
+            const uint32_t tb = tmem_base + lane_addr + (uint32_t)(as * 256);
+            uint32_t bigA[32], smallA[32], bigB[32], smallB[32];
+            tc_ld32(tb + 0, bigA);
+            tc_ld32(tb + 128, smallA);
+            tc_ld_wait(bigA, smallA);
+            tc_ld32(tb + 32, bigB);
+            tc_ld32(tb + 160, smallB);
+            filter(bigA, smallA, col0);
+            tc_ld_wait(bigB, smallB);
+            tc_ld32(tb + 64, bigA);
+            tc_ld32(tb + 192, smallA);
+            filter(bigB, smallB, col0 + 32);
+            tc_ld_wait(bigA, smallA);
+            tc_ld32(tb + 96, bigB);
+            tc_ld32(tb + 224, smallB);
+            filter(bigA, smallA, col0 + 64);
+            tc_ld_wait(bigB, smallB);
+            filter(bigB, smallB, col0 + 96);
             tc_fence_before();
             mbar_arrive(BAR(T_EMPTY + as));
         }
@@ -344,7 +400,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
         const float* ldr = ld_s + row * kpad;
         const int* lir = li_s + row * kpad;
         if (lane < k) {
-            if (prm.out_dist) prm.out_dist[gr * k + lane] = ldr[lane];
+            // lists are kept in the squared domain; euclidean = sqrt(clamp(., 0)) (torch.py:92-95) is monotone
+            float dv = ldr[lane];
+            if (prm.metric == TDR_METRIC_EUCLIDEAN) dv = sqrtf(fmaxf(dv, 0.0f));
+            if (prm.out_dist) prm.out_dist[gr * k + lane] = dv;
             prm.out_idx[gr * k + lane] = lir[lane];
         }
         if (prm.fused) {

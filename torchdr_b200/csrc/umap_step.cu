@@ -35,6 +35,38 @@ struct UmapStepParams {
     unsigned long long* stats;  // [0] += sampled edges, [1] += negatives used (roofline accounting)
 };
 
+// Per-block reduction of the optional diagnostics (gradient norm, NaN flag, sampled-edge counters) in
+// shared memory, then one global atomic per block: thousands of same-address global atomics per launch
+// would otherwise serialise in L2.
+__device__ __forceinline__ void block_flush(bool leader, double gn, bool saw_nan, unsigned long long n_act,
+                                            unsigned long long n_neg, const UmapStepParams& p) {
+    if (!p.gnorm_sq && !p.nan_flag && !p.stats) return;  // uniform
+    __shared__ double s_gn;
+    __shared__ unsigned long long s_cnt[2];
+    __shared__ int s_nan;
+    if (threadIdx.x == 0) {
+        s_gn = 0.0;
+        s_cnt[0] = s_cnt[1] = 0ull;
+        s_nan = 0;
+    }
+    __syncthreads();
+    if (leader) {
+        if (gn != 0.0) atomicAdd(&s_gn, gn);
+        if (n_act) atomicAdd(&s_cnt[0], n_act);
+        if (n_neg) atomicAdd(&s_cnt[1], n_neg);
+        if (saw_nan) s_nan = 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (p.gnorm_sq && s_gn != 0.0) atomicAdd(p.gnorm_sq, s_gn);
+        if (p.nan_flag && s_nan) atomicExch(p.nan_flag, 1);
+        if (p.stats) {
+            if (s_cnt[0]) atomicAdd(p.stats, s_cnt[0]);
+            if (s_cnt[1]) atomicAdd(p.stats + 1, s_cnt[1]);
+        }
+    }
+}
+
 template <bool PRECISE>
 __device__ __forceinline__ float pow_b(float x, float y) {
     // torch pow(tensor, scalar) evaluates powf in fp32 (Sleef, 1 ulp); parity mode goes through
@@ -129,22 +161,157 @@ __global__ void __launch_bounds__(kStepWarps * 32) umap_step_kernel(const UmapSt
             saw_nan |= (zo.x != zo.x) || (zo.y != zo.y);
         }
     }
-    if (lane == 0) {
-        if (p.gnorm_sq && gn_local != 0.0) atomicAdd(p.gnorm_sq, gn_local);
-        if (p.nan_flag && saw_nan) atomicExch(p.nan_flag, 1);
-        if (p.stats) {
-            atomicAdd(p.stats, n_act);
-            atomicAdd(p.stats + 1, n_neg_used);
+    block_flush(lane == 0, gn_local, saw_nan, n_act, n_neg_used, p);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Throughput kernel (fp32 powf): the step is bound by memory latency, not bandwidth — a row's work
+// is a chain  rowptr -> (eons, col, eps) -> z_j gathers  of dependent round trips — so the kernel is
+// organised for memory-level parallelism: G = 8 lanes per row (4 rows per warp), the three edge
+// arrays are loaded together and unconditionally for up to 4 lane-strided chunks, the gathers of all
+// due edges are issued back to back, and each lane fetches 4 negatives per Philox call before any of
+// them is consumed.  Same arithmetic as umap_step_kernel<false>; only the order of the fp32 partial
+// sums differs.
+constexpr int G = 8;           // lanes per row
+constexpr int U = 4;           // edge chunks / negatives in flight per lane
+constexpr int kV2Threads = 256;
+
+__device__ __forceinline__ float group_sum(float v, unsigned mask) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    return v;
+}
+__device__ __forceinline__ int group_sum_int(int v, unsigned mask) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(kV2Threads, 4) umap_step_kernel_v2(const UmapStepParams p) {
+    const int lane = threadIdx.x & 31;
+    const int l = lane & (G - 1);
+    const unsigned gmask = ((1u << G) - 1u) << (lane & ~(G - 1));
+    const int64_t group_global = ((int64_t)blockIdx.x * kV2Threads + threadIdx.x) / G;
+    const int64_t n_groups = (int64_t)gridDim.x * kV2Threads / G;
+    const float due_before = (float)(p.n_iter + 1);
+    const Philox rng(p.seed);
+    double gn_local = 0.0;
+    bool saw_nan = false;
+    unsigned long long n_act = 0, n_neg_used = 0;
+
+    for (int64_t r = group_global; r < p.n_local; r += n_groups) {
+        const int64_t gi = p.row0 + r;
+        const float2 zi = __ldg(p.Zin + gi);
+        const int64_t e0 = __ldg(p.rowptr + r), e1 = __ldg(p.rowptr + r + 1);
+        float gx = 0.0f, gy = 0.0f;
+        int active = 0;
+        for (int64_t base = e0; base < e1; base += G * U) {
+            float nxt[U], ep[U];
+            int cj[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t e = base + u * G + l;
+                const bool ok = e < e1;
+                nxt[u] = ok ? p.eons[e] : INFINITY;
+                cj[u] = ok ? __ldg(p.col + e) : 0;
+                ep[u] = ok ? __ldg(p.eps + e) : 0.0f;
+            }
+            float2 zj[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (nxt[u] <= due_before) zj[u] = __ldg(p.Zin + cj[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (nxt[u] <= due_before) {
+                    p.eons[base + u * G + l] = __fadd_rn(nxt[u], ep[u]);  // umap.py:253-255
+                    ++active;
+                    const float dx = __fsub_rn(zi.x, zj[u].x), dy = __fsub_rn(zi.y, zj[u].y);
+                    const float D = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                    if (D > 0.0f) {  // umap.py:243-247
+                        const float den = __fadd_rn(1.0f, __fmul_rn(p.a, powf(D, p.b)));
+                        const float coef = __fdiv_rn(__fmul_rn(powf(D, p.bm1), p.two_ab), den);
+                        gx = fmaf(dx, coef, gx);
+                        gy = fmaf(dy, coef, gy);
+                    }
+                }
+            }
+        }
+        gx = group_sum(gx, gmask);
+        gy = group_sum(gy, gmask);
+        active = group_sum_int(active, gmask);
+        gx = fminf(fmaxf(gx, -4.0f), 4.0f);  // umap.py:263
+        gy = fminf(fmaxf(gy, -4.0f), 4.0f);
+
+        int quota = active * p.rate;  // umap.py:279-284
+        if (quota > p.n_neg) quota = p.n_neg;
+        float rx = 0.0f, ry = 0.0f;
+        for (int s0 = 0; s0 < quota; s0 += G * U) {
+            // lane l owns slots s0 + 4 l .. s0 + 4 l + 3 (one Philox block)
+            const int sb = s0 + U * l;
+            int64_t j[U];
+            if (p.neg) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) j[u] = (sb + u < quota) ? __ldg(p.neg + r * p.n_neg + sb + u) : gi;
+            } else {
+                const uint4 w = rng((uint32_t)p.n_iter, (uint32_t)(p.n_iter >> 32) ^ (uint32_t)(gi >> 32), (uint32_t)gi,
+                                    (uint32_t)(sb >> 2));
+                const uint32_t wv[U] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    int64_t t = (int64_t)(((uint64_t)wv[u] * (uint64_t)(p.n_total - 1)) >> 32);
+                    j[u] = t + ((t >= gi) ? 1 : 0);  // NE base.py:636
+                }
+            }
+            float2 zn[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (sb + u < quota) zn[u] = __ldg(p.Zin + j[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (sb + u < quota) {
+                    const float dx = __fsub_rn(zi.x, zn[u].x), dy = __fsub_rn(zi.y, zn[u].y);
+                    const float D = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                    const float den = __fadd_rn(1.0f, __fmul_rn(p.a, powf(D, p.b)));  // umap.py:273
+                    const float coef = __fmul_rn(__frcp_rn(__fmul_rn(__fadd_rn(D, 1e-3f), den)), p.neg_two_b);
+                    rx = fmaf(dx, coef, rx);
+                    ry = fmaf(dy, coef, ry);
+                }
+            }
+        }
+        rx = group_sum(rx, gmask);
+        ry = group_sum(ry, gmask);
+        rx = fminf(fmaxf(rx, -4.0f), 4.0f);  // umap.py:291
+        ry = fminf(fmaxf(ry, -4.0f), 4.0f);
+        if (l == 0) {
+            const float g0 = __fadd_rn(__fmul_rn(p.lam, gx), __fmul_rn(p.rep, rx));
+            const float g1 = __fadd_rn(__fmul_rn(p.lam, gy), __fmul_rn(p.rep, ry));
+            float2 zo;
+            zo.x = fmaf(-p.lr, g0, zi.x);
+            zo.y = fmaf(-p.lr, g1, zi.y);
+            p.Zout[gi] = zo;
+            if (p.grad_out) p.grad_out[r] = make_float2(g0, g1);
+            gn_local += (double)g0 * g0 + (double)g1 * g1;
+            saw_nan |= (zo.x != zo.x) || (zo.y != zo.y);
+            n_act += active;
+            n_neg_used += quota;
         }
     }
+    block_flush(l == 0, gn_local, saw_nan, n_act, n_neg_used, p);
 }
 
 static int launch_step(const UmapStepParams& p, int precise, cudaStream_t st) {
-    int64_t blocks = (p.n_local + kStepWarps - 1) / kStepWarps;
-    const int64_t cap = (int64_t)kNumSMs * 32;  // persistent-style cap: 8 CTAs x 4 waves per SM
-    if (blocks > cap) blocks = cap;
-    if (precise) umap_step_kernel<true><<<(unsigned)blocks, kStepWarps * 32, 0, st>>>(p);
-    else umap_step_kernel<false><<<(unsigned)blocks, kStepWarps * 32, 0, st>>>(p);
+    if (precise) {
+        int64_t blocks = (p.n_local + kStepWarps - 1) / kStepWarps;
+        const int64_t cap = (int64_t)kNumSMs * 32;
+        if (blocks > cap) blocks = cap;
+        umap_step_kernel<true><<<(unsigned)blocks, kStepWarps * 32, 0, st>>>(p);
+    } else {
+        const int rows_per_block = kV2Threads / G;
+        int64_t blocks = (p.n_local + rows_per_block - 1) / rows_per_block;
+        const int64_t cap = (int64_t)kNumSMs * 8 * 4;  // grid-stride beyond 4 waves of 8 resident CTAs per SM
+        if (blocks > cap) blocks = cap;
+        umap_step_kernel_v2<<<(unsigned)blocks, kV2Threads, 0, st>>>(p);
+    }
     TDR_LAUNCH_CHECK();
     return TDR_OK;
 }
