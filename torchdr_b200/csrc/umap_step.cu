@@ -40,7 +40,8 @@ struct UmapStepParams {
 // would otherwise serialise in L2.
 __device__ __forceinline__ void block_flush(bool leader, double gn, bool saw_nan, unsigned long long n_act,
                                             unsigned long long n_neg, const UmapStepParams& p) {
-    if (!p.gnorm_sq && !p.nan_flag && !p.stats) return;  // uniform
+    if (p.nan_flag && leader && saw_nan) atomicExch(p.nan_flag, 1);  // rare: no reduction needed
+    if (!p.gnorm_sq && !p.stats) return;  // uniform: the common per-iteration case has no block barrier
     __shared__ double s_gn;
     __shared__ unsigned long long s_cnt[2];
     __shared__ int s_nan;
@@ -299,8 +300,22 @@ __global__ void __launch_bounds__(kV2Threads, 4) umap_step_kernel_v2(const UmapS
     block_flush(l == 0, gn_local, saw_nan, n_act, n_neg_used, p);
 }
 
+}  // namespace tdr
+#include "umap_step_fast.cuh"
+namespace tdr {
+
+// precise: 0 = throughput kernel (umap_step_fast.cuh), 1 = parity kernel (fp64 pow, one warp per row),
+//          2 = umap_step_kernel_v2 (libdevice powf; kept as the measured baseline of profiles/r1_step_kernel.md)
 static int launch_step(const UmapStepParams& p, int precise, cudaStream_t st) {
-    if (precise) {
+    if (precise == 0) {
+        int64_t blocks = (p.n_local + kFastGroups - 1) / kFastGroups;
+        const int64_t cap = (int64_t)kNumSMs * 4 * 8;  // 4 resident CTAs per SM, grid-stride beyond 8 waves
+        if (blocks > cap) blocks = cap;
+        umap_step_kernel_fast<<<(unsigned)blocks, kFastThreads, 0, st>>>(p);
+        TDR_LAUNCH_CHECK();
+        return TDR_OK;
+    }
+    if (precise == 1) {
         int64_t blocks = (p.n_local + kStepWarps - 1) / kStepWarps;
         const int64_t cap = (int64_t)kNumSMs * 32;
         if (blocks > cap) blocks = cap;
