@@ -76,6 +76,14 @@ TDR_API int tdr_pairwise_full_f32(const float* X, int64_t n, const float* Y, int
                           int metric, int exclude_diag, float* C /*[n,m]*/,
                           void* ws, size_t ws_bytes, tdr_stream_t stream);
 
+/* pairwise_distances_indexed, per-query key lists (distance/base.py:252-405, 2-D key_indices):
+ * out[i,s] = dist(X[query_idx[i]], Y[key_idx[i,s]]) in the exact-difference form of base.py:384-385.
+ * query_idx may be NULL (identity); key_idx is int32 or int64 [nq,k]; negative keys wrap as in torch. */
+TDR_API int tdr_indexed_dist_f32(const float* X, const int64_t* query_idx, int64_t nq,
+                                 const float* Y, int64_t ny, int d,
+                                 const void* key_idx, int key_is_int64, int k, int metric,
+                                 float* out /*[nq,k]*/, tdr_stream_t stream);
+
 /* ---- (ii) per-row bandwidth search --------------------------------------
  * UMAPAffinity rows: rho = row min, sigma by bracket+bisection
  * (torchdr/affinity/knn_normalized.py:445-468, utils/root_search.py:17-198),
@@ -96,6 +104,17 @@ TDR_API int tdr_entropic_affinity_f32(const float* C /*[n,k]*/, int64_t n, int k
                               int max_iter,
                               float* logP /*[n,k]*/, float* eps /*[n]*/, float* log_norm /*[n]*/,
                               tdr_stream_t stream);
+
+/* Dense variant (EntropicAffinity(sparsity=False), entropic.py:266-268): C is the full
+ * [n_rows, m] distance matrix (tdr_pairwise_full_f32, diagonal carrying the 1e12 penalty).  One
+ * CTA per row, one streaming pass over the row per bisection step.  logP may be NULL (only eps /
+ * log_norm wanted) or alias C (in place). */
+TDR_API int tdr_entropic_dense_f32(const float* C /*[n_rows,m]*/, int64_t n_rows, int64_t m,
+                                   float target_entropy, float log_n_total,
+                                   int use_bounds, float b_num, float b_den, float b_lr, float b_logp1,
+                                   int max_iter,
+                                   float* logP /*[n_rows,m] or NULL*/, float* eps, float* log_norm,
+                                   tdr_stream_t stream);
 
 /* Fused (i)+(ii): kNN mainloop with the UMAP sigma/rho search in the epilogue
  * (the "affinity kernel" of BASELINE.json).  Same workspace as tdr_knn_f32. */

@@ -183,6 +183,12 @@ def main():
          log_norm=ea.log_normalization_.squeeze(-1), begin=b0, end=b1,
          logP_nobounds=logP_nb, eps_nobounds=ea2.eps_, perplexity=perp)
 
+    # dense route (sparsity=False, entropic.py:266-268): full N x N log-affinity
+    ead = EntropicAffinity(perplexity=perp, max_iter=100, backend=None, device="cpu", sparsity=False)
+    logPd = ead(X, log=True, return_indices=False)
+    save("entropic_dense_n300_d16_p10", X=X, logP=logPd, eps=ead.eps_, log_norm=ead.log_normalization_.squeeze(-1),
+         perplexity=perp)
+
     # perplexity 30 on the C1-like data (k=90)
     X = blobs(2000, 50, 10, 2)
     ea = EntropicAffinity(perplexity=30, max_iter=100, backend=None, device="cpu")

@@ -170,6 +170,32 @@ def test_entropic_rows(ops, name, perp):
     torch.testing.assert_close(H, torch.full((n,), np.log(perp) + 1, dtype=torch.float32), atol=1e-3, rtol=0)
 
 
+def test_entropic_dense(ops):
+    """EntropicAffinity(sparsity=False): dense N x N rows (BASELINE config 3 route) vs the reference."""
+    import torchdr_b200 as tb
+    from torchdr_b200.affinity import entropic_bound_scalars
+
+    g = golden("entropic_dense_n300_d16_p10")
+    X = t(g["X"])
+    C = oracle.pairwise_full(X, None, "sqeuclidean", True)
+    logn = float(torch.log(torch.tensor(300.0)))
+    target = float(torch.log(torch.tensor(10)) + 1)
+    logP, eps, ln = ops.entropic_dense_rows(_cuda(C), target, logn, entropic_bound_scalars(300, 10), 100, inplace=False)
+    torch.testing.assert_close(eps.cpu(), t(g["eps"]), rtol=2e-5, atol=0)
+    off = ~torch.eye(300, dtype=torch.bool)
+    torch.testing.assert_close(logP.cpu()[off], t(g["logP"])[off], rtol=2e-5, atol=1e-4)
+    assert bool((logP.cpu().diag() < -1e6).all())
+    # through the seam, with the engine's own distance matrix
+    ea = tb.EntropicAffinity(perplexity=10, max_iter=100, sparsity=False)
+    lp, idx = ea(X, log=True, return_indices=True)
+    assert idx is None and lp.shape == (300, 300)
+    torch.testing.assert_close(ea.eps_.cpu(), t(g["eps"]), rtol=2e-3, atol=0)
+    l = lp.cpu() + logn
+    torch.testing.assert_close(l.exp().sum(1), torch.ones(300), atol=1e-3, rtol=0)  # tests/test_affinity.py:204-210
+    H = -(l.exp() * (l - 1)).masked_fill(~off, 0).sum(1)
+    torch.testing.assert_close(H, torch.full((300,), np.log(10.0) + 1, dtype=torch.float32), atol=1e-3, rtol=0)
+
+
 def test_entropic_p30_k90(ops):
     from torchdr_b200.affinity import entropic_bound_scalars
 
@@ -427,6 +453,29 @@ def test_pairwise_distances_seam():
     assert torch.equal(Ic, I[100:200])
     with pytest.raises(ValueError, match="k cannot be None"):
         tb.pairwise_distances(X, distributed_ctx=ctx)
+
+
+def test_pairwise_distances_indexed_seam():
+    """The reference's own check (tests/test_utils.py:227-241): indexed == gather of the full matrix, and the
+    exact-difference arithmetic of distance/base.py:384-385 bit for bit."""
+    import torchdr_b200 as tb
+
+    g = torch.Generator().manual_seed(0)
+    Z = torch.randn(500, 2, generator=g)
+    key = torch.randint(0, 500, (200, 37), generator=g)
+    key[5, 3] = -1  # the -1 padding of the symmetrised affinity wraps to the last row (umap.py:236-264)
+    q = torch.randperm(500, generator=g)[:200]
+    ref = torch.sum((Z[q].unsqueeze(1) - Z[key.long()]) ** 2, dim=-1)
+    out = tb.pairwise_distances_indexed(Z, query_indices=q, key_indices=key, metric="sqeuclidean")
+    assert torch.equal(out.cpu(), ref)
+    out32 = tb.pairwise_distances_indexed(Z, query_indices=q, key_indices=key.int().clamp(min=0), metric="euclidean")
+    torch.testing.assert_close(out32.cpu(), torch.sum((Z[q].unsqueeze(1) - Z[key.clamp(min=0)]) ** 2, dim=-1).sqrt())
+    X = blobs(300, 16, 4, 2)
+    full = tb.pairwise_distances(X, metric="sqeuclidean").cpu()
+    keys = torch.randint(0, 300, (300, 9), generator=g)
+    ind = tb.pairwise_distances_indexed(X, key_indices=keys, metric="sqeuclidean").cpu()
+    rel = (ind - full.gather(1, keys)).abs().sum() / full.gather(1, keys).abs().sum()
+    assert float(rel) < 1e-5  # check_similarity of tests/test_utils.py:241
 
 
 def test_affinity_seams():

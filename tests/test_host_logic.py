@@ -140,6 +140,13 @@ def _worker(rank, world, port, q):
         all_gather_rows(Z, bounds, rank)
         want = torch.arange(n, dtype=torch.float32)[:, None] + torch.tensor([0.0, 0.25])
         ok = ok and torch.equal(Z, want)
+        # equal chunks take the in-place single-collective path
+        b10 = all_bounds(10, world)
+        s10, e10 = b10[rank]
+        Z10 = torch.full((10, 2), -1.0)
+        Z10[s10:e10] = torch.arange(s10, e10, dtype=torch.float32)[:, None] + torch.tensor([0.0, 0.5])
+        all_gather_rows(Z10, b10, rank)
+        ok = ok and torch.equal(Z10, torch.arange(10, dtype=torch.float32)[:, None] + torch.tensor([0.0, 0.5]))
         # index >= 2^24 survives the exchange (the reference casts indices to fp32, sparse.py:286-293)
         big = torch.tensor([2**24 + 1 + rank], dtype=torch.int64)
         cnt = torch.zeros(world, dtype=torch.int64)

@@ -152,6 +152,15 @@ def test_entropic_p30_k90():
     assert oracle.clamp_neighbor_param(1, 2000) == 2
 
 
+def test_entropic_dense_rows():
+    # sparsity=False (entropic.py:266-268): the same row routine on the full matrix with the 1e12 diagonal
+    g = golden("entropic_dense_n300_d16_p10")
+    C = oracle.pairwise_full(t(g["X"]), None, "sqeuclidean", True)
+    logP, eps, ln = oracle.entropic_affinity_rows(C, int(g["perplexity"]))
+    assert torch.equal(eps, t(g["eps"])) and torch.equal(ln, t(g["log_norm"]))
+    assert torch.equal(logP, t(g["logP"]))
+
+
 def test_largevis_run():
     g = golden("largevis_n300_d16_p10")
     seed = int(g["seed"])

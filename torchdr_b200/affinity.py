@@ -191,13 +191,20 @@ class EntropicAffinity(_SparseAffinityBase):
                          compile=compile, sparsity=sparsity, distributed=distributed, _pre_processed=_pre_processed)
 
     def _compute_sparse_log_affinity(self, X):
-        if not self.sparsity:
-            raise NotImplementedError(
-                "[TorchDR-B200] EntropicAffinity(sparsity=False) (dense N x N, BASELINE config 3) is not built yet."
-            )
         X = self._prepare(X)
         n = X.shape[0]
         perp = check_neighbor_param(self.perplexity, n)  # entropic.py:257
+        if not self.sparsity:
+            # dense N x N route (entropic.py:266-268, BASELINE config 3): full distance matrix, then one CTA
+            # per row streams it once per bisection step; log_P overwrites C in place (4 N^2 bytes)
+            C = ops.pairwise_full(X, None, metric=self.metric, exclude_diag=bool(self.zero_diag))
+            target = float(torch.log(torch.tensor(perp)) + 1)
+            log_n = float(torch.log(torch.tensor(float(n), dtype=torch.float32)))
+            logP, eps, log_norm = ops.entropic_dense_rows(C, target, log_n, entropic_bound_scalars(n, perp),
+                                                          self.max_iter, inplace=True)
+            self.eps_ = eps
+            self.log_normalization_ = log_norm.unsqueeze(1)
+            return logP, None
         k = check_neighbor_param(3 * perp, n)  # entropic.py:259-265
         if k > _lib.TDR_MAX_K:
             raise NotImplementedError(f"[TorchDR-B200] 3*perplexity={k} exceeds the engine limit {_lib.TDR_MAX_K}.")

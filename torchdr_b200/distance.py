@@ -93,3 +93,26 @@ def pairwise_distances(X, Y=None, metric="euclidean", backend=None, exclude_diag
         C = ops.pairwise_full(X, None if same else Y, metric=metric, exclude_diag=bool(same and exclude_diag))
         idx = None
     return (C, idx) if return_indices else C
+
+
+def pairwise_distances_indexed(X, query_indices=None, key_indices=None, Y=None, metric="sqeuclidean", backend=None,
+                               device="auto"):
+    """``torchdr/distance/base.py:252-405`` for the case the neighbor-embedding losses use: per-query key lists
+    (2-D ``key_indices``), optional 1-D ``query_indices``; returns ``[n_queries, n_keys]`` in the exact-difference
+    form (``base.py:384-385``).  Other index shapes are outside the accelerated path."""
+    _check_metric(metric)
+    X = _to_device_tensor(X, device)
+    if X.dtype != torch.float32:
+        X = X.float()
+    Yd = X if Y is None else _to_device_tensor(Y, device).to(X.device).float()
+    if key_indices is None or key_indices.dim() != 2:
+        raise NotImplementedError("[TorchDR-B200] pairwise_distances_indexed needs 2-D key_indices (per-query keys).")
+    if query_indices is not None and query_indices.dim() != 1:
+        raise NotImplementedError("2D query indices not yet supported")  # base.py:340
+    key = key_indices.to(X.device)
+    if key.dtype not in (torch.int32, torch.int64):
+        key = key.long()
+    q = None if query_indices is None else query_indices.to(X.device)
+    n_q = X.shape[0] if q is None else q.numel()
+    assert key.shape[0] == n_q, f"key_indices first dim {key.shape[0]} must match number of queries {n_q}"  # base.py:349-352
+    return ops.indexed_distances(X, key, Y=Yd, query_idx=q, metric=metric)

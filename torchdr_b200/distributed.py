@@ -105,6 +105,10 @@ def all_gather_rows(Z_full: torch.Tensor, bounds, rank: int, group=None):
     longest = max(e - s for s, e in bounds)
     q = Z_full.shape[1]
     s, e = bounds[rank]
+    if all(b - a == longest for a, b in bounds) and Z_full.is_contiguous():
+        # equal chunks: in-place all-gather, each rank's slice of the output is its own input (no staging copies)
+        dist.all_gather_into_tensor(Z_full, Z_full[s:e], group=group)
+        return Z_full
     send = torch.zeros((longest, q), dtype=Z_full.dtype, device=Z_full.device)
     send[: e - s] = Z_full[s:e]
     recv = torch.empty((world * longest, q), dtype=Z_full.dtype, device=Z_full.device)

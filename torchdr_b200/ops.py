@@ -99,6 +99,42 @@ def entropic_affinity_rows(C, target_entropy, log_n_total, bounds=None, max_iter
     return logP, eps, log_norm
 
 
+def indexed_distances(X, key_idx, Y=None, query_idx=None, metric="sqeuclidean"):
+    """out[i, s] = dist(X[query_idx[i]], Y[key_idx[i, s]]) (exact-difference form)."""
+    X = _dev_f32(X, "X")
+    Y = X if Y is None else _dev_f32(Y, "Y")
+    key_idx = key_idx.contiguous()
+    assert key_idx.dtype in (torch.int32, torch.int64) and key_idx.dim() == 2
+    nq, k = key_idx.shape
+    if query_idx is not None:
+        query_idx = query_idx.to(torch.int64).contiguous()
+        assert query_idx.numel() == nq
+    out = torch.empty((nq, k), dtype=torch.float32, device=X.device)
+    with torch.cuda.device(X.device):
+        check(_lib.load().tdr_indexed_dist_f32(ptr(X), ptr(query_idx), nq, ptr(Y), Y.shape[0], X.shape[1], ptr(key_idx),
+                                               int(key_idx.dtype == torch.int64), k, _lib.METRIC_IDS[metric], ptr(out),
+                                               stream()), "tdr_indexed_dist_f32")
+    return out
+
+
+def entropic_dense_rows(C, target_entropy, log_n_total, bounds=None, max_iter=100, inplace=True, want_logP=True):
+    """Dense rows: C [n_rows, m] full distances -> (logP [n_rows, m] or None, eps, log_norm).
+
+    ``inplace`` overwrites C with log_P (the matrix is 4 N^2 bytes: 40 GB at N = 100 k)."""
+    C = _dev_f32(C, "C")
+    n_rows, m = C.shape
+    eps = torch.empty((n_rows,), dtype=torch.float32, device=C.device)
+    log_norm = torch.empty((n_rows,), dtype=torch.float32, device=C.device)
+    logP = (C if inplace else torch.empty_like(C)) if want_logP else None
+    b = bounds if bounds is not None else (0.0, 0.0, 0.0, 0.0)
+    with torch.cuda.device(C.device):
+        check(_lib.load().tdr_entropic_dense_f32(ptr(C), n_rows, m, float(target_entropy), float(log_n_total),
+                                                 int(bounds is not None), float(b[0]), float(b[1]), float(b[2]),
+                                                 float(b[3]), max_iter, ptr(logP), ptr(eps), ptr(log_norm), stream()),
+              "tdr_entropic_dense_f32")
+    return logP, eps, log_norm
+
+
 def symmetrize_csr(Pm, idx, row0, n_total, ext=None, transpose_local=True):
     """Q = P + P^T - P o P^T for the local rows -> (rowptr i64[n+1], col i32[nnz], val f32[nnz])."""
     Pm = _dev_f32(Pm, "P")
