@@ -20,6 +20,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <type_traits>
 
@@ -115,6 +117,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 // kind::f16, A/B = F16 (0), D = F32 (1), both K-major, N = 128, M = 128
 constexpr uint32_t kInstrDesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t kInstrDescN256 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 // ------------------------------------------------------------------ pre-pass: scale + fp16 split
 __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ X, int64_t n, int* __restrict__ out_bits) {
@@ -201,6 +204,8 @@ struct Params {
     const int* absmax_bits;
     int k, kpad, atoms, stages;
     int exclude_self, metric, fused, max_iter;
+    int dual;   // 1: two epilogue warpgroups (384 threads), each with its own top-k lists, on alternate tiles
+    int debug;  // timing experiments only (env TDR_TC_DEBUG): 1 = skip filter, 2 = skip MMAs, 4 = skip database TMA
     float* out_dist;
     int32_t* out_idx;
     float* P;
@@ -208,7 +213,7 @@ struct Params {
     float* sigma;
 };
 
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(384, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
               const __grid_constant__ CUtensorMap map_db_hi, const __grid_constant__ CUtensorMap map_db_lo,
               const Params prm) {
@@ -218,9 +223,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
     const int a_bytes = atoms * 2 * TILE_BYTES;  // hi + lo
     unsigned char* a_tiles = smem;                    // [atoms][hi, lo][16 KB]
     unsigned char* b_tiles = smem + a_bytes;          // [stages][atoms][hi, lo][16 KB]
-    float* ld_s = reinterpret_cast<float*>(b_tiles + (size_t)stages * a_bytes);  // [128][kpad]
-    int* li_s = reinterpret_cast<int*>(ld_s + BM * kpad);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(li_s + BM * kpad);
+    const int nl = 1 + prm.dual;  // list sets
+    float* ld_s = reinterpret_cast<float*>(b_tiles + (size_t)stages * a_bytes);  // [nl][128][kpad]
+    int* li_s = reinterpret_cast<int*>(ld_s + nl * BM * kpad);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(li_s + nl * BM * kpad);
     // barrier slots: 0 a_full | 1..S full | 1+S..2S empty | 2S+1, 2S+2 tmem_full | 2S+3, 2S+4 tmem_empty
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 5);
 
@@ -239,7 +245,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(BAR(T_FULL + s), 1);
-            mbar_init(BAR(T_EMPTY + s), 128);
+            mbar_init(BAR(T_EMPTY + s), 128u * (uint32_t)nl);  // every epilogue thread of every warpgroup arrives
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -248,7 +254,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    for (int i = tid; i < BM * kpad; i += NT) {
+    for (int i = tid; i < nl * BM * kpad; i += (int)blockDim.x) {
         ld_s[i] = INFINITY;
         li_s[i] = 0x7fffffff;
     }
@@ -271,6 +277,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                 const int s = (int)(t % stages);
                 const uint32_t ph = (uint32_t)((t / stages) & 1);
                 mbar_wait(BAR(B_EMPTY + s), ph ^ 1u);
+                if ((prm.debug & 4) && t >= stages) {
+                    mbar_arrive(BAR(B_FULL + s));
+                    continue;
+                }
                 mbar_expect_tx(BAR(B_FULL + s), (uint32_t)a_bytes);
                 unsigned char* dst = b_tiles + (size_t)s * a_bytes;
                 for (int a = 0; a < atoms; ++a) {
@@ -294,7 +304,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                 const uint32_t d_big = tmem_base + (uint32_t)(as * 256);
                 const uint32_t d_small = d_big + 128u;
                 const unsigned char* bt = b_tiles + (size_t)s * a_bytes;
-                for (int a = 0; a < atoms; ++a) {
+                for (int a = 0; a < ((prm.debug & 2) ? 0 : atoms); ++a) {
                     const uint64_t a_hi = make_smem_desc(smem_u32(a_tiles + (a * 2 + 0) * TILE_BYTES));
                     const uint64_t a_lo = make_smem_desc(smem_u32(a_tiles + (a * 2 + 1) * TILE_BYTES));
                     const uint64_t b_hi = make_smem_desc(smem_u32(bt + (a * 2 + 0) * TILE_BYTES));
@@ -303,8 +313,11 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                     for (int kk = 0; kk < KATOM / 16; ++kk) {
                         const uint64_t adv = (uint64_t)(kk * 2);  // 16 fp16 = 32 B -> +2 in the >>4 address field
                         const uint32_t acc = (a | kk) ? 1u : 0u;
-                        tc_mma_f16(d_big, a_hi + adv, b_hi + adv, kInstrDesc, acc);
-                        tc_mma_f16(d_small, a_hi + adv, b_lo + adv, kInstrDesc, acc);
+                        // The kernel is bound by shared-memory operand bandwidth (A + B are both read from smem for
+                        // every MMA).  hi.hi and hi.lo share the A operand: the database hi and lo tiles of an atom
+                        // are adjacent in smem (16 KB + 16 KB = 256 K-major rows), so ONE N = 256 MMA produces
+                        // [hi.hi | hi.lo] into TMEM columns [0,128) | [128,256) with a single read of A_hi.
+                        tc_mma_f16(d_big, a_hi + adv, b_hi + adv, kInstrDescN256, acc);
                         tc_mma_f16(d_small, a_lo + adv, b_hi + adv, kInstrDesc, 1u);
                     }
                 }
@@ -318,15 +331,19 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
         // distances of a TMEM chunk are formed as independent chains (2 FADD + 1 FFMA + 1 FMNMX each),
         // only their minimum is compared with the row's running k-th best, and the next chunk's
         // tcgen05.ld is in flight meanwhile.  The per-element test runs only when that minimum wins.
-        const int row = tid - 128;  // == TMEM lane; warp (4..7) % 4 selects lanes 32*(warp-4)..+31
+        // warps 4-7 = warpgroup 0, warps 8-11 = warpgroup 1 (dual mode): a warp may only touch TMEM lanes
+        // 32*(warp % 4)..+31, so both groups see all 128 rows; they take alternate tiles (= accumulator stages)
+        // and keep separate lists, merged after the sweep.
+        const int wg = (warp - 4) >> 2;
+        const int row = (tid - 128) & 127;  // == TMEM lane
         const int64_t gq = q0 + row;
         const int64_t self = prm.exclude_self ? prm.q_row0 + gq : -1;
         const float qn = gq < prm.nq ? __ldg(prm.qn + gq) : 0.0f;
         const int e = scale_exponent(__int_as_float(__ldg(prm.absmax_bits)));
         const float neg2s = -2.0f * ldexpf(1.0f, -2 * e);  // power of two: the FFMA below rounds once, like sub(add, 2*dot)
-        const uint32_t my_d = smem_u32(ld_s + row * kpad), my_i = smem_u32(li_s + row * kpad);
+        const uint32_t my_d = smem_u32(ld_s + (wg * BM + row) * kpad), my_i = smem_u32(li_s + (wg * BM + row) * kpad);
         float tau = INFINITY;
-        const uint32_t lane_addr = (uint32_t)((warp - 4) * 32) << 16;
+        const uint32_t lane_addr = (uint32_t)(((warp - 4) & 3) * 32) << 16;
 
         auto filter = [&](uint32_t(&big)[32], uint32_t(&small)[32], int col_base) {
             float m0 = INFINITY, m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;
@@ -356,30 +373,44 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
             }
         };
 
+        // Dual mode: BOTH warpgroups work on every tile, each on half of its columns.  With only two accumulator
+        // stages in TMEM the MMAs of tile t+2 wait for the epilogue of tile t, so what matters is the epilogue
+        // LATENCY per tile (measured: alternate-tile assignment gave (T_mma + 2 T_epi)/2 per tile).
+        const int c_beg = prm.dual ? 64 * wg : 0;   // first column of this warpgroup's share
+        const int n_ch = prm.dual ? 2 : 4;          // 32-column chunks in the share
         for (int64_t t = 0; t < n_tiles; ++t) {
             const int as = (int)(t & 1);
             const uint32_t aph = (uint32_t)((t >> 1) & 1);
+            // database norms of the NEXT tile: pull this warpgroup's lines into L1 now, so that the filter's
+            // broadcast loads do not each pay an L2 round trip
+            if (lane < n_ch && t + 1 < n_tiles && !(prm.debug & 16))
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(prm.dbn + (t + 1) * BN + c_beg + lane * 32));
             mbar_wait(BAR(T_FULL + as), aph);
             tc_fence_after();
-            const int col0 = (int)(t * BN);
-            const uint32_t tb = tmem_base + lane_addr + (uint32_t)(as * 256);
+            if (prm.debug & 1) {
+                tc_fence_before();
+                mbar_arrive(BAR(T_EMPTY + as));
+                continue;
+            }
+            const int col0 = (int)(t * BN) + c_beg;
+            const uint32_t tb = tmem_base + lane_addr + (uint32_t)(as * 256 + c_beg);
             uint32_t bigA[32], smallA[32], bigB[32], smallB[32];
             tc_ld32(tb + 0, bigA);
             tc_ld32(tb + 128, smallA);
             tc_ld_wait(bigA, smallA);
-            tc_ld32(tb + 32, bigB);
-            tc_ld32(tb + 160, smallB);
-            filter(bigA, smallA, col0);
-            tc_ld_wait(bigB, smallB);
-            tc_ld32(tb + 64, bigA);
-            tc_ld32(tb + 192, smallA);
-            filter(bigB, smallB, col0 + 32);
-            tc_ld_wait(bigA, smallA);
-            tc_ld32(tb + 96, bigB);
-            tc_ld32(tb + 224, smallB);
-            filter(bigA, smallA, col0 + 64);
-            tc_ld_wait(bigB, smallB);
-            filter(bigB, smallB, col0 + 96);
+#pragma unroll 1
+            for (int c = 0; c < n_ch; c += 2) {
+                tc_ld32(tb + 32 * (c + 1), bigB);
+                tc_ld32(tb + 128 + 32 * (c + 1), smallB);
+                filter(bigA, smallA, col0 + 32 * c);
+                tc_ld_wait(bigB, smallB);
+                if (c + 2 < n_ch) {
+                    tc_ld32(tb + 32 * (c + 2), bigA);
+                    tc_ld32(tb + 128 + 32 * (c + 2), smallA);
+                }
+                filter(bigB, smallB, col0 + 32 * (c + 1));
+                if (c + 2 < n_ch) tc_ld_wait(bigA, smallA);
+            }
             tc_fence_before();
             mbar_arrive(BAR(T_EMPTY + as));
         }
@@ -392,13 +423,37 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
 
-    // ---- write back; fused: rho/sigma search on the finished rows (all 8 warps, 16 rows each) ----
-    for (int rr = 0; rr < 16; ++rr) {
-        const int row = warp * 16 + rr;
+    // ---- write back; fused: rho/sigma search on the finished rows (one warp per row) ----
+    const int n_warps = (int)blockDim.x >> 5;
+    for (int row = warp; row < BM; row += n_warps) {
         const int64_t gr = q0 + row;
         if (gr >= prm.nq) continue;
-        const float* ldr = ld_s + row * kpad;
-        const int* lir = li_s + row * kpad;
+        float* ldr = ld_s + row * kpad;
+        int* lir = li_s + row * kpad;
+        if (nl == 2) {
+            // merge the two sorted lists of the row (disjoint index sets) by (distance, index) into list 0
+            const float* ldb = ld_s + (BM + row) * kpad;
+            const int* lib = li_s + (BM + row) * kpad;
+            const float da = lane < k ? ldr[lane] : INFINITY, db = lane < k ? ldb[lane] : INFINITY;
+            const int ia = lane < k ? lir[lane] : 0x7fffffff, ib = lane < k ? lib[lane] : 0x7fffffff;
+            int ra = lane, rb = lane;
+            for (int j = 0; j < k; ++j) {
+                const float xb = ldb[j], xa = ldr[j];
+                const int yb = lib[j], ya = lir[j];
+                ra += (xb < da || (xb == da && yb < ia)) ? 1 : 0;
+                rb += (xa < db || (xa == db && ya < ib)) ? 1 : 0;
+            }
+            __syncwarp();
+            if (lane < k && ra < k) {
+                ldr[ra] = da;
+                lir[ra] = ia;
+            }
+            if (lane < k && rb < k) {
+                ldr[rb] = db;
+                lir[rb] = ib;
+            }
+            __syncwarp();
+        }
         if (lane < k) {
             // lists are kept in the squared domain; euclidean = sqrt(clamp(., 0)) (torch.py:92-95) is monotone
             float dv = ldr[lane];
@@ -547,13 +602,20 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
     prm.metric = metric;
     prm.fused = fused;
     prm.max_iter = max_iter;
+    {
+        const char* dbg = getenv("TDR_TC_DEBUG");
+        prm.debug = dbg ? atoi(dbg) : 0;
+    }
     prm.out_dist = out_dist;
     prm.out_idx = out_idx;
     prm.P = P;
     prm.rho = rho;
     prm.sigma = sigma;
     const size_t stage_bytes = (size_t)atoms * 2 * TILE_BYTES;
-    const size_t fixed = stage_bytes + (size_t)BM * k * 8 + 512 + 1024;
+    // two epilogue warpgroups when a second set of lists still leaves room for two TMA stages
+    prm.dual = ((size_t)3 * stage_bytes + (size_t)2 * BM * k * 8 + 512 + 1024 <= (size_t)227 * 1024) ? 1 : 0;
+    if (prm.debug & 32) prm.dual = 0;
+    const size_t fixed = stage_bytes + (size_t)(1 + prm.dual) * BM * k * 8 + 512 + 1024;
     int stages = (int)((227 * 1024 - fixed) / stage_bytes);
     if (stages > 6) stages = 6;
     if (stages < 2) {
@@ -567,7 +629,7 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
         TDR_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    knn_tc_kernel<<<(unsigned)((nq + BM - 1) / BM), NT, smem, st>>>(mq_hi, mq_lo, mdb_hi, mdb_lo, prm);
+    knn_tc_kernel<<<(unsigned)((nq + BM - 1) / BM), prm.dual ? 384 : 256, smem, st>>>(mq_hi, mq_lo, mdb_hi, mdb_lo, prm);
     TDR_LAUNCH_CHECK();
     return TDR_OK;
 }
