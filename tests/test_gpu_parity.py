@@ -525,6 +525,37 @@ def test_estimators_end_to_end():
         tb.UMAP(n_neighbors=700).fit_transform(X)
 
 
+def test_estimator_edge_cases():
+    """Input handling the reference covers: duplicates (base.py:132-146), non-finite input, too few samples,
+    torch / numpy round trip, tiny inputs, ragged sizes around the 128-row tiles."""
+    import torchdr_b200 as tb
+
+    g = torch.Generator().manual_seed(0)
+    X = blobs(257, 12, 3, 8)
+    Xdup = torch.cat([X, X[:40]])  # 40 exact duplicates
+    Z = tb.UMAP(n_neighbors=10, max_iter=30, init="normal", random_state=0).fit_transform(Xdup)
+    assert Z.shape == (297, 2) and torch.equal(Z[:40], Z[257:])  # duplicates share their embedding
+    Zn = tb.UMAP(n_neighbors=10, max_iter=5, init="normal", process_duplicates=False).fit_transform(Xdup.numpy())
+    assert isinstance(Zn, np.ndarray) and np.isfinite(Zn).all()
+    bad = X.clone()
+    bad[3, 2] = float("nan")
+    with pytest.raises(ValueError, match="NaN or infinite"):
+        tb.UMAP(n_neighbors=10).fit_transform(bad)
+    with pytest.raises(ValueError, match="smaller than perplexity"):
+        tb.TSNE(perplexity=300).fit_transform(X)
+    for n in (17, 128, 129):  # around one tile
+        Xs = blobs(n, 5, 2, n)
+        Zs = tb.UMAP(n_neighbors=5, max_iter=10, init="normal", random_state=1).fit_transform(Xs)
+        assert Zs.shape == (n, 2) and bool(torch.isfinite(Zs).all())
+    # clamp of the neighbour parameter to [2, n-2] (utils/validation.py:223-244)
+    aff = tb.UMAPAffinity(n_neighbors=500, symmetrize=False)
+    P, I = aff(blobs(40, 4, 2, 1))
+    assert P.shape == (40, 38)
+    # float64 input is computed in fp32 like the rest of the path
+    Zd = tb.UMAP(n_neighbors=5, max_iter=5, init="normal").fit_transform(X.double())
+    assert Zd.shape == (257, 2)
+
+
 def test_umap_estimator_parity_hooks():
     """Drive the estimator like the reference's golden run (injected init + negatives through the hook)."""
     import torchdr_b200 as tb

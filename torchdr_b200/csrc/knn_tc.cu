@@ -34,7 +34,8 @@ constexpr int BM = 128, BN = 128, KATOM = 64;  // 64 fp16 = one 128-byte swizzle
 constexpr int NT = 256;
 constexpr int TILE_BYTES = BM * KATOM * 2;  // 16 KB: one [128 x 64] fp16 box
 constexpr int MAX_ATOMS = 2;                // d <= 128
-constexpr int MAX_K = 32;                   // top-k lists in shared memory next to 192 KB of tiles
+constexpr int MAX_K = 96;                   // top-k lists in shared memory next to the operand tiles
+constexpr int kMaxEpl = MAX_K / 32;
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -434,45 +435,71 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
             // merge the two sorted lists of the row (disjoint index sets) by (distance, index) into list 0
             const float* ldb = ld_s + (BM + row) * kpad;
             const int* lib = li_s + (BM + row) * kpad;
-            const float da = lane < k ? ldr[lane] : INFINITY, db = lane < k ? ldb[lane] : INFINITY;
-            const int ia = lane < k ? lir[lane] : 0x7fffffff, ib = lane < k ? lib[lane] : 0x7fffffff;
-            int ra = lane, rb = lane;
+            float da[kMaxEpl], db[kMaxEpl];
+            int ia[kMaxEpl], ib[kMaxEpl], ra[kMaxEpl], rb[kMaxEpl];
+#pragma unroll
+            for (int e = 0; e < kMaxEpl; ++e) {
+                const int p = lane + 32 * e;
+                da[e] = p < k ? ldr[p] : INFINITY;
+                db[e] = p < k ? ldb[p] : INFINITY;
+                ia[e] = p < k ? lir[p] : 0x7fffffff;
+                ib[e] = p < k ? lib[p] : 0x7fffffff;
+                ra[e] = rb[e] = p;
+            }
             for (int j = 0; j < k; ++j) {
                 const float xb = ldb[j], xa = ldr[j];
                 const int yb = lib[j], ya = lir[j];
-                ra += (xb < da || (xb == da && yb < ia)) ? 1 : 0;
-                rb += (xa < db || (xa == db && ya < ib)) ? 1 : 0;
+#pragma unroll
+                for (int e = 0; e < kMaxEpl; ++e) {
+                    ra[e] += (xb < da[e] || (xb == da[e] && yb < ia[e])) ? 1 : 0;
+                    rb[e] += (xa < db[e] || (xa == db[e] && ya < ib[e])) ? 1 : 0;
+                }
             }
             __syncwarp();
-            if (lane < k && ra < k) {
-                ldr[ra] = da;
-                lir[ra] = ia;
-            }
-            if (lane < k && rb < k) {
-                ldr[rb] = db;
-                lir[rb] = ib;
+#pragma unroll
+            for (int e = 0; e < kMaxEpl; ++e) {
+                const int p = lane + 32 * e;
+                if (p < k && ra[e] < k) {
+                    ldr[ra[e]] = da[e];
+                    lir[ra[e]] = ia[e];
+                }
+                if (p < k && rb[e] < k) {
+                    ldr[rb[e]] = db[e];
+                    lir[rb[e]] = ib[e];
+                }
             }
             __syncwarp();
         }
-        if (lane < k) {
+        for (int p = lane; p < k; p += 32) {
             // lists are kept in the squared domain; euclidean = sqrt(clamp(., 0)) (torch.py:92-95) is monotone
-            float dv = ldr[lane];
+            float dv = ldr[p];
             if (prm.metric == TDR_METRIC_EUCLIDEAN) dv = sqrtf(fmaxf(dv, 0.0f));
-            if (prm.out_dist) prm.out_dist[gr * k + lane] = dv;
-            prm.out_idx[gr * k + lane] = lir[lane];
+            if (prm.out_dist) prm.out_dist[gr * k + p] = dv;
+            prm.out_idx[gr * k + p] = lir[p];
         }
         if (prm.fused) {
-            UmapRow<1> u;  // k <= 32
-            u.k = k;
-            u.lane = lane;
-            u.target = log2f((float)k);
-            u.c[0] = u.valid(0) ? ldr[lane] : INFINITY;
-            u.init();
-            const float s = u.solve(prm.max_iter);
-            if (u.valid(0)) prm.P[gr * k + lane] = u.p(0, s);
-            if (lane == 0) {
-                prm.rho[gr] = u.rho;
-                prm.sigma[gr] = s;
+            auto run = [&](auto tag) {
+                constexpr int EPL = decltype(tag)::value;
+                UmapRow<EPL> u;
+                u.k = k;
+                u.lane = lane;
+                u.target = log2f((float)k);
+#pragma unroll
+                for (int e = 0; e < EPL; ++e) u.c[e] = u.valid(e) ? ldr[lane + 32 * e] : INFINITY;
+                u.init();
+                const float s = u.solve(prm.max_iter);
+#pragma unroll
+                for (int e = 0; e < EPL; ++e)
+                    if (u.valid(e)) prm.P[gr * k + lane + 32 * e] = u.p(e, s);
+                if (lane == 0) {
+                    prm.rho[gr] = u.rho;
+                    prm.sigma[gr] = s;
+                }
+            };
+            switch ((k + 31) / 32) {
+                case 1: run(std::integral_constant<int, 1>{}); break;
+                case 2: run(std::integral_constant<int, 2>{}); break;
+                default: run(std::integral_constant<int, 3>{}); break;
             }
         }
     }
@@ -517,7 +544,12 @@ static int make_map(CUtensorMap* m, const __half* base, int64_t rows, int dp) {
 
 }  // namespace tc
 
-bool knn_tc_supported(int d, int k) { return d <= tc::MAX_ATOMS * tc::KATOM && k <= tc::MAX_K; }
+bool knn_tc_supported(int d, int k) {
+    if (d > tc::MAX_ATOMS * tc::KATOM || k > tc::MAX_K) return false;
+    // shared memory: resident query tile + at least two TMA stages + one set of lists + barriers/alignment
+    const size_t stage = (size_t)((d + tc::KATOM - 1) / tc::KATOM) * 2 * tc::TILE_BYTES;
+    return 3 * stage + (size_t)tc::BM * k * 8 + 512 + 1024 <= (size_t)227 * 1024;
+}
 
 size_t knn_tc_workspace_bytes(int64_t nq, int64_t ndb, int d, bool same) {
     const int dp = (int)align_up((size_t)d, tc::KATOM);

@@ -48,7 +48,8 @@ __device__ __forceinline__ float fgroup_sum(float v, unsigned mask) {
     return v;
 }
 
-__global__ void __launch_bounds__(kFastThreads, 4) umap_step_kernel_fast(const UmapStepParams p) {
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(kFastThreads, MIN_CTAS) umap_step_kernel_fast(const UmapStepParams p) {
     __shared__ int s_col[kFastGroups][FG * FU];  // compacted columns of the due edges of the current chunk set
     const int lane = threadIdx.x & 31;
     const int l = lane & (FG - 1);
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(kFastThreads, 4) umap_step_kernel_fast(const U
     const int64_t n_groups = (int64_t)gridDim.x * kFastGroups;
     const float due_before = (float)(p.n_iter + 1);  // umap.py:251
     const Philox rng(p.seed);
+    const uint32_t nm1 = (uint32_t)(p.n_total - 1);
     double gn_local = 0.0;
     bool saw_nan = false;
     unsigned long long n_act = 0, n_neg_used = 0;
@@ -152,8 +154,8 @@ __global__ void __launch_bounds__(kFastThreads, 4) umap_step_kernel_fast(const U
                 const uint32_t wv[4] = {wd.x, wd.y, wd.z, wd.w};
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int64_t t = (int64_t)(((uint64_t)wv[u] * (uint64_t)(p.n_total - 1)) >> 32);
-                    j[u] = t + ((t >= gj) ? 1 : 0);  // NE base.py:636
+                    const uint32_t t = __umulhi(wv[u], nm1);  // uniform on [0, N-2] (N < 2^31: indices are int32)
+                    j[u] = (int64_t)(t + ((t >= (uint32_t)gj) ? 1u : 0u));  // NE base.py:636
                 }
             }
             float2 zn[4];
@@ -178,15 +180,22 @@ __global__ void __launch_bounds__(kFastThreads, 4) umap_step_kernel_fast(const U
                 ay[gg] += (g == gg) ? sy : 0.0f;
             }
         }
-        float rx = 0.0f, ry = 0.0f;
-#pragma unroll
-        for (int gg = 0; gg < 4; ++gg) {
-            const float tx = warp_sum(ax[gg]), ty = warp_sum(ay[gg]);
-            if (gg == (lane >> 3)) {
-                rx = tx;
-                ry = ty;
-            }
+        // transposed reduction: 4 groups x 32 lanes -> lane L ends with the total of group L >> 3
+        // (2 + 1 + 3 shuffles per component instead of 4 full butterflies)
+        const bool up = lane & 16, odd = lane & 8;
+        float rx, ry;
+        {
+            float k0 = up ? ax[2] : ax[0], k1 = up ? ax[3] : ax[1];
+            k0 += __shfl_xor_sync(0xffffffffu, up ? ax[0] : ax[2], 16);
+            k1 += __shfl_xor_sync(0xffffffffu, up ? ax[1] : ax[3], 16);
+            rx = (odd ? k1 : k0) + __shfl_xor_sync(0xffffffffu, odd ? k0 : k1, 8);
+            float m0 = up ? ay[2] : ay[0], m1 = up ? ay[3] : ay[1];
+            m0 += __shfl_xor_sync(0xffffffffu, up ? ay[0] : ay[2], 16);
+            m1 += __shfl_xor_sync(0xffffffffu, up ? ay[1] : ay[3], 16);
+            ry = (odd ? m1 : m0) + __shfl_xor_sync(0xffffffffu, odd ? m0 : m1, 8);
         }
+        rx = fgroup_sum(rx, gmask);
+        ry = fgroup_sum(ry, gmask);
         rx = fminf(fmaxf(rx, -4.0f), 4.0f);  // umap.py:291
         ry = fminf(fmaxf(ry, -4.0f), 4.0f);
         if (l == 0 && live) {
