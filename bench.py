@@ -225,15 +225,35 @@ def gpu_arm(args):
     stats = torch.zeros(2, dtype=torch.int64, device=dev)
     nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
 
+    # multi-GPU exchange: step kernel with fused NVLink peer stores when symmetric memory is available
+    peer, exchange = None, ("none" if world == 1 else "nccl-allgather")
+    if world > 1 and os.environ.get("TDR_NO_P2P") != "1":
+        try:
+            from torchdr_b200.distributed import PeerEmbedding
+
+            peer = PeerEmbedding(Za)
+            Za, Zb = peer.bufs[0], peer.bufs[1]
+            exchange = "p2p-fused (tdr_umap_step_p2p_f32 + symmetric-memory barrier)"
+        except Exception as exc:
+            if rank == 0:
+                print(f"[bench] symmetric memory unavailable: {exc}", file=sys.stderr)
+            peer = None
+
     def run(t0, count, Za, Zb, stats_t):
         if world == 1:
             res = ops.umap_run(Za, Zb, rowptr, col, eps, eons, t0, lr_all[t0:t0 + count], a, b, n_neg=N_NEG,
                                seed=1234, nan_flag=nan_flag, stats=stats_t)
             return (res, Zb if res is Za else Za)
         for t in range(t0, t0 + count):
-            ops.umap_step(Za, Zb, s, e - s, rowptr, col, eps, eons, t, a, b, float(lr_all[t]), neg=None,
-                          n_neg=N_NEG, seed=1234, nan_flag=nan_flag, stats=stats_t)
-            all_gather_rows(Zb, bounds, rank)
+            if peer is not None and stats_t is None:
+                out_i = 0 if Zb is peer.bufs[0] else 1
+                ops.umap_step_p2p(Za, Zb, s, e - s, rowptr, col, eps, eons, t, a, b, float(lr_all[t]),
+                                  peer.peer_ptrs(out_i), n_neg=N_NEG, seed=1234, nan_flag=nan_flag)
+                peer.barrier(out_i)
+            else:
+                ops.umap_step(Za, Zb, s, e - s, rowptr, col, eps, eons, t, a, b, float(lr_all[t]), neg=None,
+                              n_neg=N_NEG, seed=1234, nan_flag=nan_flag, stats=stats_t)
+                all_gather_rows(Zb, bounds, rank)
             Za, Zb = Zb, Za
         return Za, Zb
 
@@ -307,7 +327,7 @@ def gpu_arm(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"UMAP n_neighbors={K_NEIGHBORS} on {n}x{d} clustered synthetic (BASELINE configs[1])",
                        "points": n, "dim": d, "n_negatives": N_NEG, "schedule_max_iter": sched,
-                       "negatives": "in-kernel Philox4x32-10", "parallelism": f"rows sharded x{world}",
+                       "negatives": "in-kernel Philox4x32-10", "parallelism": f"rows sharded x{world}", "exchange": exchange,
                        "l2": "per-iteration working set (CSR edge state %.0f MB) exceeds the 126 MB L2; no flush" %
                              (nnz * 12 / 1e6 / world)},
             "roofline": roofline, "affinity_kernel": affinity,

@@ -208,6 +208,20 @@ TDR_API int tdr_umap_run_f32(float* Z_a, float* Z_b, int64_t n_total,
                      int precise, double* gnorm_sq, int* nan_flag, uint64_t* stats,
                      tdr_stream_t stream);
 
+/* Fused step + exchange for the row-sharded multi-GPU loop: same iteration as tdr_umap_step_f32
+ * (throughput kernel, in-kernel negatives), but every updated row is additionally stored into
+ * the Z_out buffer of each peer GPU through NVLink peer mappings (peer_out_ptrs: HOST array of
+ * n_peers <= 8 device addresses, e.g. torch symmetric-memory buffer_ptrs without this rank's
+ * own).  Replaces the per-iteration collective of affinity_matcher.py:395-413; the caller only
+ * needs a cross-GPU barrier before the next iteration reads the buffers. */
+TDR_API int tdr_umap_step_p2p_f32(const float* Z_in, float* Z_out, int64_t n_total, int64_t row0, int64_t n_local,
+                                  const int64_t* rowptr, const int32_t* col,
+                                  const float* epochs_per_sample, float* epoch_of_next_sample,
+                                  int n_neg, int negative_sample_rate, uint64_t seed, int64_t n_iter,
+                                  double a, double b, float lam, float repulsion, float lr,
+                                  double* gnorm_sq, int* nan_flag,
+                                  const uint64_t* peer_out_ptrs, int n_peers, tdr_stream_t stream);
+
 /* LargeVis gradient (largevis.py:181-201 differentiated): accumulates into
  * grad[n_total,2] (zeroed by the caller) with atomics — the autograd scatter of
  * affinity_matcher.py:418-425 — for local rows; P/idx are the directed kNN rows. */

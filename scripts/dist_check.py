@@ -77,6 +77,38 @@ for t in range(8):
 err = float((Zc - res).norm() / res.norm())
 report(f"8 sharded iterations vs single GPU (rel {err:.2e})", err < 1e-3)
 
+# ---- fused step + exchange over NVLink peer stores (symmetric memory) == NCCL all-gather path
+try:
+    from torchdr_b200.distributed import PeerEmbedding
+
+    peer = PeerEmbedding(Z0)
+    Zp, Zq = peer.bufs[0], peer.bufs[1]
+    eons2 = g_loc[3].clone()
+    cur = 0
+    for t in range(8):
+        ops.umap_step_p2p(Zp, Zq, s, e - s, g_loc[0], g_loc[1], g_loc[2], eons2, t, pa, pb, float(lrs[t]),
+                          peer.peer_ptrs(1 - cur), seed=11)
+        peer.barrier(1 - cur)
+        Zp, Zq = Zq, Zp
+        cur = 1 - cur
+    report("p2p-fused step: 8 iterations bit-identical to the all-gather path", torch.equal(Zp, Zc))
+    import time
+    torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+    for t in range(200):
+        ops.umap_step_p2p(Zp, Zq, s, e - s, g_loc[0], g_loc[1], g_loc[2], eons2, 8 + t, pa, pb, 0.5, peer.peer_ptrs(1 - cur), seed=11)
+        peer.barrier(1 - cur); Zp, Zq = Zq, Zp; cur = 1 - cur
+    torch.cuda.synchronize(); t_p2p = (time.perf_counter() - t0) / 200
+    Zc2, Zd2 = Zc.clone(), Zc.clone()
+    torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+    for t in range(200):
+        ops.umap_step(Zc2, Zd2, s, e - s, g_loc[0], g_loc[1], g_loc[2], eons, 8 + t, pa, pb, 0.5, neg=None, seed=11)
+        all_gather_rows(Zd2, bounds, rank); Zc2, Zd2 = Zd2, Zc2
+    torch.cuda.synchronize(); t_ag = (time.perf_counter() - t0) / 200
+    if rank == 0:
+        print(f"[dist_check] per-iteration wall time at n={n}: p2p-fused {t_p2p*1e6:.1f} us, nccl all-gather {t_ag*1e6:.1f} us", flush=True)
+except Exception as exc:
+    report(f"p2p-fused path unavailable: {type(exc).__name__}: {exc}", False)
+
 # ---- estimators under torchrun
 Xh = X.cpu().numpy()
 for cls, kw in ((tb.UMAP, dict(n_neighbors=15, max_iter=60)), (tb.LargeVis, dict(perplexity=10, max_iter=40)),

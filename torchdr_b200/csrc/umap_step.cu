@@ -35,7 +35,18 @@ struct UmapStepParams {
     double* gnorm_sq;
     int* nan_flag;
     unsigned long long* stats;  // [0] += sampled edges, [1] += negatives used (roofline accounting)
+    // fused exchange (multi-GPU): the updated row is also stored into the Z_out buffer of every peer through
+    // NVLink peer mappings, so no separate all-gather of the embedding is needed after the step
+    float2* peer_out[8];
+    int n_peers;
 };
+
+__device__ __forceinline__ void store_row(const UmapStepParams& p, int64_t gi, float2 zo) {
+    p.Zout[gi] = zo;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        if (q < p.n_peers) p.peer_out[q][gi] = zo;
+}
 
 // Per-block reduction of the optional diagnostics (gradient norm, NaN flag, sampled-edge counters) in
 // shared memory, then one global atomic per block: thousands of same-address global atomics per launch
@@ -158,7 +169,7 @@ __global__ void __launch_bounds__(kStepWarps * 32) umap_step_kernel(const UmapSt
             float2 zo;  // torch.optim.SGD: param.add_(grad, alpha=-lr)
             zo.x = fmaf(-p.lr, g0, zi.x);
             zo.y = fmaf(-p.lr, g1, zi.y);
-            p.Zout[gi] = zo;
+            store_row(p, gi, zo);
             if (p.grad_out) p.grad_out[r] = make_float2(g0, g1);
             gn_local += (double)g0 * g0 + (double)g1 * g1;
             saw_nan |= (zo.x != zo.x) || (zo.y != zo.y);
@@ -291,7 +302,7 @@ __global__ void __launch_bounds__(kV2Threads, 4) umap_step_kernel_v2(const UmapS
             float2 zo;
             zo.x = fmaf(-p.lr, g0, zi.x);
             zo.y = fmaf(-p.lr, g1, zi.y);
-            p.Zout[gi] = zo;
+            store_row(p, gi, zo);
             if (p.grad_out) p.grad_out[r] = make_float2(g0, g1);
             gn_local += (double)g0 * g0 + (double)g1 * g1;
             saw_nan |= (zo.x != zo.x) || (zo.y != zo.y);
@@ -352,12 +363,12 @@ static void fill_consts(UmapStepParams& p, float a, float b, double a64, double 
 
 using namespace tdr;
 
-extern "C" TDR_API int tdr_umap_step_f32(const float* Z_in, float* Z_out, int64_t n_total, int64_t row0, int64_t n_local,
-                                 const int64_t* rowptr, const int32_t* col, const float* epochs_per_sample,
-                                 float* epoch_of_next_sample, const int64_t* neg, int n_neg,
-                                 int negative_sample_rate, uint64_t seed, int64_t n_iter, double a, double b,
-                                 float lam, float repulsion, float lr, int precise, float* grad_out,
-                                 double* gnorm_sq, int* nan_flag, uint64_t* stats, tdr_stream_t stream) {
+static int umap_step_impl(const float* Z_in, float* Z_out, int64_t n_total, int64_t row0, int64_t n_local,
+                          const int64_t* rowptr, const int32_t* col, const float* epochs_per_sample,
+                          float* epoch_of_next_sample, const int64_t* neg, int n_neg, int negative_sample_rate,
+                          uint64_t seed, int64_t n_iter, double a, double b, float lam, float repulsion, float lr,
+                          int precise, float* grad_out, double* gnorm_sq, int* nan_flag, uint64_t* stats,
+                          float* const* peer_out, int n_peers, tdr_stream_t stream) {
     TDR_CHECK_ARG(Z_in && Z_out && rowptr && col && epochs_per_sample && epoch_of_next_sample,
                   "tdr_umap_step_f32: null pointer");
     TDR_CHECK_ARG(Z_in != Z_out, "tdr_umap_step_f32: Z_in and Z_out must not alias (Jacobi update)");
@@ -388,7 +399,38 @@ extern "C" TDR_API int tdr_umap_step_f32(const float* Z_in, float* Z_out, int64_
     p.gnorm_sq = gnorm_sq;
     p.nan_flag = nan_flag;
     p.stats = reinterpret_cast<unsigned long long*>(stats);
+    TDR_CHECK_ARG(n_peers >= 0 && n_peers <= 8 && (n_peers == 0 || peer_out), "tdr_umap_step: at most 8 peer buffers");
+    p.n_peers = n_peers;
+    for (int q = 0; q < n_peers; ++q) {
+        TDR_CHECK_ARG(peer_out[q] && (const float*)peer_out[q] != Z_in, "tdr_umap_step: bad peer buffer");
+        p.peer_out[q] = reinterpret_cast<float2*>(peer_out[q]);
+    }
     return launch_step(p, precise, (cudaStream_t)stream);
+}
+
+extern "C" TDR_API int tdr_umap_step_f32(const float* Z_in, float* Z_out, int64_t n_total, int64_t row0, int64_t n_local,
+                                 const int64_t* rowptr, const int32_t* col, const float* epochs_per_sample,
+                                 float* epoch_of_next_sample, const int64_t* neg, int n_neg,
+                                 int negative_sample_rate, uint64_t seed, int64_t n_iter, double a, double b,
+                                 float lam, float repulsion, float lr, int precise, float* grad_out,
+                                 double* gnorm_sq, int* nan_flag, uint64_t* stats, tdr_stream_t stream) {
+    return umap_step_impl(Z_in, Z_out, n_total, row0, n_local, rowptr, col, epochs_per_sample, epoch_of_next_sample, neg,
+                          n_neg, negative_sample_rate, seed, n_iter, a, b, lam, repulsion, lr, precise, grad_out, gnorm_sq,
+                          nan_flag, stats, nullptr, 0, stream);
+}
+
+extern "C" TDR_API int tdr_umap_step_p2p_f32(const float* Z_in, float* Z_out, int64_t n_total, int64_t row0,
+                                             int64_t n_local, const int64_t* rowptr, const int32_t* col,
+                                             const float* epochs_per_sample, float* epoch_of_next_sample, int n_neg,
+                                             int negative_sample_rate, uint64_t seed, int64_t n_iter, double a, double b,
+                                             float lam, float repulsion, float lr, double* gnorm_sq, int* nan_flag,
+                                             const uint64_t* peer_out_ptrs /*host*/, int n_peers, tdr_stream_t stream) {
+    float* peers[8] = {nullptr};
+    TDR_CHECK_ARG(n_peers >= 0 && n_peers <= 8, "tdr_umap_step_p2p_f32: at most 8 peers");
+    for (int q = 0; q < n_peers; ++q) peers[q] = reinterpret_cast<float*>(peer_out_ptrs[q]);
+    return umap_step_impl(Z_in, Z_out, n_total, row0, n_local, rowptr, col, epochs_per_sample, epoch_of_next_sample,
+                          nullptr, n_neg, negative_sample_rate, seed, n_iter, a, b, lam, repulsion, lr, 0, nullptr,
+                          gnorm_sq, nan_flag, nullptr, peers, n_peers, stream);
 }
 
 extern "C" TDR_API int tdr_umap_run_f32(float* Z_a, float* Z_b, int64_t n_total, const int64_t* rowptr,

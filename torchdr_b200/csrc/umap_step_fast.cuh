@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(kFastThreads, MIN_CTAS) umap_step_kernel_fast(
             float2 zo;  // torch.optim.SGD: param.add_(grad, alpha=-lr)
             zo.x = fmaf(-p.lr, g0, zi.x);
             zo.y = fmaf(-p.lr, g1, zi.y);
-            p.Zout[gi] = zo;
+            store_row(p, gi, zo);
             if (p.grad_out) p.grad_out[r] = make_float2(g0, g1);
             gn_local += (double)g0 * g0 + (double)g1 * g1;
             saw_nan |= (zo.x != zo.x) || (zo.y != zo.y);

@@ -117,3 +117,38 @@ def all_gather_rows(Z_full: torch.Tensor, bounds, rank: int, group=None):
         if r != rank:
             Z_full[rs:re] = recv[r * longest : r * longest + (re - rs)]
     return Z_full
+
+
+class PeerEmbedding:
+    """Double-buffered embedding ``Z[N, q]`` in symmetric memory (``torch.distributed._symmetric_memory``).
+
+    Every rank holds the full embedding; the step kernel (``tdr_umap_step_p2p_f32``) stores each updated row
+    into its own buffer AND, through the NVLink peer mappings exposed here, into every peer's buffer, so the
+    per-iteration exchange is part of the compute kernel.  ``barrier`` is the symmetric-memory signal-pad
+    barrier (a few microseconds on the stream), needed before the freshly written buffer is read.
+    Raises if symmetric memory cannot be set up (the caller then uses the NCCL all-gather path).
+    """
+
+    def __init__(self, Z0: torch.Tensor, group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        if self.world > 9:
+            raise RuntimeError("tdr_umap_step_p2p_f32 addresses at most 8 peers")
+        self.bufs, self.handles = [], []
+        for _ in range(2):
+            t = symm.empty(tuple(Z0.shape), dtype=Z0.dtype, device=Z0.device)
+            self.handles.append(symm.rendezvous(t, group))
+            self.bufs.append(t)
+        self.bufs[0].copy_(Z0)
+        self.bufs[1].copy_(Z0)
+        torch.cuda.synchronize(Z0.device)
+        self.handles[0].barrier(channel=0)
+
+    def peer_ptrs(self, i: int):
+        return [int(p) for r, p in enumerate(self.handles[i].buffer_ptrs) if r != self.rank]
+
+    def barrier(self, i: int):
+        self.handles[i].barrier(channel=0)

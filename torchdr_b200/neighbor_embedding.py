@@ -21,7 +21,7 @@ import torch.distributed as dist
 from . import _lib, ops
 from .affinity import EntropicAffinity, UMAPAffinity
 from .distance import _to_device_tensor
-from .distributed import all_bounds, all_gather_rows, is_distributed
+from .distributed import PeerEmbedding, all_bounds, all_gather_rows, is_distributed
 
 
 def find_ab_params(spread, min_dist):
@@ -421,13 +421,43 @@ class UMAP(_NeighborEmbeddingB200):
         self._last_step = -1
         step = 0
         stop = False
+        hooks_per_step = type(self).on_training_step_start is not UMAP.on_training_step_start or \
+            type(self).on_training_step_end is not _NeighborEmbeddingB200.on_training_step_end
+        # multi-GPU: fused step + exchange over NVLink peer stores (PeerEmbedding) when symmetric memory is
+        # available, else one NCCL all-gather per iteration
+        peer, cur = None, 0
+        self.exchange_ = "none" if self.world_size == 1 else "nccl-allgather"
+        if self.world_size > 1 and not hooks_per_step and not self.precise and os.environ.get("TDR_NO_P2P") != "1":
+            try:
+                peer = PeerEmbedding(Za)
+                Za, Zb = peer.bufs[0], peer.bufs[1]
+                self.exchange_ = "p2p-fused"
+            except Exception as exc:  # symmetric memory unavailable on this system
+                self.logger.warning(f"symmetric memory unavailable ({exc}); falling back to NCCL all-gather")
+                peer = None
         while step < self.max_iter and not stop:
             # batch = steps up to (and including) the next one with n_iter % check_interval == 0
             nxt_check = step if step % self.check_interval == 0 else (step // self.check_interval + 1) * self.check_interval
             last = min(nxt_check, self.max_iter - 1)
-            hooks_per_step = type(self).on_training_step_start is not UMAP.on_training_step_start or \
-                type(self).on_training_step_end is not _NeighborEmbeddingB200.on_training_step_end
-            if self.world_size > 1 or hooks_per_step:
+            if peer is not None:
+                for t in range(step, last + 1):
+                    lr = self._hyper()[0]
+                    want = t == last and t % self.check_interval == 0
+                    if want:
+                        self._gnorm.zero_()
+                    ops.umap_step_p2p(Za, Zb, s, e - s, rowptr, col, eps, eons, t, self._a, self._b, lr,
+                                      peer.peer_ptrs(1 - cur), n_neg=self.n_negatives, rate=self.negative_sample_rate,
+                                      seed=seed, lam=lam, repulsion=rep, gnorm_sq=self._gnorm if want else None,
+                                      nan_flag=self._nan)
+                    peer.barrier(1 - cur)
+                    if want:
+                        dist.all_reduce(self._gnorm, op=dist.ReduceOp.SUM)
+                    Za, Zb = Zb, Za
+                    cur = 1 - cur
+                    self._advance_schedule()
+                self.n_iter_ = torch.tensor(last, dtype=torch.long)
+                self.embedding_ = Za
+            elif self.world_size > 1 or hooks_per_step:
                 for t in range(step, last + 1):
                     self.n_iter_ = torch.tensor(t, dtype=torch.long)
                     self.on_training_step_start()
@@ -468,7 +498,7 @@ class UMAP(_NeighborEmbeddingB200):
             self._check_nan(last)
             if last % self.check_interval == 0:
                 stop = self._converged(last, float(self._gnorm.item()) ** 0.5)
-        self.embedding_ = Za
+        self.embedding_ = Za.clone() if peer is not None else Za  # leave symmetric memory before it is released
 
 
 class _EntropicInputMixin:

@@ -241,6 +241,18 @@ def umap_step(Z_in, Z_out, row0, n_local, rowptr, col, eps, eons, n_iter, a, b, 
               "tdr_umap_step_f32")
 
 
+def umap_step_p2p(Z_in, Z_out, row0, n_local, rowptr, col, eps, eons, n_iter, a, b, lr, peer_ptrs, n_neg=75, rate=5,
+                  seed=0, lam=1.0, repulsion=1.0, gnorm_sq=None, nan_flag=None):
+    """Step + exchange in one kernel: updated rows are also stored into the peers' Z_out (device addresses)."""
+    arr = (ctypes.c_uint64 * max(len(peer_ptrs), 1))(*[int(x) for x in peer_ptrs])
+    with torch.cuda.device(Z_in.device):
+        check(_lib.load().tdr_umap_step_p2p_f32(ptr(Z_in), ptr(Z_out), Z_in.shape[0], row0, n_local, ptr(rowptr),
+                                                ptr(col), ptr(eps), ptr(eons), n_neg, rate, seed, n_iter, float(a),
+                                                float(b), float(lam), float(repulsion), float(lr), ptr(gnorm_sq),
+                                                ptr(nan_flag), arr, len(peer_ptrs), stream()),
+              "tdr_umap_step_p2p_f32")
+
+
 def umap_run(Z_a, Z_b, rowptr, col, eps, eons, n_iter0, lrs, a, b, n_neg=75, rate=5, seed=0, lam=1.0,
              repulsion=1.0, precise=False, gnorm_sq=None, nan_flag=None, stats=None):
     """len(lrs) iterations on one GPU; returns the tensor holding the result."""
