@@ -374,6 +374,17 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
+    # NCCL prints its version banner to STDOUT when NCCL_DEBUG=VERSION; the contract is ONE JSON line there
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
+    # ... and native libraries may still write to fd 1: park the real stdout and point fd 1 at stderr until the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
 
     if args.impl == "reference":
         if rank != 0:
@@ -392,7 +403,7 @@ def main():
                              "sample": r["sample"]},
             "e2e": {"value": r["e2e_value"], "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
-        print(json.dumps(line))
+        emit(line)
         return
 
     out, (rank, world, dev) = gpu_arm(args)
@@ -408,7 +419,7 @@ def main():
             r = cpu_reference(10, 2, args.points, args.dim)
             out["cpu_baseline"] = {"value": r["value"], "unit": "iters/s", "cores": r["cores"], "kind": r["kind"],
                                    "sample": r["sample"], "e2e_value": r["e2e_value"]}
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         import torch.distributed as dist
 
