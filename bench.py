@@ -9,8 +9,8 @@ Workload (BASELINE.json configs[1]): UMAP n_neighbors=15 on 1 M x 128 synthetic 
 (the reference benchmark's generator, benchmarks/faiss/run_benchmark.py:127-146).  A *step* is
 one UMAP optimisation iteration over all points; the graph (kNN -> sigma/rho -> symmetrise ->
 edge schedule) is built once, untimed, through the same C-ABI calls.  Strong scaling: the point
-set is fixed and rows are sharded across ranks; after every iteration the updated rows are
-all-gathered (NCCL).
+set is fixed and rows are sharded across ranks; every iteration's updated rows reach the peers
+through NVLink stores issued by the step kernel itself (fallback: one NCCL all-gather).
 """
 
 import argparse
@@ -308,15 +308,27 @@ def gpu_arm(args):
             traffic = json.load(open(prof)).get("dram_bytes_per_launch")
         except Exception:
             pass
-    roofline = {"bound": "hbm", "kernel": "umap_step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+    if traffic is not None and world > 1:
+        traffic = None  # the ncu capture is of the N = 1 launch
+    roofline = {"bound": "hbm", "kernel": "tdr::umap_step_kernel_fast", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes / world,
-                "note": "per-GPU; at N>1 the per-step time also contains the NCCL all-gather"}
+                "note": ("per GPU; achieved = algorithmic bytes (DESIGN.md 3.5, counts taken in-kernel) / mean launch "
+                         "time over the timed region; ncu shows the kernel is instruction-issue bound (profiles/"
+                         "r1_step_kernel.md); at N>1 the per-step time also contains the cross-GPU barrier")}
     aff_bytes = 4.0 * n * d / 1 + n / world * K_NEIGHBORS * 8.0 + 8.0 * n / world
-    affinity = {"kernel": "knn_tile_kernel<FUSED>", "ms": knn_ms, "algorithmic_bytes": aff_bytes,
-                "gbs": aff_bytes / (knn_ms * 1e-3) / 1e9,
-                "tflops_2nnd": 2.0 * (n / world) * n * d / (knn_ms * 1e-3) / 1e12,
-                "note": "compute-bound by construction (SURVEY 8d); fp32 FFMA mainloop"}
+    tc_peak = None
+    try:
+        tc_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+    except Exception:
+        pass
+    tf_equiv = 2.0 * (n / world) * n * d / (knn_ms * 1e-3) / 1e12
+    affinity = {"kernel": "tdr::tc::knn_tc_kernel (fused kNN + sigma/rho, tcgen05 kind::f16, 3 split passes)",
+                "ms": knn_ms, "algorithmic_bytes": aff_bytes, "gbs": aff_bytes / (knn_ms * 1e-3) / 1e9,
+                "tflops_2nnd": tf_equiv, "tensor_tflops_3pass": 3.0 * tf_equiv,
+                "tensor_frac_of_measured_bf16_peak": (3.0 * tf_equiv / tc_peak) if tc_peak else None,
+                "note": "compute-bound by construction (SURVEY 8d): GB/s on the 640 MB algorithmic bytes is quoted "
+                        "because the metric asks for it; the roofline that binds is the tensor pipe"}
 
     out = None
     if rank == 0:
