@@ -454,14 +454,8 @@ static int prepare(const float* Xq, int64_t nq, const float* Xdb, int64_t ndb, i
 template <int MODE>
 static int launch_knn(const KnnParams& prm, dim3 grid, cudaStream_t st) {
     const size_t smem = knn_smem_bytes(prm.kpad, MODE);
-    static bool attr_set = false;
-    static size_t attr_bytes = 0;
-    if (!attr_set || smem > attr_bytes) {
-        TDR_CUDA(cudaFuncSetAttribute(knn_tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      227 * 1024));
-        attr_set = true;
-        attr_bytes = 227 * 1024;
-    }
+    // per call: the attribute belongs to the current device's context (a process may drive several GPUs)
+    TDR_CUDA(cudaFuncSetAttribute(knn_tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     knn_tile_kernel<MODE><<<grid, NT, smem, st>>>(prm);
     TDR_LAUNCH_CHECK();
     return TDR_OK;

@@ -656,11 +656,8 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
     }
     prm.stages = stages;
     const size_t smem = fixed + (size_t)stages * stage_bytes;
-    static bool attr_set = false;
-    if (!attr_set) {
-        TDR_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
+    // per call: the attribute belongs to the current device's context (a process may drive several GPUs)
+    TDR_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     knn_tc_kernel<<<(unsigned)((nq + BM - 1) / BM), prm.dual ? 384 : 256, smem, st>>>(mq_hi, mq_lo, mdb_hi, mdb_lo, prm);
     TDR_LAUNCH_CHECK();
     return TDR_OK;
