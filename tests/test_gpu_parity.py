@@ -525,6 +525,39 @@ def test_estimators_end_to_end():
         tb.UMAP(n_neighbors=700).fit_transform(X)
 
 
+def test_long_run_quality_matches_reference_path():
+    """Long runs cannot be compared coordinate by coordinate (the loop is chaotic); the reference compares runs
+    by neighbourhood preservation (benchmarks/umap_vs_largevis_distributed.py:97-107).  300 iterations of the
+    engine (in-kernel negatives) vs 300 iterations of the oracle restatement of the reference path."""
+    import torchdr_b200 as tb
+
+    n, d, k, T = 3000, 24, 15, 300
+    X = blobs(n, d, 12, 77, spread=1.0, scale=5.0)
+    # reference path (oracle): kNN -> sigma -> symmetrise -> schedule -> T steps with torch.randint negatives
+    C, I = oracle.knn_dense(X, k)
+    P, _, _ = oracle.umap_affinity_rows(C, k)
+    V, J = oracle.symmetrize_ell(P, I)
+    per, nxt = oracle.umap_edge_schedule(V, T)
+    g = torch.Generator().manual_seed(5)
+    Z0 = torch.randn(n, 2, generator=g)
+    Z0 = 1e-4 * Z0 / Z0[:, 0].std()
+    me = torch.arange(n)
+    negs = [oracle.adjust_negatives(torch.randint(0, n - 1, (n, 75), generator=g), me) for _ in range(T)]
+    a, b = oracle.find_ab()
+    Zref, _ = oracle.umap_run(Z0, J, per, nxt, negs, oracle.linear_lr_sequence(1.0, T, T), a, b)
+    Zeng = tb.UMAP(n_neighbors=k, max_iter=T, init=Z0.clone(), random_state=3, process_duplicates=False,
+                   min_grad_norm=0.0).fit_transform(X)
+    np_ref = float(tb.neighborhood_preservation(X, Zref, K=k))
+    np_eng = float(tb.neighborhood_preservation(X, Zeng, K=k))
+    # the metric itself against a direct CPU evaluation of the reference formula
+    _, nx = oracle.knn_dense(X, k)
+    _, nz = oracle.knn_dense(Zref, k)
+    direct = float((nx.unsqueeze(2) == nz.unsqueeze(1)).any(2).float().sum(1).div(k).mean())
+    assert abs(direct - np_ref) < 2e-3
+    print(f"neighbourhood preservation K={k}: reference path {np_ref:.4f}, engine {np_eng:.4f}")
+    assert np_ref > 0.1 and abs(np_eng - np_ref) < 0.03
+
+
 def test_estimator_edge_cases():
     """Input handling the reference covers: duplicates (base.py:132-146), non-finite input, too few samples,
     torch / numpy round trip, tiny inputs, ragged sizes around the 128-row tiles."""

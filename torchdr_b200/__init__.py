@@ -9,6 +9,7 @@ from .distance import pairwise_distances, pairwise_distances_indexed, LIST_METRI
 from .affinity import UMAPAffinity, EntropicAffinity  # noqa: F401
 from .neighbor_embedding import UMAP, LargeVis, TSNE  # noqa: F401
 from .distributed import DistributedContext  # noqa: F401
+from .eval import neighborhood_preservation  # noqa: F401
 
 __all__ = [
     "pairwise_distances",
@@ -19,4 +20,5 @@ __all__ = [
     "LargeVis",
     "TSNE",
     "DistributedContext",
+    "neighborhood_preservation",
 ]

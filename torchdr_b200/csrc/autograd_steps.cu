@@ -48,8 +48,7 @@ largevis_grad_kernel(const float2* __restrict__ Z, int64_t n_total, int64_t row0
         const float cx = c * dx, cy = c * dy;
         gx += cx;
         gy += cy;
-        atomicAdd(grad + 2 * j, -cx);
-        atomicAdd(grad + 2 * j + 1, -cy);
+        atomicAdd(reinterpret_cast<float2*>(grad) + j, make_float2(-cx, -cy));  // one 8-byte red.global.add.v2.f32
     }
     const Philox rng(seed);
     for (int s = lane; s < n_neg; s += 32) {
@@ -63,14 +62,12 @@ largevis_grad_kernel(const float2* __restrict__ Z, int64_t n_total, int64_t row0
         const float cx = c * dx, cy = c * dy;
         gx += cx;
         gy += cy;
-        atomicAdd(grad + 2 * j, -cx);
-        atomicAdd(grad + 2 * j + 1, -cy);
+        atomicAdd(reinterpret_cast<float2*>(grad) + j, make_float2(-cx, -cy));  // one 8-byte red.global.add.v2.f32
     }
     gx = warp_sum(gx);
     gy = warp_sum(gy);
     if (lane == 0) {
-        atomicAdd(grad + 2 * gi, gx);
-        atomicAdd(grad + 2 * gi + 1, gy);
+        atomicAdd(reinterpret_cast<float2*>(grad) + gi, make_float2(gx, gy));
     }
 }
 
@@ -92,14 +89,12 @@ tsne_attract_kernel(const float2* __restrict__ Z, int64_t row0, int64_t n_local,
         const float cx = c * dx, cy = c * dy;
         gx += cx;
         gy += cy;
-        atomicAdd(grad + 2 * j, -cx);
-        atomicAdd(grad + 2 * j + 1, -cy);
+        atomicAdd(reinterpret_cast<float2*>(grad) + j, make_float2(-cx, -cy));  // one 8-byte red.global.add.v2.f32
     }
     gx = warp_sum(gx);
     gy = warp_sum(gy);
     if (lane == 0) {
-        atomicAdd(grad + 2 * gi, gx);
-        atomicAdd(grad + 2 * gi + 1, gy);
+        atomicAdd(reinterpret_cast<float2*>(grad) + gi, make_float2(gx, gy));
     }
 }
 
