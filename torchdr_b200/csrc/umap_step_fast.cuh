@@ -198,19 +198,23 @@ __global__ void __launch_bounds__(kFastThreads, MIN_CTAS) umap_step_kernel_fast(
         ry = fgroup_sum(ry, gmask);
         rx = fminf(fmaxf(rx, -4.0f), 4.0f);  // umap.py:291
         ry = fminf(fmaxf(ry, -4.0f), 4.0f);
+        const float g0 = __fadd_rn(__fmul_rn(p.lam, gx), __fmul_rn(p.rep, rx));  // NE base.py:237-241
+        const float g1 = __fadd_rn(__fmul_rn(p.lam, gy), __fmul_rn(p.rep, ry));
+        float2 zo;  // torch.optim.SGD: param.add_(grad, alpha=-lr)
+        zo.x = fmaf(-p.lr, g0, zi.x);
+        zo.y = fmaf(-p.lr, g1, zi.y);
         if (l == 0 && live) {
-            const float g0 = __fadd_rn(__fmul_rn(p.lam, gx), __fmul_rn(p.rep, rx));  // NE base.py:237-241
-            const float g1 = __fadd_rn(__fmul_rn(p.lam, gy), __fmul_rn(p.rep, ry));
-            float2 zo;  // torch.optim.SGD: param.add_(grad, alpha=-lr)
-            zo.x = fmaf(-p.lr, g0, zi.x);
-            zo.y = fmaf(-p.lr, g1, zi.y);
-            store_row(p, gi, zo);
             if (p.grad_out) p.grad_out[r] = make_float2(g0, g1);
             gn_local += (double)g0 * g0 + (double)g1 * g1;
             saw_nan |= (zo.x != zo.x) || (zo.y != zo.y);
             n_act += active;
             n_neg_used += quota;
         }
+        // The warp's 4 rows are consecutive: move the 4 results to lanes 0-3 and write ONE contiguous 32-byte
+        // segment per destination (own buffer + every peer over NVLink) instead of 4 scattered 8-byte stores.
+        __syncwarp();
+        const float ox = __shfl_sync(0xffffffffu, zo.x, (lane & 3) * FG), oy = __shfl_sync(0xffffffffu, zo.y, (lane & 3) * FG);
+        if (lane < 4 && rb + lane < p.n_local) store_row(p, p.row0 + rb + lane, make_float2(ox, oy));
     }
     block_flush(l == 0, gn_local, saw_nan, n_act, n_neg_used, p);
 }

@@ -440,13 +440,18 @@ class UMAP(_NeighborEmbeddingB200):
             nxt_check = step if step % self.check_interval == 0 else (step // self.check_interval + 1) * self.check_interval
             last = min(nxt_check, self.max_iter - 1)
             if peer is not None:
+                lrs = []
+                for t in range(step, last + 1):  # schedule bookkeeping up front, launches back to back below
+                    lrs.append(self._hyper()[0])
+                    self._advance_schedule()
+                ptrs = (peer.peer_ptrs(0), peer.peer_ptrs(1))
                 for t in range(step, last + 1):
-                    lr = self._hyper()[0]
+                    lr = lrs[t - step]
                     want = t == last and t % self.check_interval == 0
                     if want:
                         self._gnorm.zero_()
                     ops.umap_step_p2p(Za, Zb, s, e - s, rowptr, col, eps, eons, t, self._a, self._b, lr,
-                                      peer.peer_ptrs(1 - cur), n_neg=self.n_negatives, rate=self.negative_sample_rate,
+                                      ptrs[1 - cur], n_neg=self.n_negatives, rate=self.negative_sample_rate,
                                       seed=seed, lam=lam, repulsion=rep, gnorm_sq=self._gnorm if want else None,
                                       nan_flag=self._nan)
                     peer.barrier(1 - cur)
@@ -454,7 +459,6 @@ class UMAP(_NeighborEmbeddingB200):
                         dist.all_reduce(self._gnorm, op=dist.ReduceOp.SUM)
                     Za, Zb = Zb, Za
                     cur = 1 - cur
-                    self._advance_schedule()
                 self.n_iter_ = torch.tensor(last, dtype=torch.long)
                 self.embedding_ = Za
             elif self.world_size > 1 or hooks_per_step:
