@@ -263,7 +263,7 @@ def gpu_arm(args):
 
             peer = PeerEmbedding(Za)
             Za, Zb = peer.bufs[0], peer.bufs[1]
-            exchange = "p2p-fused (tdr_umap_step_p2p_f32 + symmetric-memory barrier)"
+            exchange = "p2p-fused (tdr_umap_run_p2p_f32: step kernel with NVLink peer stores + flag barrier kernel)"
         except Exception as exc:
             if rank == 0:
                 print(f"[bench] symmetric memory unavailable: {exc}", file=sys.stderr)
@@ -274,12 +274,14 @@ def gpu_arm(args):
             res = ops.umap_run(Za, Zb, rowptr, col, eps, eons, t0, lr_all[t0:t0 + count], a, b, n_neg=N_NEG,
                                seed=1234, nan_flag=nan_flag, stats=stats_t)
             return (res, Zb if res is Za else Za)
+        if peer is not None and stats_t is None and count > 0:
+            cur = 0 if Za is peer.bufs[0] else 1
+            cur = ops.umap_run_p2p(peer, cur, s, e - s, rowptr, col, eps, eons, t0, lr_all[t0:t0 + count], a, b,
+                                   n_neg=N_NEG, seed=1234, nan_flag=nan_flag)
+            return peer.bufs[cur], peer.bufs[1 - cur]
         for t in range(t0, t0 + count):
-            if peer is not None and stats_t is None:
-                out_i = 0 if Zb is peer.bufs[0] else 1
-                ops.umap_step_p2p(Za, Zb, s, e - s, rowptr, col, eps, eons, t, a, b, float(lr_all[t]),
-                                  peer.peer_ptrs(out_i), n_neg=N_NEG, seed=1234, nan_flag=nan_flag)
-                peer.barrier(out_i)
+            if False:
+                pass
             else:
                 ops.umap_step(Za, Zb, s, e - s, rowptr, col, eps, eons, t, a, b, float(lr_all[t]), neg=None,
                               n_neg=N_NEG, seed=1234, nan_flag=nan_flag, stats=stats_t)

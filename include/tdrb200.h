@@ -222,6 +222,23 @@ TDR_API int tdr_umap_step_p2p_f32(const float* Z_in, float* Z_out, int64_t n_tot
                                   double* gnorm_sq, int* nan_flag,
                                   const uint64_t* peer_out_ptrs, int n_peers, tdr_stream_t stream);
 
+/* n_steps sharded iterations without returning to the host language: step kernel with fused peer
+ * stores (above) + a one-warp barrier kernel on peer-mapped flags between iterations.  Z_a/Z_b are this
+ * rank's two embedding buffers, peers_a/peers_b the peers' addresses of the same two buffers (HOST
+ * arrays, n_peers = world - 1 entries, ranks ascending without this rank); my_flags is this rank's
+ * zero-initialised uint32[world] flag buffer and peer_flags the peers' addresses of theirs; epoch0 is
+ * the number of barriers already executed on these flags.  Result in Z_a if n_steps is even. */
+TDR_API int tdr_umap_run_p2p_f32(float* Z_a, float* Z_b, int64_t n_total, int64_t row0, int64_t n_local,
+                                 const int64_t* rowptr, const int32_t* col,
+                                 const float* epochs_per_sample, float* epoch_of_next_sample,
+                                 int n_neg, int negative_sample_rate, uint64_t seed, int64_t n_iter0,
+                                 int n_steps, const float* lrs_host,
+                                 double a, double b, float lam, float repulsion,
+                                 double* gnorm_sq, int* nan_flag,
+                                 const uint64_t* peers_a, const uint64_t* peers_b,
+                                 uint32_t* my_flags, const uint64_t* peer_flags, int n_peers,
+                                 int rank, int world, uint32_t epoch0, tdr_stream_t stream);
+
 /* LargeVis gradient (largevis.py:181-201 differentiated): accumulates into
  * grad[n_total,2] (zeroed by the caller) with atomics — the autograd scatter of
  * affinity_matcher.py:418-425 — for local rows; P/idx are the directed kNN rows. */

@@ -92,7 +92,18 @@ try:
         Zp, Zq = Zq, Zp
         cur = 1 - cur
     report("p2p-fused step: 8 iterations bit-identical to the all-gather path", torch.equal(Zp, Zc))
+    # native multi-step loop (flag barrier kernel instead of the host-driven barrier)
+    peer2 = PeerEmbedding(Z0)
+    c2 = ops.umap_run_p2p(peer2, 0, s, e - s, g_loc[0], g_loc[1], g_loc[2], g_loc[3].clone(), 0, lrs, pa, pb, seed=11)
+    torch.cuda.synchronize()
+    report("native p2p loop (tdr_umap_run_p2p_f32): 8 iterations bit-identical", torch.equal(peer2.bufs[c2], Zc))
     import time
+    e3 = g_loc[3].clone()
+    torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+    c2 = ops.umap_run_p2p(peer2, c2, s, e - s, g_loc[0], g_loc[1], g_loc[2], e3, 8, [0.5] * 200, pa, pb, seed=11)
+    torch.cuda.synchronize(); t_nat = (time.perf_counter() - t0) / 200
+    if rank == 0:
+        print(f"[dist_check] native p2p loop per-iteration wall time at n={n}: {t_nat*1e6:.1f} us", flush=True)
     torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
     for t in range(200):
         ops.umap_step_p2p(Zp, Zq, s, e - s, g_loc[0], g_loc[1], g_loc[2], eons2, 8 + t, pa, pb, 0.5, peer.peer_ptrs(1 - cur), seed=11)

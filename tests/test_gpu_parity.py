@@ -558,6 +558,27 @@ def test_long_run_quality_matches_reference_path():
     assert np_ref > 0.1 and abs(np_eng - np_ref) < 0.03
 
 
+def test_pca_init_matches_reference_formula():
+    """init="pca": covariance + eigh on the device vs the reference's full-SVD PCA with svd_flip
+    (spectral_embedding/pca.py:171-178, utils/utils.py:264-301), then the common 1e-4/std rescale."""
+    from torchdr_b200.neighbor_embedding import _pca_init
+
+    X = blobs(700, 20, 6, 11)
+    Xc = X - X.mean(0, keepdim=True)
+    U, S, Vt = torch.linalg.svd(Xc, full_matrices=False)
+    max_abs = U.abs().argmax(0)
+    signs = torch.sign(U[max_abs, torch.arange(U.shape[1])])
+    ref = (U * signs)[:, :2] * S[:2]
+    got = _pca_init(_cuda(X), 2).cpu()
+    assert rel_fro(got, ref) < 1e-4
+    import torchdr_b200 as tb
+
+    m = tb.UMAP(n_neighbors=10, max_iter=1, init="pca", process_duplicates=False)
+    m._setup_distributed(False)
+    Z0 = m._init_embedding(_cuda(X)).cpu()
+    torch.testing.assert_close(Z0[:, 0].std(), torch.tensor(1e-4), rtol=1e-4, atol=0)  # affinity_matcher.py:550
+
+
 def test_estimator_edge_cases():
     """Input handling the reference covers: duplicates (base.py:132-146), non-finite input, too few samples,
     torch / numpy round trip, tiny inputs, ragged sizes around the 128-row tiles."""

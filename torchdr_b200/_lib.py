@@ -55,6 +55,10 @@ SIGNATURES = {
     "tdr_umap_step_p2p_f32": (c_int, [P, P, c_int64, c_int64, c_int64, P, P, P, P, c_int, c_int, c_uint64, c_int64,
                                       c_double, c_double, c_float, c_float, c_float, P, P,
                                       ctypes.POINTER(c_uint64), c_int, P]),
+    "tdr_umap_run_p2p_f32": (c_int, [P, P, c_int64, c_int64, c_int64, P, P, P, P, c_int, c_int, c_uint64, c_int64, c_int,
+                                     ctypes.POINTER(c_float), c_double, c_double, c_float, c_float, P, P,
+                                     ctypes.POINTER(c_uint64), ctypes.POINTER(c_uint64), P, ctypes.POINTER(c_uint64),
+                                     c_int, c_int, c_int, ctypes.c_uint32, P]),
     "tdr_largevis_grad_f32": (c_int, [P, c_int64, c_int64, c_int64, P, P, c_int, P, c_int, c_uint64, c_int64,
                                       c_float, c_float, P, P]),
     "tdr_tsne_workspace_bytes": (c_size_t, [c_int64]),

@@ -454,3 +454,62 @@ extern "C" TDR_API int tdr_umap_run_f32(float* Z_a, float* Z_b, int64_t n_total,
     }
     return TDR_OK;
 }
+
+// ---- cross-GPU barrier on peer-mapped flags + the multi-step sharded loop -------------------------------
+// flags: one uint32 per rank in EVERY rank's (zero-initialised, peer-mapped) flag buffer.  Rank r announces epoch
+// E by storing E into slot r of every peer's buffer, then waits until every slot of its own buffer has reached E.
+// Launched on the stream right after the step kernel, so the step's peer stores have completed (kernel boundary)
+// before the flag goes out; the next step kernel in the stream starts only after all peers have announced.
+namespace tdr {
+__global__ void peer_barrier_kernel(volatile uint32_t* my_flags, const UmapStepParams peers_as_ptrs, int n_peers,
+                                    int my_rank, int world, uint32_t epoch) {
+    const int lane = threadIdx.x;
+    if (lane < n_peers) {
+        __threadfence_system();
+        volatile uint32_t* remote = reinterpret_cast<volatile uint32_t*>(peers_as_ptrs.peer_out[lane]);
+        remote[my_rank] = epoch;
+    }
+    if (lane < world && lane != my_rank) {
+        while ((int32_t)(my_flags[lane] - epoch) < 0) {
+        }
+    }
+    __threadfence_system();
+}
+}  // namespace tdr
+
+extern "C" TDR_API int tdr_umap_run_p2p_f32(float* Z_a, float* Z_b, int64_t n_total, int64_t row0, int64_t n_local,
+                                            const int64_t* rowptr, const int32_t* col, const float* epochs_per_sample,
+                                            float* epoch_of_next_sample, int n_neg, int negative_sample_rate,
+                                            uint64_t seed, int64_t n_iter0, int n_steps, const float* lrs_host, double a,
+                                            double b, float lam, float repulsion, double* gnorm_sq, int* nan_flag,
+                                            const uint64_t* peers_a /*host*/, const uint64_t* peers_b /*host*/,
+                                            uint32_t* my_flags, const uint64_t* peer_flags /*host*/, int n_peers,
+                                            int rank, int world, uint32_t epoch0, tdr_stream_t stream) {
+    TDR_CHECK_ARG(Z_a && Z_b && Z_a != Z_b && lrs_host && n_steps >= 0 && my_flags && peers_a && peers_b && peer_flags,
+                  "tdr_umap_run_p2p_f32: bad arguments");
+    TDR_CHECK_ARG(n_peers >= 1 && n_peers <= 8 && world == n_peers + 1 && rank >= 0 && rank < world,
+                  "tdr_umap_run_p2p_f32: 2..9 ranks");
+    UmapStepParams fl{};
+    for (int q = 0; q < n_peers; ++q) fl.peer_out[q] = reinterpret_cast<float2*>(peer_flags[q]);
+    float* src = Z_a;
+    float* dst = Z_b;
+    const uint64_t* dst_peers = peers_b;
+    const uint64_t* src_peers = peers_a;
+    for (int t = 0; t < n_steps; ++t) {
+        int rc = tdr_umap_step_p2p_f32(src, dst, n_total, row0, n_local, rowptr, col, epochs_per_sample,
+                                       epoch_of_next_sample, n_neg, negative_sample_rate, seed, n_iter0 + t, a, b, lam,
+                                       repulsion, lrs_host[t], (t == n_steps - 1) ? gnorm_sq : nullptr, nan_flag,
+                                       dst_peers, n_peers, stream);
+        if (rc != TDR_OK) return rc;
+        tdr::peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(my_flags, fl, n_peers, rank, world,
+                                                                     epoch0 + (uint32_t)t + 1u);
+        TDR_LAUNCH_CHECK();
+        float* tmp = src;
+        src = dst;
+        dst = tmp;
+        const uint64_t* tp = src_peers;
+        src_peers = dst_peers;
+        dst_peers = tp;
+    }
+    return TDR_OK;
+}

@@ -142,10 +142,22 @@ class PeerEmbedding:
             t = symm.empty(tuple(Z0.shape), dtype=Z0.dtype, device=Z0.device)
             self.handles.append(symm.rendezvous(t, group))
             self.bufs.append(t)
+        # peer-mapped flag words for the native multi-step loop (tdr_umap_run_p2p_f32): one uint32 per rank
+        self.flags = symm.empty((64,), dtype=torch.int32, device=Z0.device)
+        self.flags.zero_()
+        self.flag_handle = symm.rendezvous(self.flags, group)
+        self.epoch = 0
         self.bufs[0].copy_(Z0)
         self.bufs[1].copy_(Z0)
         torch.cuda.synchronize(Z0.device)
         self.handles[0].barrier(channel=0)
+        import ctypes
+
+        def arr(ptrs):
+            return (ctypes.c_uint64 * len(ptrs))(*ptrs)
+
+        self.ptr_arrays = (arr(self.peer_ptrs(0)), arr(self.peer_ptrs(1)))
+        self.flag_ptr_array = arr([int(p) for r, p in enumerate(self.flag_handle.buffer_ptrs) if r != self.rank])
 
     def peer_ptrs(self, i: int):
         return [int(p) for r, p in enumerate(self.handles[i].buffer_ptrs) if r != self.rank]

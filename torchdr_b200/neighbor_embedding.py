@@ -444,21 +444,16 @@ class UMAP(_NeighborEmbeddingB200):
                 for t in range(step, last + 1):  # schedule bookkeeping up front, launches back to back below
                     lrs.append(self._hyper()[0])
                     self._advance_schedule()
-                ptrs = (peer.peer_ptrs(0), peer.peer_ptrs(1))
-                for t in range(step, last + 1):
-                    lr = lrs[t - step]
-                    want = t == last and t % self.check_interval == 0
-                    if want:
-                        self._gnorm.zero_()
-                    ops.umap_step_p2p(Za, Zb, s, e - s, rowptr, col, eps, eons, t, self._a, self._b, lr,
-                                      ptrs[1 - cur], n_neg=self.n_negatives, rate=self.negative_sample_rate,
-                                      seed=seed, lam=lam, repulsion=rep, gnorm_sq=self._gnorm if want else None,
-                                      nan_flag=self._nan)
-                    peer.barrier(1 - cur)
-                    if want:
-                        dist.all_reduce(self._gnorm, op=dist.ReduceOp.SUM)
-                    Za, Zb = Zb, Za
-                    cur = 1 - cur
+                want = last % self.check_interval == 0
+                if want:
+                    self._gnorm.zero_()
+                # one native call for the whole batch: step kernel (fused NVLink stores) + flag barrier per iteration
+                cur = ops.umap_run_p2p(peer, cur, s, e - s, rowptr, col, eps, eons, step, lrs, self._a, self._b,
+                                       n_neg=self.n_negatives, rate=self.negative_sample_rate, seed=seed, lam=lam,
+                                       repulsion=rep, gnorm_sq=self._gnorm if want else None, nan_flag=self._nan)
+                if want:
+                    dist.all_reduce(self._gnorm, op=dist.ReduceOp.SUM)
+                Za, Zb = peer.bufs[cur], peer.bufs[1 - cur]
                 self.n_iter_ = torch.tensor(last, dtype=torch.long)
                 self.embedding_ = Za
             elif self.world_size > 1 or hooks_per_step:

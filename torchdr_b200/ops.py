@@ -253,6 +253,27 @@ def umap_step_p2p(Z_in, Z_out, row0, n_local, rowptr, col, eps, eons, n_iter, a,
               "tdr_umap_step_p2p_f32")
 
 
+def umap_run_p2p(peer, cur, row0, n_local, rowptr, col, eps, eons, n_iter0, lrs, a, b, n_neg=75, rate=5, seed=0,
+                 lam=1.0, repulsion=1.0, gnorm_sq=None, nan_flag=None):
+    """len(lrs) sharded iterations in one native call (step kernel with fused peer stores + flag barrier).
+
+    ``peer`` is a distributed.PeerEmbedding, ``cur`` the index of the buffer holding the current embedding;
+    returns the index of the buffer holding the result."""
+    lrs = np.ascontiguousarray(lrs, dtype=np.float32)
+    n = len(lrs)
+    pa, pb = peer.ptr_arrays[cur], peer.ptr_arrays[1 - cur]
+    Za, Zb = peer.bufs[cur], peer.bufs[1 - cur]
+    with torch.cuda.device(Za.device):
+        check(_lib.load().tdr_umap_run_p2p_f32(ptr(Za), ptr(Zb), Za.shape[0], row0, n_local, ptr(rowptr), ptr(col),
+                                               ptr(eps), ptr(eons), n_neg, rate, seed, n_iter0, n,
+                                               lrs.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), float(a), float(b),
+                                               float(lam), float(repulsion), ptr(gnorm_sq), ptr(nan_flag), pa, pb,
+                                               ptr(peer.flags), peer.flag_ptr_array, peer.world - 1, peer.rank, peer.world,
+                                               peer.epoch, stream()), "tdr_umap_run_p2p_f32")
+    peer.epoch += n
+    return cur if n % 2 == 0 else 1 - cur
+
+
 def umap_run(Z_a, Z_b, rowptr, col, eps, eons, n_iter0, lrs, a, b, n_neg=75, rate=5, seed=0, lam=1.0,
              repulsion=1.0, precise=False, gnorm_sq=None, nan_flag=None, stats=None):
     """len(lrs) iterations on one GPU; returns the tensor holding the result."""
