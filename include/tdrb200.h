@@ -261,6 +261,25 @@ TDR_API int tdr_tsne_grad_f32(const float* Z, int64_t n_total, int64_t row0, int
                       const float* P, const int32_t* idx, int k, float lam, int phase,
                       float* grad, void* ws, size_t ws_bytes, tdr_stream_t stream);
 
+/* InfoTSNE gradient (infotsne.py:179-197 differentiated): t-SNE attraction on the kNN rows plus the
+ * noise-contrastive repulsion (1/N) sum_i log sum_{s in Neg(i)} 1/(1+D_is); both scatter into row i
+ * and the sampled rows like autograd's index_put(accumulate).  Arguments as tdr_largevis_grad_f32
+ * (neg = NULL draws the n_neg negatives per row in-kernel, NE base.py:629-636); grad is caller-zeroed. */
+TDR_API int tdr_infotsne_grad_f32(const float* Z, int64_t n_total, int64_t row0, int64_t n_local,
+                          const float* P, const int32_t* idx, int k,
+                          const int64_t* neg, int n_neg, uint64_t seed, int64_t n_iter,
+                          float lam, float repulsion, float* grad /*[n_total,2]*/, tdr_stream_t stream);
+
+/* SNE gradient (sne.py:162-179 differentiated): attraction lam * sum P_ij D_ij on the kNN rows plus the
+ * dense repulsion (1/N) sum_i log sum_j exp(-C_ij) (expanded-form C on the embedding, diagonal included).
+ *   phase 0: row_sums[row0 .. row0+n_local) = sum_j exp(-C_ij); attraction scattered into grad (caller-zeroed).
+ *   (host: all-gather row_sums when distributed)
+ *   phase 1: grad[local rows] += -(2 repulsion / N) sum_j e_ij (1/S_i + 1/S_j)(z_i - z_j).
+ * row_sums: float [n_total]. */
+TDR_API int tdr_sne_grad_f32(const float* Z, int64_t n_total, int64_t row0, int64_t n_local,
+                     const float* P, const int32_t* idx, int k, float lam, float repulsion, int phase,
+                     float* grad, float* row_sums, tdr_stream_t stream);
+
 /* SGD with momentum (torch.optim.SGD semantics: buf = mu*buf + g; z -= lr*buf; first
  * step buf = g), NE base.py:331-343.  first != 0 initialises the buffer. */
 TDR_API int tdr_sgd_momentum_f32(float* Z, float* buf, const float* grad, int64_t n_elems,

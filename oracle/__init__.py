@@ -19,7 +19,7 @@ Rules (enforced by ``tests/test_layout.py``):
 Parity pinning: the reference ships no golden vectors for this path (its tests
 check properties only).  The oracle is therefore pinned
 against outputs of the reference itself, generated in the build container by
-``tests/golden/make_golden.py`` (which imports ``/root/reference/torchdr``) and
+``tests/golden/make_golden.py`` / ``make_golden_more.py`` (which import ``/root/reference/torchdr``) and
 committed as ``tests/golden/*.npz``.  ``tests/test_oracle_golden.py`` checks
 every oracle function against those files.
 """
@@ -48,4 +48,6 @@ from .umap import (  # noqa: F401
 )
 from .largevis import largevis_run  # noqa: F401
 from .tsne import tsne_run  # noqa: F401
+from .infotsne import infotsne_run, infotsne_loss  # noqa: F401
+from .sne import sne_run, sne_loss  # noqa: F401
 from .partition import chunk_bounds, owner_of  # noqa: F401

@@ -123,7 +123,8 @@ except Exception as exc:
 # ---- estimators under torchrun
 Xh = X.cpu().numpy()
 for cls, kw in ((tb.UMAP, dict(n_neighbors=15, max_iter=60)), (tb.LargeVis, dict(perplexity=10, max_iter=40)),
-                (tb.TSNE, dict(perplexity=10, max_iter=30))):
+                (tb.TSNE, dict(perplexity=10, max_iter=30)), (tb.InfoTSNE, dict(perplexity=10, max_iter=30, n_negatives=64)),
+                (tb.SNE, dict(perplexity=10, max_iter=30))):
     m = cls(init="normal", random_state=0, process_duplicates=False, **kw)
     Z = m.fit_transform(Xh)
     fin = bool(np.isfinite(Z).all()) and Z.shape == (n, 2)
@@ -132,6 +133,15 @@ for cls, kw in ((tb.UMAP, dict(n_neighbors=15, max_iter=60)), (tb.LargeVis, dict
     dist.broadcast(Z0r, src=0)
     same = float((Zt - Z0r).abs().max())
     report(f"{cls.__name__} fit under torchrun x{world}: finite={fin}, max |rank0 - rank{rank}| = {same:.1e}", fin and same == 0.0)
+
+# row-sharded dense SNE / sampled InfoTSNE vs the same fit on one GPU (short run, injected init)
+g0 = torch.Generator().manual_seed(3)
+Zi = torch.randn(n, 2, generator=g0)
+for cls, kw in ((tb.SNE, dict(perplexity=10, max_iter=5)), (tb.InfoTSNE, dict(perplexity=10, max_iter=5, n_negatives=64))):
+    Zd = cls(init=Zi, random_state=0, process_duplicates=False, **kw).fit_transform(Xh)
+    Zs = cls(init=Zi, random_state=0, process_duplicates=False, distributed=False, **kw).fit_transform(Xh)
+    rel = float(np.linalg.norm(Zd - Zs) / np.linalg.norm(Zs))
+    report(f"{cls.__name__}: {world}-GPU fit vs single-GPU fit after 5 iterations (rel {rel:.2e})", rel < 1e-3)
 
 t = torch.tensor([1.0 if ok else 0.0], device=dev)
 dist.all_reduce(t, op=dist.ReduceOp.MIN)

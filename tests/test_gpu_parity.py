@@ -431,6 +431,83 @@ def test_tsne_gradient_and_steps(ops):
             assert rel_fro(Z.cpu(), g[f"Z_{step + 1}"]) < 1e-4, step
 
 
+def test_infotsne_gradient_and_steps(ops):
+    g = golden("infotsne_n300_d16_p10")
+    seed, n_neg = int(g["seed"]), int(g["n_neg"])
+    P, I = _cuda(t(g["P"])), _cuda(t(g["I"]))
+    Z = _cuda(t(g["Z0"])).clone()
+    grad = torch.zeros(300, 2, device=DEV)
+    ops.infotsne_grad(Z, 0, 300, P, I, grad, 0, neg=_cuda(negative_table(seed, 0, 300, n_neg)), n_neg=n_neg, lam=12.0)
+    assert rel_fro(grad.cpu(), g["G_1"]) < 1e-5
+    mom = torch.zeros_like(Z)
+    lam, first, mu = 12.0, True, 0.5
+    for step in range(12):
+        grad.zero_()
+        ops.infotsne_grad(Z, 0, 300, P, I, grad, step, neg=_cuda(negative_table(seed, step, 300, n_neg)),
+                          n_neg=n_neg, lam=lam)
+        if step + 1 in (2, 5, 12):
+            assert rel_fro(grad.cpu(), g[f"G_{step + 1}"]) < 1e-3, step
+        ops.sgd_momentum(Z, mom, grad, float(g["lr"][step]), mu, first)  # momentum keeps its first-build value
+        first = False
+        if step == int(g["exag_iter"]):
+            lam, first = 1.0, True
+        if step + 1 in (1, 2, 5, 10, 11, 12):
+            assert rel_fro(Z.cpu(), g[f"Z_{step + 1}"]) < 1e-4, step
+    # n_neg beyond the register cache (320) and in-kernel draws: gradient against the oracle's autograd
+    n_big = 400
+    Zc = t(g["Z0"]) * 1e4
+    neg = negative_table(seed, 3, 300, n_big)
+    Zp = Zc.clone().requires_grad_(True)
+    oracle.infotsne_loss(Zp, t(g["P"]), t(g["I"]), neg, torch.arange(300), 300, lam=1.0).backward()
+    grad.zero_()
+    ops.infotsne_grad(_cuda(Zc), 0, 300, P, I, grad, 3, neg=_cuda(neg), n_neg=n_big, lam=1.0)
+    assert rel_fro(grad.cpu(), Zp.grad) < 1e-5
+    # partitioned rows scatter into the same buffer
+    grad2 = torch.zeros_like(grad)
+    for s0, e0 in ((0, 101), (101, 300)):
+        ops.infotsne_grad(_cuda(Zc), s0, e0 - s0, P[s0:e0].contiguous(), I[s0:e0].contiguous(), grad2, 3,
+                          neg=_cuda(neg[s0:e0].contiguous()), n_neg=n_big, lam=1.0)
+    assert rel_fro(grad2.cpu(), Zp.grad) < 1e-5
+    grad.zero_()
+    ops.infotsne_grad(_cuda(Zc), 0, 300, P, I, grad, 3, neg=None, n_neg=n_big, seed=5, lam=1.0)  # Philox negatives
+    assert torch.isfinite(grad).all() and 0.5 < float(grad.norm() / Zp.grad.norm()) < 2.0
+
+
+def test_sne_gradient_and_steps(ops):
+    g = golden("sne_n300_d16_p10")
+    P, I = _cuda(t(g["P"])), _cuda(t(g["I"]))
+    Z = _cuda(t(g["Z0"])).clone()
+    rows = torch.zeros(300, 1, device=DEV)
+    grad = torch.zeros(300, 2, device=DEV)
+
+    def gradient(Zc, out, bounds=((0, 300),)):
+        out.zero_()
+        for s0, e0 in bounds:
+            ops.sne_grad(Zc, s0, e0 - s0, P[s0:e0].contiguous(), I[s0:e0].contiguous(), 1.0, 1.0, 0, out, rows)
+        for s0, e0 in bounds:
+            ops.sne_grad(Zc, s0, e0 - s0, P[s0:e0].contiguous(), I[s0:e0].contiguous(), 1.0, 1.0, 1, out, rows)
+
+    gradient(Z, grad)
+    assert rel_fro(grad.cpu(), g["G_1"]) < 1e-5
+    mom = torch.zeros_like(Z)
+    for step in range(10):
+        gradient(Z, grad)
+        if step + 1 in (2, 5, 10):
+            assert rel_fro(grad.cpu(), g[f"G_{step + 1}"]) < 1e-3, step
+        ops.sgd_momentum(Z, mom, grad, float(g["lr"][step]), 0.8, step == 0)
+        if step + 1 in (1, 2, 5, 10):
+            assert rel_fro(Z.cpu(), g[f"Z_{step + 1}"]) < 1e-4, step
+    # spread-out embedding (row normalisers far from N) + row partition
+    Zc = t(g["Z0"]) * 2e4
+    Zp = Zc.clone().requires_grad_(True)
+    oracle.sne_loss(Zp, t(g["P"]), t(g["I"]), torch.arange(300)).backward()
+    gradient(_cuda(Zc), grad)
+    assert rel_fro(grad.cpu(), Zp.grad) < 1e-5
+    grad2 = torch.zeros_like(grad)
+    gradient(_cuda(Zc), grad2, bounds=((0, 77), (77, 300)))
+    assert rel_fro(grad2.cpu(), Zp.grad) < 1e-5
+
+
 # --------------------------------------------------------------------------- seams
 def test_pairwise_distances_seam():
     import torchdr_b200 as tb
@@ -513,7 +590,9 @@ def test_estimators_end_to_end():
     X = X.astype(np.float32)
     for cls, kw in ((tb.UMAP, dict(n_neighbors=15, max_iter=200)),
                     (tb.LargeVis, dict(perplexity=20, max_iter=200)),
-                    (tb.TSNE, dict(perplexity=20, max_iter=300))):
+                    (tb.TSNE, dict(perplexity=20, max_iter=300)),
+                    (tb.InfoTSNE, dict(perplexity=20, max_iter=300, n_negatives=100)),
+                    (tb.SNE, dict(perplexity=20, max_iter=300))):
         m = cls(init="normal", random_state=0, **kw)
         Z = m.fit_transform(X)
         assert isinstance(Z, np.ndarray) and Z.shape == (600, 2) and np.isfinite(Z).all()
@@ -523,6 +602,38 @@ def test_estimators_end_to_end():
     assert isinstance(Zt, torch.Tensor) and Zt.device.type == "cpu"
     with pytest.raises(ValueError, match="smaller than n_neighbors"):
         tb.UMAP(n_neighbors=700).fit_transform(X)
+
+
+def test_eval_metrics_on_the_knn_kernel():
+    """knn_label_accuracy (eval/knn_labels.py:176-186) and neighborhood_preservation
+    (eval/neighborhood_preservation.py:166-171) against the same formulas on the oracle's kNN."""
+    from sklearn.datasets import make_blobs
+
+    import torchdr_b200 as tb
+
+    Xn, y = make_blobs(n_samples=900, n_features=12, centers=6, cluster_std=3.0, random_state=1)
+    X = torch.from_numpy(Xn.astype(np.float32))
+    lab = torch.from_numpy(y)
+    k = 10
+    _, I = oracle.knn_dense(X, k)
+    _, _, _, set_ok = oracle.knn_ambiguity(X, k)
+    want = (lab[I.long()] == lab.unsqueeze(1)).float().mean(1)
+    got = tb.knn_label_accuracy(X, lab, k=k, return_per_sample=True)
+    assert isinstance(got, torch.Tensor) and got.shape == (900,)
+    assert torch.equal(got.cpu()[set_ok], want[set_ok])
+    acc = tb.knn_label_accuracy(Xn.astype(np.float32), y, k=k)
+    assert isinstance(acc, float) and abs(acc - float(want.mean())) < 2e-3 and 0.3 < acc < 1.0
+    Z = X[:, :2].contiguous()
+    _, Iz = oracle.knn_dense(Z, k)
+    _, _, _, set_ok_z = oracle.knn_ambiguity(Z, k)
+    want_np = (I.unsqueeze(2) == Iz.unsqueeze(1)).any(2).float().sum(1) / k
+    got_np = tb.neighborhood_preservation(X, Z, K=k, return_per_sample=True).cpu()
+    both = set_ok & set_ok_z
+    assert torch.equal(got_np[both], want_np[both])
+    with pytest.raises(ValueError, match="must be less than number of samples"):
+        tb.knn_label_accuracy(X, lab, k=900)
+    with pytest.raises(ValueError, match="same number of samples"):
+        tb.neighborhood_preservation(X, Z[:10], K=3)
 
 
 def test_long_run_quality_matches_reference_path():

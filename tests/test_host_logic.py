@@ -101,6 +101,11 @@ def test_constructor_surface_and_errors():
     assert (m.n_neighbors, m.max_iter, m.lr, m.n_negatives, m.init) == (30, 1000, 1.0, 150, "pca")
     assert abs(m._a - 1.5769434602697652) < 1e-12 and abs(m._b - 0.8950608778515733) < 1e-12
     assert tb.TSNE().early_exaggeration_coeff == 12.0 and tb.LargeVis().n_negatives == 5
+    it, sn = tb.InfoTSNE(), tb.SNE()  # infotsne.py:106-136, sne.py:95-120
+    assert (it.n_negatives, it.early_exaggeration_coeff, it.early_exaggeration_iter, it.max_iter, it.scheduler) == \
+        (300, 12, 250, 1000, "LinearLR")
+    assert (sn.early_exaggeration_coeff, sn.early_exaggeration_iter, sn.max_iter, sn.scheduler, sn.lr) == \
+        (1, 0, 2000, None, "auto")
     with pytest.raises(ValueError, match="distance is not supported"):
         tb.UMAPAffinity(metric="chebyshev")
     with pytest.raises(RuntimeError, match="requires launching with torchrun"):

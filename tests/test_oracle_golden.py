@@ -181,6 +181,27 @@ def test_tsne_run():
     assert torch.equal(Z, t(g["Z_20"]))
 
 
+def test_infotsne_run():
+    g = golden("infotsne_n300_d16_p10")
+    seed, n_neg = int(g["seed"]), int(g["n_neg"])
+    negs = [negative_table(seed, s, 300, n_neg) for s in range(20)]
+    assert torch.equal(negs[0].int(), t(g["neg0"]))
+    Z, lrs, grads = oracle.infotsne_run(t(g["Z0"]), t(g["P"]), t(g["I"]), negs, 20, exag_iter=int(g["exag_iter"]),
+                                        return_grads=True)
+    np.testing.assert_allclose(np.asarray(lrs), g["lr"], rtol=1e-12)  # incl. the scheduler rebuilt at the switch
+    assert torch.equal(grads[0], t(g["G_1"]))
+    assert torch.equal(grads[11], t(g["G_12"]))
+    assert torch.equal(Z, t(g["Z_20"]))
+
+
+def test_sne_run():
+    g = golden("sne_n300_d16_p10")
+    Z, grads = oracle.sne_run(t(g["Z0"]), t(g["P"]), t(g["I"]), 20, return_grads=True)
+    assert torch.equal(grads[0], t(g["G_1"]))
+    assert torch.equal(grads[9], t(g["G_10"]))
+    assert torch.equal(Z, t(g["Z_20"]))
+
+
 def test_partition():
     for n, w in [(100, 4), (10, 3), (7, 8), (50_000_000, 8)]:
         prev = 0

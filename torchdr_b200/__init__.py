@@ -7,9 +7,9 @@ through the C ABI of ``include/tdrb200.h`` (``torchdr_b200/lib/libtdrb200.so``).
 from . import _lib  # noqa: F401
 from .distance import pairwise_distances, pairwise_distances_indexed, LIST_METRICS_B200  # noqa: F401
 from .affinity import UMAPAffinity, EntropicAffinity  # noqa: F401
-from .neighbor_embedding import UMAP, LargeVis, TSNE  # noqa: F401
+from .neighbor_embedding import UMAP, LargeVis, TSNE, InfoTSNE, SNE  # noqa: F401
 from .distributed import DistributedContext  # noqa: F401
-from .eval import neighborhood_preservation  # noqa: F401
+from .eval import neighborhood_preservation, knn_label_accuracy  # noqa: F401
 
 __all__ = [
     "pairwise_distances",
@@ -19,6 +19,9 @@ __all__ = [
     "UMAP",
     "LargeVis",
     "TSNE",
+    "InfoTSNE",
+    "SNE",
     "DistributedContext",
     "neighborhood_preservation",
+    "knn_label_accuracy",
 ]

@@ -10,6 +10,12 @@
 //   attraction on the directed kNN edges: dL/dD = lam P/(1+D);
 //   repulsion = log sum_{all i,j} 1/(1+C_ij) with C in the expanded form of
 //   distance/torch.py:89-91, diagonal included:  grad_i = -(4/S) sum_j w_ij^2 (z_i - z_j).
+// InfoTSNE  torchdr/neighbor_embedding/infotsne.py:179-197
+//   attraction as t-SNE; repulsion = (1/N) sum_i log sum_{s in Neg(i)} 1/(1+D_is):
+//   dL/dD_is = -(rep/N) w_is^2 / S_i,  w = 1/(1+D), S_i = sum_s w_is  (softmax of log Q times dlogQ/dD).
+// SNE       torchdr/neighbor_embedding/sne.py:162-179
+//   attraction sum P_ij D_ij (dL/dD = lam P); repulsion = (1/N) sum_i log sum_j exp(-C_ij), C the expanded
+//   form on the embedding, diagonal included:  grad_i = -(2 rep/N) sum_j e_ij (1/S_i + 1/S_j)(z_i - z_j).
 // SGD       torch.optim.SGD with momentum (NE base.py:331-343).
 #include "common.cuh"
 
@@ -151,6 +157,146 @@ tsne_repulse_kernel(const float2* __restrict__ Z, int64_t n_total, int64_t row0,
     }
 }
 
+// mode 0: c = 2 lam P/(1+D) (t-SNE, InfoTSNE);  mode 1: c = 2 lam P (SNE, sne.py:170)
+template <int MODE>
+__global__ void __launch_bounds__(kAgWarps * 32)
+edge_attract_kernel(const float2* __restrict__ Z, int64_t row0, int64_t n_local, const float* __restrict__ P,
+                    const int32_t* __restrict__ idx, int k, float lam, float* __restrict__ grad) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * kAgWarps + (threadIdx.x >> 5);
+    if (r >= n_local) return;
+    const int64_t gi = row0 + r;
+    const float2 zi = __ldg(Z + gi);
+    float gx = 0.0f, gy = 0.0f;
+    for (int s = lane; s < k; s += 32) {
+        const int64_t j = __ldg(idx + r * k + s);
+        const float2 zj = __ldg(Z + j);
+        const float dx = __fsub_rn(zi.x, zj.x), dy = __fsub_rn(zi.y, zj.y);
+        float c = 2.0f * lam * __ldg(P + r * k + s);
+        if (MODE == 0) c = __fdiv_rn(c, __fadd_rn(1.0f, __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))));
+        const float cx = c * dx, cy = c * dy;
+        gx += cx;
+        gy += cy;
+        atomicAdd(reinterpret_cast<float2*>(grad) + j, make_float2(-cx, -cy));
+    }
+    gx = warp_sum(gx);
+    gy = warp_sum(gy);
+    if (lane == 0) atomicAdd(reinterpret_cast<float2*>(grad) + gi, make_float2(gx, gy));
+}
+
+// InfoTSNE repulsion: one warp per row; each lane keeps up to kInfoCache of its negatives (index, w, dx, dy) in
+// registers between the normaliser pass and the gradient pass (n_neg <= 32 * kInfoCache = 320 covers the
+// default 300); slots beyond that are recomputed.
+constexpr int kInfoCache = 10;
+
+__global__ void __launch_bounds__(kAgWarps * 32)
+infotsne_repulse_kernel(const float2* __restrict__ Z, int64_t n_total, int64_t row0, int64_t n_local,
+                        const int64_t* __restrict__ neg, int n_neg, uint64_t seed, int64_t n_iter,
+                        float rep_over_n, float* __restrict__ grad) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * kAgWarps + (threadIdx.x >> 5);
+    if (r >= n_local) return;
+    const int64_t gi = row0 + r;
+    const float2 zi = __ldg(Z + gi);
+    const Philox rng(seed);
+    int64_t cj[kInfoCache];
+    float cw[kInfoCache], cdx[kInfoCache], cdy[kInfoCache];
+    float S = 0.0f;
+#pragma unroll
+    for (int u = 0; u < kInfoCache; ++u) {
+        const int s = lane + 32 * u;
+        cw[u] = 0.0f; cdx[u] = 0.0f; cdy[u] = 0.0f; cj[u] = gi;
+        if (s < n_neg) {
+            cj[u] = neg ? __ldg(neg + r * n_neg + s) : draw_negative(rng, n_iter, gi, s, n_total);
+            const float2 zj = __ldg(Z + cj[u]);
+            cdx[u] = __fsub_rn(zi.x, zj.x);
+            cdy[u] = __fsub_rn(zi.y, zj.y);
+            cw[u] = __fdiv_rn(1.0f, __fadd_rn(1.0f, __fadd_rn(__fmul_rn(cdx[u], cdx[u]), __fmul_rn(cdy[u], cdy[u]))));
+            S += cw[u];
+        }
+    }
+    for (int s = lane + 32 * kInfoCache; s < n_neg; s += 32) {
+        const int64_t j = neg ? __ldg(neg + r * n_neg + s) : draw_negative(rng, n_iter, gi, s, n_total);
+        const float2 zj = __ldg(Z + j);
+        const float dx = __fsub_rn(zi.x, zj.x), dy = __fsub_rn(zi.y, zj.y);
+        S += __fdiv_rn(1.0f, __fadd_rn(1.0f, __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))));
+    }
+    S = warp_sum(S);
+    const float scale = -2.0f * rep_over_n / S;  // infotsne.py:197: logsumexp over the row, / n_samples_in_
+    float gx = 0.0f, gy = 0.0f;
+#pragma unroll
+    for (int u = 0; u < kInfoCache; ++u) {
+        if (lane + 32 * u < n_neg) {
+            const float c = scale * cw[u] * cw[u];
+            const float cx = c * cdx[u], cy = c * cdy[u];
+            gx += cx;
+            gy += cy;
+            atomicAdd(reinterpret_cast<float2*>(grad) + cj[u], make_float2(-cx, -cy));
+        }
+    }
+    for (int s = lane + 32 * kInfoCache; s < n_neg; s += 32) {
+        const int64_t j = neg ? __ldg(neg + r * n_neg + s) : draw_negative(rng, n_iter, gi, s, n_total);
+        const float2 zj = __ldg(Z + j);
+        const float dx = __fsub_rn(zi.x, zj.x), dy = __fsub_rn(zi.y, zj.y);
+        const float w = __fdiv_rn(1.0f, __fadd_rn(1.0f, __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))));
+        const float c = scale * w * w;
+        const float cx = c * dx, cy = c * dy;
+        gx += cx;
+        gy += cy;
+        atomicAdd(reinterpret_cast<float2*>(grad) + j, make_float2(-cx, -cy));
+    }
+    gx = warp_sum(gx);
+    gy = warp_sum(gy);
+    if (lane == 0) atomicAdd(reinterpret_cast<float2*>(grad) + gi, make_float2(gx, gy));
+}
+
+// SNE dense repulsion, same tiling as tsne_repulse_kernel.  PHASE 0: row normalisers S_i = sum_j exp(-C_ij)
+// (atomically accumulated over the j splits);  PHASE 1: u_i = sum_j e_ij (1/S_i + 1/S_j)(z_i - z_j).
+template <int PHASE>
+__global__ void __launch_bounds__(TSNE_TI)
+sne_repulse_kernel(const float2* __restrict__ Z, int64_t n_total, int64_t row0, int64_t n_local,
+                   int64_t j_per_split, float* __restrict__ S /*[n_total]*/, float scale,
+                   float* __restrict__ grad) {
+    __shared__ float4 tile[TSNE_TJ];
+    const int64_t r = (int64_t)blockIdx.x * TSNE_TI + threadIdx.x;
+    const bool live = r < n_local;
+    const float2 zi = live ? __ldg(Z + row0 + r) : make_float2(0.f, 0.f);
+    const float ni = fmaf(zi.x, zi.x, zi.y * zi.y);
+    const float inv_si = (PHASE == 1 && live) ? __frcp_rn(S[row0 + r]) : 0.0f;
+    float ux = 0.0f, uy = 0.0f, s = 0.0f;
+    const int64_t j_begin = (int64_t)blockIdx.y * j_per_split;
+    const int64_t j_end = min(n_total, j_begin + j_per_split);
+    for (int64_t j0 = j_begin; j0 < j_end; j0 += TSNE_TJ) {
+        const int cnt = (int)min((int64_t)TSNE_TJ, j_end - j0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < cnt; t += TSNE_TI) {
+            const float2 zj = __ldg(Z + j0 + t);
+            tile[t] = make_float4(zj.x, zj.y, fmaf(zj.x, zj.x, zj.y * zj.y), PHASE == 1 ? __frcp_rn(S[j0 + t]) : 0.f);
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int t = 0; t < cnt; ++t) {
+            const float4 zj = tile[t];
+            const float C = __fsub_rn(__fadd_rn(ni, zj.z), 2.0f * fmaf(zi.x, zj.x, zi.y * zj.y));  // distance/torch.py:89-91
+            const float e = __expf(-C);
+            if (PHASE == 0) {
+                s += e;
+            } else {
+                const float w = e * (inv_si + zj.w);
+                ux = fmaf(w, zi.x - zj.x, ux);
+                uy = fmaf(w, zi.y - zj.y, uy);
+            }
+        }
+    }
+    if (!live) return;
+    if (PHASE == 0) {
+        atomicAdd(S + row0 + r, s);
+    } else {
+        atomicAdd(grad + 2 * (row0 + r), scale * ux);
+        atomicAdd(grad + 2 * (row0 + r) + 1, scale * uy);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 tsne_finish_kernel(const float* __restrict__ U, const double* __restrict__ S, int64_t row0, int64_t n_local,
                    float* __restrict__ grad) {
@@ -234,6 +380,52 @@ extern "C" TDR_API int tdr_tsne_grad_f32(const float* Z, int64_t n_total, int64_
         // S now holds the global normaliser (all-reduced by the host when distributed)
         if (n_local > 0)
             tsne_finish_kernel<<<(unsigned)((2 * n_local + 255) / 256), 256, 0, st>>>(U, S, row0, n_local, grad);
+    }
+    TDR_LAUNCH_CHECK();
+    return TDR_OK;
+}
+
+extern "C" TDR_API int tdr_infotsne_grad_f32(const float* Z, int64_t n_total, int64_t row0, int64_t n_local, const float* P,
+                                     const int32_t* idx, int k, const int64_t* neg, int n_neg, uint64_t seed,
+                                     int64_t n_iter, float lam, float repulsion, float* grad, tdr_stream_t stream) {
+    TDR_CHECK_ARG(Z && P && idx && grad, "tdr_infotsne_grad_f32: null pointer");
+    TDR_CHECK_ARG(n_total >= 2 && row0 >= 0 && n_local >= 0 && row0 + n_local <= n_total && k >= 1 && n_neg >= 1,
+                  "tdr_infotsne_grad_f32: bad shape");
+    if (n_local == 0) return TDR_OK;
+    const unsigned blocks = (unsigned)((n_local + kAgWarps - 1) / kAgWarps);
+    const float2* Z2 = reinterpret_cast<const float2*>(Z);
+    edge_attract_kernel<0><<<blocks, kAgWarps * 32, 0, (cudaStream_t)stream>>>(Z2, row0, n_local, P, idx, k, lam, grad);
+    infotsne_repulse_kernel<<<blocks, kAgWarps * 32, 0, (cudaStream_t)stream>>>(
+        Z2, n_total, row0, n_local, neg, n_neg, seed, n_iter, repulsion / (float)n_total, grad);
+    TDR_LAUNCH_CHECK();
+    return TDR_OK;
+}
+
+extern "C" TDR_API int tdr_sne_grad_f32(const float* Z, int64_t n_total, int64_t row0, int64_t n_local, const float* P,
+                                const int32_t* idx, int k, float lam, float repulsion, int phase, float* grad,
+                                float* row_sums, tdr_stream_t stream) {
+    TDR_CHECK_ARG(Z && grad && row_sums, "tdr_sne_grad_f32: null pointer");
+    TDR_CHECK_ARG(n_total >= 2 && row0 >= 0 && n_local >= 0 && row0 + n_local <= n_total, "tdr_sne_grad_f32: bad shape");
+    TDR_CHECK_ARG(phase == 0 || phase == 1, "tdr_sne_grad_f32: phase must be 0 or 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    const float2* Z2 = reinterpret_cast<const float2*>(Z);
+    if (phase == 0) TDR_CUDA(cudaMemsetAsync(row_sums + row0, 0, (size_t)n_local * sizeof(float), st));
+    if (n_local == 0) return TDR_OK;
+    const unsigned bx = (unsigned)((n_local + TSNE_TI - 1) / TSNE_TI);
+    unsigned by = 1;
+    while ((int64_t)bx * by < 2 * kNumSMs && (int64_t)by * TSNE_TJ * 2 <= n_total) by *= 2;
+    const int64_t per = (n_total + by - 1) / by;
+    const int64_t per_al = (per + TSNE_TJ - 1) / TSNE_TJ * TSNE_TJ;
+    if (phase == 0) {
+        sne_repulse_kernel<0><<<dim3(bx, by), TSNE_TI, 0, st>>>(Z2, n_total, row0, n_local, per_al, row_sums, 0.0f, grad);
+        if (P && idx && k > 0) {
+            const unsigned blocks = (unsigned)((n_local + kAgWarps - 1) / kAgWarps);
+            edge_attract_kernel<1><<<blocks, kAgWarps * 32, 0, st>>>(Z2, row0, n_local, P, idx, k, lam, grad);
+        }
+    } else {
+        // row_sums now holds every row's normaliser (all-gathered by the host when distributed)
+        sne_repulse_kernel<1><<<dim3(bx, by), TSNE_TI, 0, st>>>(Z2, n_total, row0, n_local, per_al, row_sums,
+                                                               -2.0f * repulsion / (float)n_total, grad);
     }
     TDR_LAUNCH_CHECK();
     return TDR_OK;

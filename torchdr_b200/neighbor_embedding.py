@@ -1,8 +1,8 @@
-"""Estimator seam: ``UMAP``, ``LargeVis``, ``TSNE`` with the reference's sklearn-style surface.
+"""Estimator seam: ``UMAP``, ``LargeVis``, ``TSNE``, ``InfoTSNE``, ``SNE`` with the reference's sklearn-style surface.
 
 Mirrors ``torchdr/base.py:27-229`` (``DRModule.fit / fit_transform / transform``),
 ``torchdr/affinity_matcher.py:201-352`` (affinity -> init -> optimisation loop with the
-``on_*`` lifecycle hooks) and ``torchdr/neighbor_embedding/{base,umap,largevis,tsne}.py``.
+``on_*`` lifecycle hooks) and ``torchdr/neighbor_embedding/{base,umap,largevis,tsne,infotsne,sne}.py``.
 The loop body is one CUDA kernel per iteration (UMAP) or two (gradient + momentum SGD); the
 optimiser / scheduler objects are the reference's own ``torch.optim`` classes stepped on a
 dummy parameter, so learning-rate and momentum sequences — including the reference's
@@ -582,4 +582,81 @@ class TSNE(_EntropicInputMixin, _NeighborEmbeddingB200):
     def clear_memory(self):
         if hasattr(self, "_tsne_ws"):
             del self._tsne_ws
+        super().clear_memory()
+
+
+class InfoTSNE(_EntropicInputMixin, _NeighborEmbeddingB200):
+    """``torchdr/neighbor_embedding/infotsne.py:14-197``."""
+
+    def __init__(self, perplexity=30, n_components=2, lr="auto", optimizer="SGD", optimizer_kwargs="auto",
+                 scheduler="LinearLR", scheduler_kwargs=None, init="pca", init_scaling=1e-4, min_grad_norm=1e-7,
+                 max_iter=1000, device="auto", backend=None, verbose=False, random_state=None,
+                 early_exaggeration_coeff=12, early_exaggeration_iter=250, max_iter_affinity=100,
+                 metric="sqeuclidean", n_negatives=300, sparsity=True, check_interval=50, discard_NNs=False,
+                 compile=False, distributed="auto", **kwargs):
+        self.metric = metric
+        self.perplexity = perplexity
+        self.max_iter_affinity = max_iter_affinity
+        self.sparsity = sparsity
+        self.n_negatives = n_negatives
+        if discard_NNs:
+            raise NotImplementedError("[TorchDR-B200] discard_NNs=True is not implemented in the step kernel.")
+        self.discard_NNs = discard_NNs
+        super().__init__(n_components=n_components, lr=lr, optimizer=optimizer, optimizer_kwargs=optimizer_kwargs,
+                         scheduler=scheduler, scheduler_kwargs=scheduler_kwargs, min_grad_norm=min_grad_norm,
+                         max_iter=max_iter, init=init, init_scaling=init_scaling, device=device, backend=backend,
+                         verbose=verbose, random_state=random_state,
+                         early_exaggeration_coeff=early_exaggeration_coeff,
+                         early_exaggeration_iter=early_exaggeration_iter, check_interval=check_interval,
+                         compile=compile, distributed=distributed, **kwargs)
+        self.affinity_in = EntropicAffinity(perplexity=perplexity, metric=metric, max_iter=max_iter_affinity,
+                                            device=self.device, backend=backend, verbose=verbose, sparsity=sparsity,
+                                            distributed=self.distributed)
+
+    def _compute_gradient(self, Z, step):
+        s, e = self.chunk_start_, self.chunk_end_
+        seed = int(self._actual_seed) if self.random_state is not None else 0
+        ops.infotsne_grad(Z, s, e - s, self.affinity_in_, self.NN_indices_, self._grad, step,
+                          neg=getattr(self, "neg_indices_", None), n_neg=self.n_negatives, seed=seed,
+                          lam=float(self.early_exaggeration_coeff_), repulsion=float(self.repulsion_strength))
+
+
+class SNE(_EntropicInputMixin, _NeighborEmbeddingB200):
+    """``torchdr/neighbor_embedding/sne.py:21-179``."""
+
+    def __init__(self, perplexity=30, n_components=2, lr="auto", optimizer="SGD", optimizer_kwargs="auto",
+                 scheduler=None, scheduler_kwargs=None, init="pca", init_scaling=1e-4, min_grad_norm=1e-7,
+                 max_iter=2000, device="auto", backend=None, verbose=False, random_state=None, max_iter_affinity=100,
+                 metric="sqeuclidean", sparsity=True, early_exaggeration_coeff=None, early_exaggeration_iter=None,
+                 check_interval=50, compile=False, distributed="auto", **kwargs):
+        self.metric = metric
+        self.perplexity = perplexity
+        self.max_iter_affinity = max_iter_affinity
+        self.sparsity = sparsity
+        super().__init__(n_components=n_components, lr=lr, optimizer=optimizer, optimizer_kwargs=optimizer_kwargs,
+                         scheduler=scheduler, scheduler_kwargs=scheduler_kwargs, min_grad_norm=min_grad_norm,
+                         max_iter=max_iter, init=init, init_scaling=init_scaling, device=device, backend=backend,
+                         verbose=verbose, random_state=random_state,
+                         early_exaggeration_coeff=early_exaggeration_coeff,
+                         early_exaggeration_iter=early_exaggeration_iter, check_interval=check_interval,
+                         compile=compile, distributed=distributed, **kwargs)
+        self.affinity_in = EntropicAffinity(perplexity=perplexity, metric=metric, max_iter=max_iter_affinity,
+                                            device=self.device, backend=backend, verbose=verbose, sparsity=sparsity,
+                                            distributed=self.distributed)
+
+    def _compute_gradient(self, Z, step):
+        s, e = self.chunk_start_, self.chunk_end_
+        if not hasattr(self, "_sne_rows"):
+            self._sne_rows = torch.zeros((Z.shape[0], 1), dtype=torch.float32, device=Z.device)
+        lam, rep = float(self.early_exaggeration_coeff_), float(self.repulsion_strength)
+        ops.sne_grad(Z, s, e - s, self.affinity_in_, self.NN_indices_, lam, rep, 0, self._grad, self._sne_rows)
+        if self.world_size > 1:
+            # the reference has every rank compute the whole N x N term and divide by W (sne.py:172-179);
+            # here each rank owns a row range and the per-row normalisers are all-gathered
+            all_gather_rows(self._sne_rows, self._bounds, self.rank)
+        ops.sne_grad(Z, s, e - s, self.affinity_in_, self.NN_indices_, lam, rep, 1, self._grad, self._sne_rows)
+
+    def clear_memory(self):
+        if hasattr(self, "_sne_rows"):
+            del self._sne_rows
         super().clear_memory()

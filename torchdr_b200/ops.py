@@ -306,6 +306,21 @@ def tsne_grad(Z, row0, n_local, Pm, idx, lam, phase, grad, ws):
                                             int(phase), ptr(grad), ptr(ws), ws.numel(), stream()), "tdr_tsne_grad_f32")
 
 
+def infotsne_grad(Z, row0, n_local, Pm, idx, grad, n_iter, neg=None, n_neg=300, seed=0, lam=1.0, repulsion=1.0):
+    with torch.cuda.device(Z.device):
+        check(_lib.load().tdr_infotsne_grad_f32(ptr(Z), Z.shape[0], row0, n_local, ptr(Pm), ptr(idx), Pm.shape[1],
+                                                ptr(neg), n_neg, seed, n_iter, float(lam), float(repulsion),
+                                                ptr(grad), stream()), "tdr_infotsne_grad_f32")
+
+
+def sne_grad(Z, row0, n_local, Pm, idx, lam, repulsion, phase, grad, row_sums):
+    k = Pm.shape[1] if Pm is not None else 0
+    with torch.cuda.device(Z.device):
+        check(_lib.load().tdr_sne_grad_f32(ptr(Z), Z.shape[0], row0, n_local, ptr(Pm), ptr(idx), k, float(lam),
+                                           float(repulsion), int(phase), ptr(grad), ptr(row_sums), stream()),
+              "tdr_sne_grad_f32")
+
+
 def sgd_momentum(Z, buf, grad, lr, momentum, first, gnorm_sq=None, nan_flag=None):
     with torch.cuda.device(Z.device):
         check(_lib.load().tdr_sgd_momentum_f32(ptr(Z), ptr(buf), ptr(grad), Z.numel(), float(lr), float(momentum),
