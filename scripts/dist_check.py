@@ -124,7 +124,7 @@ except Exception as exc:
 Xh = X.cpu().numpy()
 for cls, kw in ((tb.UMAP, dict(n_neighbors=15, max_iter=60)), (tb.LargeVis, dict(perplexity=10, max_iter=40)),
                 (tb.TSNE, dict(perplexity=10, max_iter=30)), (tb.InfoTSNE, dict(perplexity=10, max_iter=30, n_negatives=64)),
-                (tb.SNE, dict(perplexity=10, max_iter=30))):
+                (tb.SNE, dict(perplexity=10, max_iter=30, lr=30.0))):
     m = cls(init="normal", random_state=0, process_duplicates=False, **kw)
     Z = m.fit_transform(Xh)
     fin = bool(np.isfinite(Z).all()) and Z.shape == (n, 2)
@@ -137,7 +137,7 @@ for cls, kw in ((tb.UMAP, dict(n_neighbors=15, max_iter=60)), (tb.LargeVis, dict
 # row-sharded dense SNE / sampled InfoTSNE vs the same fit on one GPU (short run, injected init)
 g0 = torch.Generator().manual_seed(3)
 Zi = torch.randn(n, 2, generator=g0)
-for cls, kw in ((tb.SNE, dict(perplexity=10, max_iter=5)), (tb.InfoTSNE, dict(perplexity=10, max_iter=5, n_negatives=64))):
+for cls, kw in ((tb.SNE, dict(perplexity=10, max_iter=5, lr=30.0)), (tb.InfoTSNE, dict(perplexity=10, max_iter=5, n_negatives=64))):
     Zd = cls(init=Zi, random_state=0, process_duplicates=False, **kw).fit_transform(Xh)
     Zs = cls(init=Zi, random_state=0, process_duplicates=False, distributed=False, **kw).fit_transform(Xh)
     rel = float(np.linalg.norm(Zd - Zs) / np.linalg.norm(Zs))

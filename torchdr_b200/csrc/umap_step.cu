@@ -43,6 +43,7 @@ struct UmapStepParams {
 
 __device__ __forceinline__ void store_row(const UmapStepParams& p, int64_t gi, float2 zo) {
     p.Zout[gi] = zo;
+    if (p.n_peers == 0) return;  // uniform: single-GPU launches skip the peer loop
 #pragma unroll
     for (int q = 0; q < 8; ++q)
         if (q < p.n_peers) p.peer_out[q][gi] = zo;
@@ -315,6 +316,8 @@ __global__ void __launch_bounds__(kV2Threads, 4) umap_step_kernel_v2(const UmapS
 
 }  // namespace tdr
 #include "umap_step_fast.cuh"
+#include "umap_step_fast2.cuh"
+#include "umap_step_fast3.cuh"
 namespace tdr {
 
 // precise: 0 = throughput kernel (umap_step_fast.cuh), 1 = parity kernel (fp64 pow, one warp per row),
@@ -326,9 +329,25 @@ static int launch_step(const UmapStepParams& p, int precise, cudaStream_t st) {
         if (blocks > cap) blocks = cap;
         static const int occ = [] {
             const char* e = getenv("TDR_STEP_OCC");
-            return e ? atoi(e) : 5;  // measured at 1 M points: 4 -> 2196, 5 -> 2307, 6 -> 2178 it/s (48 regs, 70 B spill at 5)
+            return e ? atoi(e) : 4;  // fast3 at 1 M points: 3 -> 3269, 4 -> 3699, 5 -> 3506 it/s (64 regs, no spill at 4)
         }();
-        if (occ == 5) umap_step_kernel_fast<5><<<(unsigned)blocks, kFastThreads, 0, st>>>(p);
+        static const int variant = [] {
+            const char* e = getenv("TDR_STEP_FAST");
+            return e ? atoi(e) : 3;  // 3 = umap_step_fast3.cuh (pooled rows), 2 = umap_step_fast2.cuh, 1 = umap_step_fast.cuh
+        }();
+        if (variant == 3) {
+            int64_t b3 = (p.n_local + kWarps3 * kRows3 - 1) / (kWarps3 * kRows3);
+            if (b3 > cap) b3 = cap;
+            if (occ == 5) umap_step_kernel_fast3<5><<<(unsigned)b3, kFastThreads, 0, st>>>(p);
+            else if (occ == 6) umap_step_kernel_fast3<6><<<(unsigned)b3, kFastThreads, 0, st>>>(p);
+            else if (occ == 3) umap_step_kernel_fast3<3><<<(unsigned)b3, kFastThreads, 0, st>>>(p);
+            else umap_step_kernel_fast3<4><<<(unsigned)b3, kFastThreads, 0, st>>>(p);
+        } else if (variant == 2) {
+            if (occ == 5) umap_step_kernel_fast2<5><<<(unsigned)blocks, kFastThreads, 0, st>>>(p);
+            else if (occ == 6) umap_step_kernel_fast2<6><<<(unsigned)blocks, kFastThreads, 0, st>>>(p);
+            else if (occ == 8) umap_step_kernel_fast2<8><<<(unsigned)blocks, kFastThreads, 0, st>>>(p);
+            else umap_step_kernel_fast2<4><<<(unsigned)blocks, kFastThreads, 0, st>>>(p);
+        } else if (occ == 5) umap_step_kernel_fast<5><<<(unsigned)blocks, kFastThreads, 0, st>>>(p);
         else if (occ == 6) umap_step_kernel_fast<6><<<(unsigned)blocks, kFastThreads, 0, st>>>(p);
         else umap_step_kernel_fast<4><<<(unsigned)blocks, kFastThreads, 0, st>>>(p);
         TDR_LAUNCH_CHECK();

@@ -33,7 +33,9 @@ __device__ __forceinline__ float pow_fast(float x, float y) {
     const float m = __int_as_float(ix - (e << 23));
     const float ef = (float)e;
     const float hi = y * ef;
-    const float lo = fmaf(y, ef, -hi) + y * __log2f(m);
+    float lg;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(m));  // m is normal: no denormal pre-scaling needed
+    const float lo = fmaf(y, ef, -hi) + y * lg;
     float n = rintf(hi);
     const float f = (hi - n) + lo;
     float r;
