@@ -315,41 +315,55 @@ __global__ void __launch_bounds__(kV2Threads, 4) umap_step_kernel_v2(const UmapS
 }
 
 }  // namespace tdr
-#include "umap_step_fast.cuh"
-#include "umap_step_fast2.cuh"
+#include "umap_step_math.cuh"
 #include "umap_step_fast3.cuh"
+#include "umap_step_fast4.cuh"
 namespace tdr {
 
-// precise: 0 = throughput kernel (umap_step_fast.cuh), 1 = parity kernel (fp64 pow, one warp per row),
+template <int OCC, int CAP, bool NEG_CG>
+static cudaError_t launch_fast4(const UmapStepParams& p, unsigned blocks, cudaStream_t st) {
+    constexpr size_t smem = sizeof(Warp4Smem<CAP>) * kWarps4;
+    static const cudaError_t attr = cudaFuncSetAttribute(umap_step_kernel_fast4<OCC, CAP, NEG_CG>,
+                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (attr != cudaSuccess) return attr;
+    umap_step_kernel_fast4<OCC, CAP, NEG_CG><<<blocks, kFastThreads, smem, st>>>(p);
+    return cudaSuccess;
+}
+
+// precise: 0 = throughput kernel (umap_step_fast4.cuh), 1 = parity kernel (fp64 pow, one warp per row),
 //          2 = umap_step_kernel_v2 (libdevice powf; kept as the measured baseline of profiles/r1_step_kernel.md)
 static int launch_step(const UmapStepParams& p, int precise, cudaStream_t st) {
     if (precise == 0) {
-        int64_t blocks = (p.n_local + kFastGroups - 1) / kFastGroups;
         const int64_t cap = (int64_t)kNumSMs * 4 * 8;  // grid-stride beyond ~8 waves of resident CTAs
-        if (blocks > cap) blocks = cap;
-        static const int occ = [] {
-            const char* e = getenv("TDR_STEP_OCC");
-            return e ? atoi(e) : 4;  // fast3 at 1 M points: 3 -> 3269, 4 -> 3699, 5 -> 3506 it/s (64 regs, no spill at 4)
-        }();
         static const int variant = [] {
             const char* e = getenv("TDR_STEP_FAST");
-            return e ? atoi(e) : 3;  // 3 = umap_step_fast3.cuh (pooled rows), 2 = umap_step_fast2.cuh, 1 = umap_step_fast.cuh
+            return e ? atoi(e) : 4;  // 4 = umap_step_fast4.cuh (lane per row), 3 = umap_step_fast3.cuh (8 rows per warp)
+        }();
+        static const int cfg = [] {
+            const char* e = getenv("TDR_STEP_CFG");
+            return e ? atoi(e) : 0;
         }();
         if (variant == 3) {
             int64_t b3 = (p.n_local + kWarps3 * kRows3 - 1) / (kWarps3 * kRows3);
             if (b3 > cap) b3 = cap;
-            if (occ == 5) umap_step_kernel_fast3<5><<<(unsigned)b3, kFastThreads, 0, st>>>(p);
-            else if (occ == 6) umap_step_kernel_fast3<6><<<(unsigned)b3, kFastThreads, 0, st>>>(p);
-            else if (occ == 3) umap_step_kernel_fast3<3><<<(unsigned)b3, kFastThreads, 0, st>>>(p);
-            else umap_step_kernel_fast3<4><<<(unsigned)b3, kFastThreads, 0, st>>>(p);
-        } else if (variant == 2) {
-            if (occ == 5) umap_step_kernel_fast2<5><<<(unsigned)blocks, kFastThreads, 0, st>>>(p);
-            else if (occ == 6) umap_step_kernel_fast2<6><<<(unsigned)blocks, kFastThreads, 0, st>>>(p);
-            else if (occ == 8) umap_step_kernel_fast2<8><<<(unsigned)blocks, kFastThreads, 0, st>>>(p);
-            else umap_step_kernel_fast2<4><<<(unsigned)blocks, kFastThreads, 0, st>>>(p);
-        } else if (occ == 5) umap_step_kernel_fast<5><<<(unsigned)blocks, kFastThreads, 0, st>>>(p);
-        else if (occ == 6) umap_step_kernel_fast<6><<<(unsigned)blocks, kFastThreads, 0, st>>>(p);
-        else umap_step_kernel_fast<4><<<(unsigned)blocks, kFastThreads, 0, st>>>(p);
+            umap_step_kernel_fast3<4><<<(unsigned)b3, kFastThreads, 0, st>>>(p);
+            TDR_LAUNCH_CHECK();
+            return TDR_OK;
+        }
+        int64_t b4 = (p.n_local + kWarps4 * 32 - 1) / (kWarps4 * 32);
+        if (b4 > cap) b4 = cap;
+        const unsigned g4 = (unsigned)b4;
+        cudaError_t err;
+        // (CTAs per SM, list entries per warp, negatives through L2 only); ms per iteration at 1 M x 128, k = 15:
+        //   (4, 256, cg) 0.225   (5, 256, cg) 0.225   (3, 384, cg) 0.237   (3, 384, ldg) 0.242   (4, 384, ldg) 0.361
+        switch (cfg) {
+            case 1: err = launch_fast4<3, 384, true>(p, g4, st); break;
+            case 2: err = launch_fast4<4, 320, true>(p, g4, st); break;
+            case 3: err = launch_fast4<4, 256, false>(p, g4, st); break;
+            case 4: err = launch_fast4<4, 288, true>(p, g4, st); break;
+            default: err = launch_fast4<4, 256, true>(p, g4, st); break;
+        }
+        TDR_CUDA(err);
         TDR_LAUNCH_CHECK();
         return TDR_OK;
     }

@@ -1,12 +1,10 @@
-// Third throughput variant of the UMAP step (included by umap_step.cu after umap_step_fast2.cuh).
+// Pooled-row throughput variant of the UMAP step, 8 rows per warp iteration (included by umap_step.cu;
+// selected with TDR_STEP_FAST=3, kept as the measured predecessor of umap_step_fast4.cuh).
 //
-// ncu on umap_step_kernel_fast2 (profiles/r1_step_kernel.md): 286 M warp instructions per iteration at
-// 27 of 32 lanes active, i.e. ~1150 instructions per 4 rows although the useful work of 4 rows (100 edges
-// scanned, 29 attractions, 143 repulsions) is ~350.  The waste is structural: 8 lanes per row means every
-// loop runs for the LARGEST of the warp's rows (degree 25 +- 12 -> two 32-slot chunk sets half of the
-// time, 7 +- 2.3 due edges -> two 8-lane passes, 37 +- 6 negative quads -> two 32-lane passes), and the
-// per-row register accumulators cost 16 select+add per pass plus transposed reductions.
-//
+// The first throughput kernels gave 8 lanes to a row, so every loop ran for the LARGEST of the warp's rows
+// (degree 25 +- 12, 7 +- 2.3 due edges, 37 +- 6 negative quads per 4 rows) and the per-row register
+// accumulators cost 16 select+add per pass plus transposed reductions: 286 M warp instructions per
+// iteration at 1 M points although the useful work is about a third of that.
 // This version treats the warp's rows as ONE pool in every phase (8 consecutive rows per warp iteration):
 //   scan   the rows' CSR segments are contiguous: lanes take consecutive edges of the pooled range
 //          (row id = number of row offsets <= edge offset), due edges are appended in edge order to a
@@ -16,9 +14,8 @@
 //   repulse quads (row, 4 negative slots = one Philox block) are dealt the same way, results to the list;
 //   sums   the 4 owner lanes of a row add the row's entries (stride 4) and finish with two butterflies.
 // The order of a row's sum depends only on the row's own counts, so results do not depend on how rows
-// are grouped into warps or sharded over GPUs (bit-identical single- vs multi-GPU), except when the pool
-// overflows the list (kCap entries) and is flushed in several rounds (hub rows).
-// Arithmetic per edge / negative is exactly that of umap_step_kernel_fast2.
+// are grouped into warps or sharded over GPUs, except when the pool overflows the list (kCap3 entries)
+// and is flushed in several rounds (hub rows).  237 M warp instructions, 0.270 ms per iteration.
 #pragma once
 
 namespace tdr {
