@@ -342,12 +342,12 @@ def gpu_arm(args):
             pass
     if traffic is not None and world > 1:
         traffic = None  # the ncu capture is of the N = 1 launch
-    roofline = {"bound": "hbm", "kernel": "tdr::umap_step_kernel_fast", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "tdr::umap_step_kernel_fast4", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes / world,
                 "note": ("per GPU; achieved = algorithmic bytes (DESIGN.md 3.5, counts taken in-kernel) / mean launch "
-                         "time over the timed region; ncu shows the kernel is instruction-issue bound (profiles/"
-                         "r1_step_kernel.md); at N>1 the per-step time also contains the cross-GPU barrier")}
+                         "time over the timed region; ncu shows the kernel is bound by instruction issue and the L2 "
+                         "sector rate of the random z_j gathers, not by DRAM (profiles/r1_step_kernel.md); at N>1 the per-step time also contains the cross-GPU barrier")}
     aff_bytes = 4.0 * n * d / 1 + n / world * K_NEIGHBORS * 8.0 + 8.0 * n / world
     tc_peak = None
     try:
