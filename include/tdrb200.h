@@ -70,6 +70,14 @@ TDR_API int tdr_knn_f32(const float* Xq, int64_t nq, int64_t q_row0,
  * for tests and profiling.  The environment variable TDR_KNN_PATH seeds it at load time. */
 TDR_API int tdr_knn_set_path(int path);
 
+/* Tile-pruned sweep of the tensor-core kNN (queries that are rows of the database, >= 64 database tiles):
+ * database tiles whose bounding box is farther from the query tile's box than a bound on the tile's k-th
+ * neighbour distances are not swept.  Results are bit-identical to the full sweep.  on = 1 (default; the
+ * environment variable TDR_KNN_PRUNE seeds it) / 0.  sweep_stats: optional device pointer to two uint64
+ * counters, [0] += tiles swept, [1] += tiles a full sweep would visit (per kNN call, summed over query tiles);
+ * null disables the counters.  Process-wide. */
+TDR_API int tdr_knn_set_prune(int on, uint64_t* sweep_stats);
+
 /* Full matrix C[n,m] (k=None path, distance/torch.py:81-116).  Y may equal X.
  * Workspace: tdr_knn_workspace_bytes(n, m, d, 1). */
 TDR_API int tdr_pairwise_full_f32(const float* X, int64_t n, const float* Y, int64_t m, int d,

@@ -41,8 +41,17 @@ def plan(X, k, W=8, margin_rel=1e-3, margin_abs_norm=1e-4):
     Tpad = T * (1 + margin_rel) + margin_abs_norm * 2 * norms.max()
     cd = np.sqrt(np.maximum(((cen ** 2).sum(1)[:, None] + (cen ** 2).sum(1)[None, :] - 2 * cen @ cen.T), 0)) * (1 - 1e-4)
     lb = cd - rad[:, None] - rad[None, :]
-    survive = (lb <= 0) | (lb * lb <= Tpad[:, None])
-    return survive, T
+    survive_ball = (lb <= 0) | (lb * lb <= Tpad[:, None])
+    # axis-aligned boxes: sum_d max(0, lo_B - hi_A, lo_A - hi_B)^2
+    lo = np.stack([X[t * BM:(t + 1) * BM].min(0) for t in range(nt)])
+    hi = np.stack([X[t * BM:(t + 1) * BM].max(0) for t in range(nt)])
+    survive_box = np.zeros((nt, nt), bool)
+    for a in range(nt):
+        gap = np.maximum(0, np.maximum(lo - hi[a][None, :], lo[a][None, :] - hi))
+        survive_box[a] = (gap * gap).sum(1) * (1 - 1e-4) <= Tpad[a]
+    print(f"  ball: {survive_ball.sum(1).mean():.1f} tiles/query tile, box: {survive_box.sum(1).mean():.1f}, both: "
+          f"{(survive_ball & survive_box).sum(1).mean():.1f} (max {(survive_ball & survive_box).sum(1).max()})")
+    return survive_ball & survive_box, T
 
 
 def main():
@@ -54,6 +63,11 @@ def main():
         X = torch.randn(n, d, generator=torch.Generator().manual_seed(0)).numpy()
     else:
         X = clustered(n, d, "cpu").numpy()
+        if kind.startswith("big"):  # cluster size of the 1 M benchmark (1000 points) at a smaller n
+            g = torch.Generator().manual_seed(42)
+            nc = n // 1000
+            centers = torch.randn(nc, d, generator=g) * 10
+            X = (centers.repeat_interleave(1000, 0) + torch.randn(n, d, generator=g) * 0.5).numpy()
         if kind == "shuffled":
             X = X[np.random.default_rng(0).permutation(n)]
     survive, T = plan(X, k)

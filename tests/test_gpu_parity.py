@@ -93,6 +93,48 @@ def test_knn_cross_and_chunk(ops):
     assert torch.equal(Ic, If[200:455]) and torch.equal(Cc, Cf[200:455])
 
 
+@pytest.mark.parametrize("kind,n,d,k", [("clustered", 60_000, 128, 15), ("clustered", 20_000, 50, 90),
+                                        ("uniform", 12_000, 64, 15), ("shuffled", 16_000, 128, 15)])
+def test_knn_pruned_sweep_is_bit_identical(ops, kind, n, d, k):
+    """The tile-pruned sweep (csrc/knn_tc.cu) must return exactly what the full sweep returns — distances,
+    indices, and the fused sigma/rho rows — on data where it prunes (index-local clusters), where it cannot
+    (uniform, shuffled) and for a row chunk at an offset that is not a multiple of the tile size."""
+    if kind == "uniform":
+        X = torch.randn(n, d, generator=torch.Generator().manual_seed(3))
+    else:
+        X = clustered(n, d)
+        if kind == "shuffled":
+            X = X[torch.randperm(n, generator=torch.Generator().manual_seed(4))].contiguous()
+    Xd = _cuda(X)
+    stats = torch.zeros(2, dtype=torch.int64, device=DEV)
+    try:
+        ops.knn_set_prune(False)
+        C0, I0 = ops.knn(Xd, Xd, k)
+        Cc0, Ic0 = ops.knn(Xd[1000:5301], Xd, k, q_row0=1000)
+        F0 = ops.knn_umap_fused(Xd, Xd, min(k, 32)) if d <= 128 else None
+        E0, J0 = ops.knn(Xd, Xd, k, metric="euclidean")
+        ops.knn_set_prune(True, stats)
+        C1, I1 = ops.knn(Xd, Xd, k)
+        swept, full = (int(v) for v in stats.tolist())
+        Cc1, Ic1 = ops.knn(Xd[1000:5301], Xd, k, q_row0=1000)
+        F1 = ops.knn_umap_fused(Xd, Xd, min(k, 32)) if d <= 128 else None
+        E1, J1 = ops.knn(Xd, Xd, k, metric="euclidean")
+    finally:
+        ops.knn_set_prune(True, None)
+    assert torch.equal(I0, I1) and torch.equal(C0, C1)
+    assert torch.equal(Ic0, Ic1) and torch.equal(Cc0, Cc1)
+    assert torch.equal(J0, J1) and torch.equal(E0, E1)
+    if F0 is not None:
+        for a, b in zip(F0, F1):
+            assert torch.equal(a, b)
+    assert torch.equal(Ic1, I1[1000:5301])
+    n_tiles = (n + 127) // 128
+    assert full == n_tiles * n_tiles and 0 < swept <= full
+    print(f"{kind} {n}x{d} k={k}: swept {swept} of {full} tile pairs ({100.0 * swept / full:.2f} %)")
+    if kind == "clustered":
+        assert swept < 0.25 * full
+
+
 def test_pairwise_full(ops):
     g = golden("pairwise_full_n64")
     X, Y = t(g["X"]), t(g["Y"])

@@ -37,6 +37,7 @@ SIGNATURES = {
     "tdr_entropic_dense_f32": (c_int, [P, c_int64, c_int64, c_float, c_float, c_int, c_float, c_float, c_float,
                                        c_float, c_int, P, P, P, P]),
     "tdr_knn_set_path": (c_int, [c_int]),
+    "tdr_knn_set_prune": (c_int, [c_int, P]),
     "tdr_knn_umap_fused_f32": (c_int, [P, c_int64, c_int64, P, c_int64, c_int, c_int, c_int, c_int, P, P, P, P, P,
                                        P, c_size_t, P]),
     "tdr_symmetrize_workspace_bytes": (c_size_t, [c_int64, c_int, c_int64]),

@@ -30,10 +30,11 @@ enum { MODE_KNN = 0, MODE_FUSED = 1, MODE_FULL = 2 };
 
 // knn_tc.cu
 bool knn_tc_supported(int d, int k);
-size_t knn_tc_workspace_bytes(int64_t nq, int64_t ndb, int d, bool same);
+size_t knn_tc_workspace_bytes(int64_t nq, int64_t ndb, int d, int k, bool same);
 int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb, int64_t ndb, int d, int k,
                   bool same, int exclude_self, int metric, int fused, int max_iter, float* out_dist, int32_t* out_idx,
                   float* P, float* rho, float* sigma, void* ws, size_t ws_bytes, cudaStream_t st);
+void knn_tc_set_prune(int on, unsigned long long* stats);
 // 0 = auto, 1 = SIMT fp32 kernel, 2 = tcgen05 kernel (tests / profiling); env TDR_KNN_PATH seeds it
 static int g_knn_path = [] {
     const char* e = getenv("TDR_KNN_PATH");
@@ -519,13 +520,19 @@ using namespace tdr;
 extern "C" TDR_API size_t tdr_knn_workspace_bytes(int64_t nq, int64_t ndb, int d, int k) {
     // conservative: assume distinct query / database buffers; covers both kernel paths
     size_t b = prepare_bytes(nq, ndb, d, false) + 256;
-    if (knn_tc_supported(d, k)) b = std::max(b, knn_tc_workspace_bytes(nq, ndb, d, false) + 256);
+    if (knn_tc_supported(d, k)) b = std::max(b, knn_tc_workspace_bytes(nq, ndb, d, k, false) + 256);
     return b;
 }
 
 extern "C" TDR_API int tdr_knn_set_path(int path) {
     TDR_CHECK_ARG(path >= 0 && path <= 2, "tdr_knn_set_path: 0 = auto, 1 = SIMT fp32, 2 = tcgen05");
     g_knn_path = path;
+    return TDR_OK;
+}
+
+extern "C" TDR_API int tdr_knn_set_prune(int on, uint64_t* sweep_stats) {
+    TDR_CHECK_ARG(on == 0 || on == 1, "tdr_knn_set_prune: on must be 0 or 1");
+    knn_tc_set_prune(on, reinterpret_cast<unsigned long long*>(sweep_stats));
     return TDR_OK;
 }
 

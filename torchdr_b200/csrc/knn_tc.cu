@@ -196,6 +196,27 @@ __device__ __noinline__ float list_insert(uint32_t my_d, uint32_t my_i, int k, f
     return lds_f32(my_d + 4u * (uint32_t)(k - 1));
 }
 
+// Unsorted variant for short lists (k <= 32).  While the list is not full a candidate is appended (two stores);
+// once it is full the candidate overwrites the current worst entry (position amax) and one pass over the list
+// finds the new worst by (distance, index).  The loads of that pass are independent, whereas the sorted insert
+// above walks a chain of dependent shared-memory round trips (~750 cycles per call at k = 15): in the pruned
+// sweep, where every tile is a near one, the inserts are what the epilogue spends its time on.
+// Returns (worst distance bits | its position << 32).  The list is rank-sorted once after the sweep.
+__device__ __noinline__ unsigned long long list_scan_max(uint32_t my_d, uint32_t my_i, int k) {
+    float m = -INFINITY;
+    int mi = -1, mp = 0;
+#pragma unroll 4
+    for (int p = 0; p < k; ++p) {
+        const float v = lds_f32(my_d + 4u * (uint32_t)p);
+        const int i = lds_s32(my_i + 4u * (uint32_t)p);
+        const bool gt = v > m || (v == m && i > mi);
+        m = gt ? v : m;
+        mi = gt ? i : mi;
+        mp = gt ? p : mp;
+    }
+    return (unsigned long long)__float_as_uint(m) | ((unsigned long long)(uint32_t)mp << 32);
+}
+
 // ------------------------------------------------------------------ main kernel
 struct Params {
     int64_t nq, ndb, q_row0;  // q_row0: global id of query row 0 (self exclusion)
@@ -205,8 +226,17 @@ struct Params {
     const int* absmax_bits;
     int k, kpad, atoms, stages;
     int exclude_self, metric, fused, max_iter;
+    int unsorted;  // 1: lists are kept unsorted during the sweep (list_replace; k <= 32) and rank-sorted at the end
     int dual;   // 1: two epilogue warpgroups (384 threads), each with its own top-k lists, on alternate tiles
     int debug;  // timing experiments only (env TDR_TC_DEBUG): 1 = skip filter, 2 = skip MMAs, 4 = skip database TMA
+    // tile-pruned sweep (see the "pruned sweep" section below): which database tiles this CTA visits
+    int win;                 // > 0: only the tiles within +-win of the CTA's own rows (phase A)
+    const int* tile_list;    // [gridDim.x][list_cap] ascending tile ids (phase B), or null = all tiles
+    const int* tile_count;   // [gridDim.x]; a count above list_cap means "list overflowed: sweep everything"
+    int list_cap;
+    float* kth_out;          // phase A: only a bound on the k-th distance of every row is written (squared domain)
+    const float* tau_seed;   // phase B: that bound; the row's threshold starts there instead of at +inf
+    unsigned long long* sweep_stats;  // optional: [0] += tiles swept, [1] += tiles of a full sweep
     float* out_dist;
     int32_t* out_idx;
     float* P;
@@ -236,6 +266,26 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
     const int64_t n_tiles = (prm.ndb + BN - 1) / BN;
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    // The sweep of this CTA: n_sweep database tiles, the t-th of which is tile_of(t) (ascending, so equal
+    // distances still arrive in index order).  Every role derives it from the same kernel arguments.
+    int64_t t_first = 0, n_sweep = n_tiles;
+    const int* my_list = nullptr;
+    if (prm.win > 0) {
+        const int64_t r0 = prm.q_tile_row0 + q0;
+        t_first = max((int64_t)0, r0 / BN - prm.win);
+        n_sweep = min(n_tiles, (r0 + BM - 1) / BN + prm.win + 1) - t_first;
+    } else if (prm.tile_count) {
+        const int c = __ldg(prm.tile_count + blockIdx.x);
+        if (c <= prm.list_cap) {
+            my_list = prm.tile_list + (int64_t)blockIdx.x * prm.list_cap;
+            n_sweep = c;
+        }
+    }
+    auto tile_of = [&](int64_t t) -> int64_t { return my_list ? (int64_t)__ldg(my_list + t) : t_first + t; };
+    if (prm.sweep_stats && tid == 0 && prm.win == 0) {
+        atomicAdd(prm.sweep_stats + 0, (unsigned long long)n_sweep);
+        atomicAdd(prm.sweep_stats + 1, (unsigned long long)n_tiles);
+    }
     const int B_FULL = 1, B_EMPTY = 1 + stages, T_FULL = 1 + 2 * stages, T_EMPTY = 3 + 2 * stages;
 
     if (warp == 1 && lane == 0) {
@@ -274,9 +324,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                 tma_load_2d(smem_u32(a_tiles + (a * 2 + 1) * TILE_BYTES), &map_q_lo, BAR(0), a * KATOM,
                             (int)(prm.q_tile_row0 + q0));
             }
-            for (int64_t t = 0; t < n_tiles; ++t) {
+            for (int64_t t = 0; t < n_sweep; ++t) {
                 const int s = (int)(t % stages);
                 const uint32_t ph = (uint32_t)((t / stages) & 1);
+                const int row_db = (int)(tile_of(t) * BN);
                 mbar_wait(BAR(B_EMPTY + s), ph ^ 1u);
                 if ((prm.debug & 4) && t >= stages) {
                     mbar_arrive(BAR(B_FULL + s));
@@ -285,8 +336,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                 mbar_expect_tx(BAR(B_FULL + s), (uint32_t)a_bytes);
                 unsigned char* dst = b_tiles + (size_t)s * a_bytes;
                 for (int a = 0; a < atoms; ++a) {
-                    tma_load_2d(smem_u32(dst + (a * 2 + 0) * TILE_BYTES), &map_db_hi, BAR(B_FULL + s), a * KATOM, (int)(t * BN));
-                    tma_load_2d(smem_u32(dst + (a * 2 + 1) * TILE_BYTES), &map_db_lo, BAR(B_FULL + s), a * KATOM, (int)(t * BN));
+                    tma_load_2d(smem_u32(dst + (a * 2 + 0) * TILE_BYTES), &map_db_hi, BAR(B_FULL + s), a * KATOM, row_db);
+                    tma_load_2d(smem_u32(dst + (a * 2 + 1) * TILE_BYTES), &map_db_lo, BAR(B_FULL + s), a * KATOM, row_db);
                 }
             }
         }
@@ -294,7 +345,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
             mbar_wait(BAR(0), 0);
-            for (int64_t t = 0; t < n_tiles; ++t) {
+            for (int64_t t = 0; t < n_sweep; ++t) {
                 const int s = (int)(t % stages);
                 const uint32_t ph = (uint32_t)((t / stages) & 1);
                 const int as = (int)(t & 1);
@@ -343,7 +394,17 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
         const int e = scale_exponent(__int_as_float(__ldg(prm.absmax_bits)));
         const float neg2s = -2.0f * ldexpf(1.0f, -2 * e);  // power of two: the FFMA below rounds once, like sub(add, 2*dot)
         const uint32_t my_d = smem_u32(ld_s + (wg * BM + row) * kpad), my_i = smem_u32(li_s + (wg * BM + row) * kpad);
+        // Threshold of the row.  Phase B of the pruned sweep starts it one ulp above the bound of phase A (so the
+        // strict test below admits every candidate <= bound); the lists start empty either way, and since at least
+        // k candidates of the swept tiles lie within the bound the union of the row's lists fills up.
         float tau = INFINITY;
+        if (prm.tau_seed && gq < prm.nq) {
+            const float sd = __ldg(prm.tau_seed + gq);
+            if (sd < INFINITY)
+                tau = sd >= 0.0f ? __uint_as_float(__float_as_uint(sd + 0.0f) + 1u) : __uint_as_float(__float_as_uint(sd) - 1u);
+        }
+        int amax = 0, cnt = 0;  // unsorted mode: position of the list's worst entry, filled slots
+        const bool unsorted = prm.unsorted != 0;
         const uint32_t lane_addr = (uint32_t)(((warp - 4) & 3) * 32) << 16;
 
         auto filter = [&](uint32_t(&big)[32], uint32_t(&small)[32], int col_base) {
@@ -369,23 +430,82 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float dist = __uint_as_float(big[j]);
-                    if (dist < tau && (int64_t)(col_base + j) != self) tau = list_insert(my_d, my_i, k, dist, col_base + j);
+                    if (dist < tau && (int64_t)(col_base + j) != self) {
+                        if (unsorted) {
+                            const int slot = cnt < k ? cnt : amax;
+                            sts_f32(my_d + 4u * (uint32_t)slot, dist);
+                            sts_s32(my_i + 4u * (uint32_t)slot, col_base + j);
+                            if (++cnt >= k) {
+                                const unsigned long long r = list_scan_max(my_d, my_i, k);
+                                tau = fminf(tau, __uint_as_float((uint32_t)r));
+                                amax = (int)(r >> 32);
+                            }
+                        } else {
+                            tau = fminf(tau, list_insert(my_d, my_i, k, dist, col_base + j));
+                        }
+                    }
                 }
             }
         };
 
+        const int c_beg = prm.dual ? 64 * wg : 0;   // first column of this warpgroup's share
+        const int n_ch = prm.dual ? 2 : 4;          // 32-column chunks in the share
+        if (prm.kth_out && unsorted) {
+            // ---- phase A of the pruned sweep, k <= 32: no lists.  gm[j] = smallest distance among the columns this
+            // thread sees at chunk position j; the row's 32 (x 2 warpgroups) minima belong to disjoint column sets,
+            // so their k-th smallest bounds the k-th neighbour distance (k columns at most that far) — and it is
+            // nearly tight: with 18+ columns per group the k-th of 64 group minima sits at about the same quantile
+            // as the exact k-th of the window.
+            float gm[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) gm[j] = INFINITY;
+            for (int64_t t = 0; t < n_sweep; ++t) {
+                const int as = (int)(t & 1);
+                const uint32_t aph = (uint32_t)((t >> 1) & 1);
+                mbar_wait(BAR(T_FULL + as), aph);
+                tc_fence_after();
+                const int col0 = (int)(tile_of(t) * BN) + c_beg;
+                const uint32_t tb = tmem_base + lane_addr + (uint32_t)(as * 256 + c_beg);
+#pragma unroll 1
+                for (int c = 0; c < n_ch; ++c) {
+                    uint32_t big[32], small[32];
+                    tc_ld32(tb + 32 * c, big);
+                    tc_ld32(tb + 128 + 32 * c, small);
+                    tc_ld_wait(big, small);
+                    const int col_base = col0 + 32 * c;
+#pragma unroll
+                    for (int j4 = 0; j4 < 32; j4 += 4) {
+                        const float4 nb = __ldg(reinterpret_cast<const float4*>(prm.dbn + col_base + j4));
+                        const float nbv[4] = {nb.x, nb.y, nb.z, nb.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = j4 + u;
+                            float dd = fmaf(__fadd_rn(__uint_as_float(big[j]), __uint_as_float(small[j])), neg2s,
+                                            __fadd_rn(qn, nbv[u]));
+                            if ((int64_t)(col_base + j) == self) dd = INFINITY;
+                            gm[j] = fminf(gm[j], dd);
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(BAR(T_EMPTY + as));
+            }
+            // the last tile's MMAs have retired (T_FULL), so the TMA ring is free: park the minima there,
+            // [j][warpgroup * 128 + row] (conflict-free), for the write-back warps
+            float* scratch = reinterpret_cast<float*>(b_tiles);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) scratch[j * (nl * BM) + wg * BM + row] = gm[j];
+        } else {
         // Dual mode: BOTH warpgroups work on every tile, each on half of its columns.  With only two accumulator
         // stages in TMEM the MMAs of tile t+2 wait for the epilogue of tile t, so what matters is the epilogue
         // LATENCY per tile (measured: alternate-tile assignment gave (T_mma + 2 T_epi)/2 per tile).
-        const int c_beg = prm.dual ? 64 * wg : 0;   // first column of this warpgroup's share
-        const int n_ch = prm.dual ? 2 : 4;          // 32-column chunks in the share
-        for (int64_t t = 0; t < n_tiles; ++t) {
+        for (int64_t t = 0; t < n_sweep; ++t) {
             const int as = (int)(t & 1);
             const uint32_t aph = (uint32_t)((t >> 1) & 1);
             // database norms of the NEXT tile: pull this warpgroup's lines into L1 now, so that the filter's
             // broadcast loads do not each pay an L2 round trip
-            if (lane < n_ch && t + 1 < n_tiles && !(prm.debug & 16))
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(prm.dbn + (t + 1) * BN + c_beg + lane * 32));
+            if (lane < n_ch && t + 1 < n_sweep && !(prm.debug & 16))
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(prm.dbn + tile_of(t + 1) * BN + c_beg + lane * 32));
             mbar_wait(BAR(T_FULL + as), aph);
             tc_fence_after();
             if (prm.debug & 1) {
@@ -393,7 +513,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                 mbar_arrive(BAR(T_EMPTY + as));
                 continue;
             }
-            const int col0 = (int)(t * BN) + c_beg;
+            const int col0 = (int)(tile_of(t) * BN) + c_beg;
             const uint32_t tb = tmem_base + lane_addr + (uint32_t)(as * 256 + c_beg);
             uint32_t bigA[32], smallA[32], bigB[32], smallB[32];
             tc_ld32(tb + 0, bigA);
@@ -415,6 +535,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
             tc_fence_before();
             mbar_arrive(BAR(T_EMPTY + as));
         }
+        }  // lists
     }
 
     tc_fence_before();
@@ -431,7 +552,55 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
         if (gr >= prm.nq) continue;
         float* ldr = ld_s + row * kpad;
         int* lir = li_s + row * kpad;
-        if (nl == 2) {
+        if (prm.kth_out && prm.unsorted) {
+            // phase A, k <= 32: k-th smallest of the row's nl * 32 group minima (ranked by (value, group id))
+            const float* scratch = reinterpret_cast<const float*>(b_tiles);
+            float v[2];
+            int rk[2] = {0, 0};
+#pragma unroll
+            for (int e = 0; e < 2; ++e) v[e] = e < nl ? scratch[lane * (nl * BM) + e * BM + row] : INFINITY;
+            for (int q = 0; q < nl * 32; ++q) {
+                const int qe = q >> 5, qj = q & 31;
+                const float x = scratch[qj * (nl * BM) + qe * BM + row];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) rk[e] += (x < v[e] || (x == v[e] && q < e * 32 + lane)) ? 1 : 0;
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+                if (e < nl && rk[e] == k - 1) prm.kth_out[gr] = v[e];
+            continue;
+        }
+        if (prm.unsorted) {
+            // rank-sort the union of the row's (unsorted) lists by (distance, index) into list 0; k <= 32, so the
+            // union has at most 64 entries = 2 per lane.  Unused slots are (+inf, INT_MAX) and rank last.
+            const int total = nl * k;
+            float dv[2];
+            int iv[2], rk[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int q = lane + 32 * e;  // entry q: list q / k, slot q % k
+                const bool ok = q < total;
+                const int li = ok ? q / k : 0, sl = ok ? q - li * k : 0;
+                dv[e] = ok ? ld_s[(li * BM + row) * kpad + sl] : INFINITY;
+                iv[e] = ok ? li_s[(li * BM + row) * kpad + sl] : 0x7fffffff;
+                rk[e] = 0;
+            }
+            for (int q = 0; q < total; ++q) {
+                const int li = q / k, sl = q - li * k;
+                const float x = ld_s[(li * BM + row) * kpad + sl];
+                const int y = li_s[(li * BM + row) * kpad + sl];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) rk[e] += (x < dv[e] || (x == dv[e] && y < iv[e])) ? 1 : 0;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+                if (lane + 32 * e < total && rk[e] < k) {
+                    ldr[rk[e]] = dv[e];
+                    lir[rk[e]] = iv[e];
+                }
+            __syncwarp();
+        } else if (nl == 2) {
             // merge the two sorted lists of the row (disjoint index sets) by (distance, index) into list 0
             const float* ldb = ld_s + (BM + row) * kpad;
             const int* lib = li_s + (BM + row) * kpad;
@@ -470,6 +639,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
             }
             __syncwarp();
         }
+        if (prm.kth_out) {  // phase A of the pruned sweep: the row's bound, nothing else
+            if (lane == 0) prm.kth_out[gr] = ldr[k - 1];
+            continue;
+        }
         for (int p = lane; p < k; p += 32) {
             // lists are kept in the squared domain; euclidean = sqrt(clamp(., 0)) (torch.py:92-95) is monotone
             float dv = ldr[p];
@@ -503,6 +676,111 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
             }
         }
     }
+}
+
+// ------------------------------------------------------------------ pruned sweep
+// Exact kNN without sweeping database tiles that cannot hold a neighbour.  Every 128-row tile gets an
+// axis-aligned bounding box; phase A runs the kernel above over the +-kWindow tiles around each query tile,
+// which gives every row an upper bound tau_i on its k-th neighbour distance; tile_prune_kernel keeps, per
+// query tile A, the database tiles B with
+//        sum_d max(0, lo_B[d] - hi_A[d], lo_A[d] - hi_B[d])^2  <=  max_{i in A} tau_i  (+ margin),
+// i.e. drops B only if every point of B is farther from every point of A than a bound on all k-th neighbour
+// distances of A; phase B runs the kernel over the surviving tiles (ascending order).  A dropped tile cannot
+// change any list, so the result is bit-identical to the full sweep: each (row, column) distance is computed by
+// the same instructions on the same operands, and the margin covers the fp32 error of those distances
+// (documented gap 4e-6 (|x|^2 + |y|^2)).  Boxes, not balls: a tile that straddles two clusters has a
+// huge ball but a box that is still thin in most dimensions (scripts/prune_sim.py: 9 of 782 tiles survive per
+// query tile at 100 k x 128 with 100-point clusters; balls keep 780).  Data without index locality keeps
+// every tile and costs phase A + the box test extra (measured in profiles/).
+constexpr int kWindow = 4;       // phase A: own tile +- 4 (>= 5 full tiles = 640 rows >= k + 1)
+constexpr int kPruneMinTiles = 64;
+constexpr int kListCap = 1024;   // surviving tiles kept per query tile; beyond that the CTA sweeps everything
+
+// lo/hi over rows [row0 + 128 b, row0 + 128 b + 128) /\ [0, row_limit).  ld_t > 0: transposed output [d][ld_t]
+// (tiles b >= the last real one are written as empty boxes), ld_t == 0: row-major [n_tiles][d].
+__global__ void __launch_bounds__(128) tile_box_kernel(const float* __restrict__ X, int64_t row0, int64_t row_limit,
+                                                       int d, float* __restrict__ lo, float* __restrict__ hi,
+                                                       int64_t ld_t) {
+    const int64_t b = blockIdx.x;
+    const int j = threadIdx.x;
+    if (j >= d) return;
+    const int64_t r_beg = row0 + b * BM;
+    const int64_t r_end = min(r_beg + BM, row_limit);
+    float mn = INFINITY, mx = -INFINITY;
+    for (int64_t r = r_beg; r < r_end; ++r) {
+        const float v = __ldg(X + r * d + j);
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+    }
+    if (ld_t) {
+        lo[(int64_t)j * ld_t + b] = mn;
+        hi[(int64_t)j * ld_t + b] = mx;
+    } else {
+        lo[b * d + j] = mn;
+        hi[b * d + j] = mx;
+    }
+}
+
+__global__ void __launch_bounds__(256) maxnorm_kernel(const float* __restrict__ nrm, int64_t n, int* __restrict__ out_bits) {
+    float m = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, nrm[i]);
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_int(m));
+}
+
+// one warp per query tile, lanes = 32 consecutive database tiles; 16 dimensions at a time with a warp-uniform
+// early exit (a far tile is settled by its first few dimensions)
+__global__ void __launch_bounds__(256)
+tile_prune_kernel(const float* __restrict__ qlo, const float* __restrict__ qhi, const float* __restrict__ dlo_t,
+                  const float* __restrict__ dhi_t, int64_t n_qtiles, int64_t n_tiles, int64_t ld_t, int d,
+                  const float* __restrict__ tau, int64_t nq, const int* __restrict__ maxnorm_bits,
+                  int* __restrict__ list, int* __restrict__ count, int cap) {
+    __shared__ float s_box[8][2][MAX_ATOMS * KATOM];
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t qt = (int64_t)blockIdx.x * 8 + warp;
+    if (qt >= n_qtiles) return;  // whole warp
+    for (int j = lane; j < d; j += 32) {
+        s_box[warp][0][j] = __ldg(qlo + qt * d + j);
+        s_box[warp][1][j] = __ldg(qhi + qt * d + j);
+    }
+    float tm = 0.0f;
+    for (int r = lane; r < BM; r += 32) {
+        const int64_t gr = qt * BM + r;
+        if (gr < nq) tm = fmaxf(tm, __ldg(tau + gr));
+    }
+    tm = warp_max(tm);
+    // margin: 1e-3 relative + 5 x the documented fp32 gap of the kernel's distances on the scale of the norms
+    const float bound = fmaf(tm, 1.001f, 2e-5f * 2.0f * __int_as_float(__ldg(maxnorm_bits)));
+    __syncwarp();
+    const float* lo_a = s_box[warp][0];
+    const float* hi_a = s_box[warp][1];
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int cnt = 0;
+    int* my_list = list + qt * cap;
+    for (int64_t t0 = 0; t0 < n_tiles; t0 += 32) {
+        const int64_t t = t0 + lane;  // < ld_t (multiple of 32); tiles >= n_tiles hold empty boxes
+        float acc = 0.0f;
+        for (int c = 0; c < d; c += 16) {
+            const int c_end = min(c + 16, d);
+#pragma unroll 4
+            for (int j = c; j < c_end; ++j) {
+                const float lb = __ldg(dlo_t + (int64_t)j * ld_t + t), hb = __ldg(dhi_t + (int64_t)j * ld_t + t);
+                const float g = fmaxf(fmaxf(lb - hi_a[j], lo_a[j] - hb), 0.0f);
+                acc = fmaf(g, g, acc);
+            }
+            if (__all_sync(FULL, acc * 0.9999f > bound)) break;
+        }
+        const bool keep = t < n_tiles && !(acc * 0.9999f > bound);
+        const unsigned m = __ballot_sync(FULL, keep);
+        if (keep) {
+            const int pos = cnt + __popc(m & lt_mask);
+            if (pos < cap) my_list[pos] = (int)t;
+        }
+        cnt += __popc(m);
+    }
+    if (lane == 0) count[qt] = cnt;
 }
 
 // ------------------------------------------------------------------ host side
@@ -551,7 +829,42 @@ bool knn_tc_supported(int d, int k) {
     return 3 * stage + (size_t)tc::BM * k * 8 + 512 + 1024 <= (size_t)227 * 1024;
 }
 
-size_t knn_tc_workspace_bytes(int64_t nq, int64_t ndb, int d, bool same) {
+// process-wide switches of the pruned sweep (tdr_knn_set_prune)
+static int g_prune = [] {
+    const char* e = getenv("TDR_KNN_PRUNE");
+    return e ? atoi(e) : 1;
+}();
+static unsigned long long* g_sweep_stats = nullptr;
+
+void knn_tc_set_prune(int on, unsigned long long* stats) {
+    g_prune = on;
+    g_sweep_stats = stats;
+}
+
+namespace tc {
+struct PruneLayout {
+    int64_t n_tiles, ld_t, n_qtiles;
+    int cap;
+    size_t box_t, qbox, tau, count, list, dist, total;
+};
+static PruneLayout prune_layout(int64_t nq, int64_t ndb, int d, int k) {
+    PruneLayout L;
+    L.n_tiles = (ndb + BN - 1) / BN;
+    L.ld_t = (int64_t)align_up((size_t)L.n_tiles, 32);
+    L.n_qtiles = (nq + BM - 1) / BM;
+    L.cap = (int)std::min<int64_t>(L.n_tiles, kListCap);
+    L.box_t = align_up((size_t)d * L.ld_t * 4, 256);
+    L.qbox = align_up((size_t)L.n_qtiles * d * 4, 256);
+    L.tau = align_up((size_t)nq * 4, 256);
+    L.count = align_up((size_t)L.n_qtiles * 4, 256);
+    L.list = align_up((size_t)L.n_qtiles * L.cap * 4, 256);
+    L.dist = align_up((size_t)nq * k * 4, 256);  // distances for the sigma/rho kernel when the caller wants none
+    L.total = 256 + 2 * L.box_t + 2 * L.qbox + L.tau + L.count + L.list + L.dist;
+    return L;
+}
+}  // namespace tc
+
+size_t knn_tc_workspace_bytes(int64_t nq, int64_t ndb, int d, int k, bool same) {
     const int dp = (int)align_up((size_t)d, tc::KATOM);
     const int64_t ndb_pad = (int64_t)align_up((size_t)ndb, 128);
     const int64_t nq_pad = (int64_t)align_up((size_t)nq, 128);
@@ -562,6 +875,9 @@ size_t knn_tc_workspace_bytes(int64_t nq, int64_t ndb, int d, bool same) {
         b += align_up((size_t)nq_pad * 4, 256);
         b += 2 * align_up((size_t)nq * dp * 2, 256);
     }
+    // pruned sweep (queries inside the database only); part of the size whether or not the switch is on, so
+    // that a workspace sized before tdr_knn_set_prune() stays valid after it
+    if ((ndb + tc::BN - 1) / tc::BN >= tc::kPruneMinTiles) b += tc::prune_layout(nq, ndb, d, k).total;
     return b;
 }
 
@@ -570,7 +886,7 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
                   bool same, int exclude_self, int metric, int fused, int max_iter, float* out_dist, int32_t* out_idx,
                   float* P, float* rho, float* sigma, void* ws, size_t ws_bytes, cudaStream_t st) {
     using namespace tc;
-    const size_t need = knn_tc_workspace_bytes(nq, ndb, d, same);
+    const size_t need = knn_tc_workspace_bytes(nq, ndb, d, k, same);
     if (!ws || ws_bytes < need || (uintptr_t)ws % 256) {
         set_error("knn (tensor-core path) workspace: need %zu bytes (256-aligned), got %zu", need, ws_bytes);
         return TDR_E_WORKSPACE;
@@ -645,6 +961,10 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
     prm.sigma = sigma;
     const size_t stage_bytes = (size_t)atoms * 2 * TILE_BYTES;
     // two epilogue warpgroups when a second set of lists still leaves room for two TMA stages
+    {
+        const char* us = getenv("TDR_TC_UNSORTED");
+        prm.unsorted = (k <= 32 && !(us && atoi(us) == 0)) ? 1 : 0;
+    }
     prm.dual = ((size_t)3 * stage_bytes + (size_t)2 * BM * k * 8 + 512 + 1024 <= (size_t)227 * 1024) ? 1 : 0;
     if (prm.debug & 32) prm.dual = 0;
     const size_t fixed = stage_bytes + (size_t)(1 + prm.dual) * BM * k * 8 + 512 + 1024;
@@ -658,7 +978,66 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
     const size_t smem = fixed + (size_t)stages * stage_bytes;
     // per call: the attribute belongs to the current device's context (a process may drive several GPUs)
     TDR_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    knn_tc_kernel<<<(unsigned)((nq + BM - 1) / BM), prm.dual ? 384 : 256, smem, st>>>(mq_hi, mq_lo, mdb_hi, mdb_lo, prm);
+    const unsigned grid = (unsigned)((nq + BM - 1) / BM);
+    const unsigned threads = prm.dual ? 384 : 256;
+
+    // ---- pruned sweep: boxes -> phase A (window) -> surviving-tile lists; the launch below is phase B
+    const int64_t n_tiles = (ndb + BN - 1) / BN;
+    if (g_prune && same && n_tiles >= kPruneMinTiles && !prm.debug) {
+        const PruneLayout L = prune_layout(nq, ndb, d, k);
+        char* w = p;  // same: p is the end of the split buffers
+        if ((size_t)(w - (char*)ws) + L.total > ws_bytes) {
+            set_error("knn (tensor-core path) workspace: pruned sweep needs %zu more bytes", L.total);
+            return TDR_E_WORKSPACE;
+        }
+        int* maxnorm = (int*)w;
+        w += 256;
+        float* dlo_t = (float*)w;
+        w += L.box_t;
+        float* dhi_t = (float*)w;
+        w += L.box_t;
+        float* qlo = (float*)w;
+        w += L.qbox;
+        float* qhi = (float*)w;
+        w += L.qbox;
+        float* tau = (float*)w;
+        w += L.tau;
+        int* count = (int*)w;
+        w += L.count;
+        int* list = (int*)w;
+        w += L.list;
+        float* dist_scratch = (float*)w;
+        TDR_CUDA(cudaMemsetAsync(maxnorm, 0, 4, st));
+        tile_box_kernel<<<(unsigned)L.ld_t, 128, 0, st>>>(Xdb, 0, ndb, d, dlo_t, dhi_t, L.ld_t);
+        tile_box_kernel<<<(unsigned)L.n_qtiles, 128, 0, st>>>(Xdb, q_row0, q_row0 + nq, d, qlo, qhi, 0);
+        maxnorm_kernel<<<(unsigned)std::min<int64_t>((int64_t)kNumSMs * 8, (ndb + 255) / 256), 256, 0, st>>>(dbn, ndb, maxnorm);
+        Params pa = prm;
+        pa.win = kWindow;
+        pa.kth_out = tau;
+        pa.fused = 0;
+        pa.out_dist = nullptr;
+        pa.out_idx = nullptr;
+        knn_tc_kernel<<<grid, threads, smem, st>>>(mq_hi, mq_lo, mdb_hi, mdb_lo, pa);
+        tile_prune_kernel<<<(unsigned)((L.n_qtiles + 7) / 8), 256, 0, st>>>(qlo, qhi, dlo_t, dhi_t, L.n_qtiles, L.n_tiles,
+                                                                           L.ld_t, d, tau, nq, maxnorm, list, count, L.cap);
+        TDR_LAUNCH_CHECK();
+        prm.tau_seed = tau;
+        prm.tile_list = list;
+        prm.tile_count = count;
+        prm.list_cap = L.cap;
+        prm.sweep_stats = g_sweep_stats;
+        if (prm.fused) {
+            // With a handful of tiles per CTA the in-kernel sigma/rho search (12 warps per SM walking dependent
+            // bisection chains) would take longer than the sweep itself: 8.4 ms of 18.8 ms at 1 M x 128, against
+            // 3.5 ms for the standalone row kernel at full occupancy.  Same arithmetic, bit-identical rows.
+            prm.fused = 0;
+            if (!prm.out_dist) prm.out_dist = dist_scratch;
+            knn_tc_kernel<<<grid, threads, smem, st>>>(mq_hi, mq_lo, mdb_hi, mdb_lo, prm);
+            TDR_LAUNCH_CHECK();
+            return tdr_umap_affinity_f32(prm.out_dist, nq, k, max_iter, P, rho, sigma, (tdr_stream_t)st);
+        }
+    }
+    knn_tc_kernel<<<grid, threads, smem, st>>>(mq_hi, mq_lo, mdb_hi, mdb_lo, prm);
     TDR_LAUNCH_CHECK();
     return TDR_OK;
 }

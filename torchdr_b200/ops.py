@@ -37,6 +37,14 @@ def knn(Xq, Xdb, k, q_row0=0, exclude_self=True, metric="sqeuclidean"):
     return dist, idx
 
 
+def knn_set_prune(on=True, stats=None):
+    """Switch the tile-pruned sweep of the tensor-core kNN (``tdr_knn_set_prune``).  ``stats``: optional int64[2]
+    CUDA tensor that accumulates (tiles swept, tiles of a full sweep); keep it alive while it is registered."""
+    if stats is not None:
+        assert stats.is_cuda and stats.dtype == torch.int64 and stats.numel() >= 2 and stats.is_contiguous()
+    check(_lib.load().tdr_knn_set_prune(int(bool(on)), ptr(stats)), "tdr_knn_set_prune")
+
+
 def knn_umap_fused(Xq, Xdb, k, q_row0=0, exclude_self=True, max_iter=100, want_dist=True):
     """Fused kNN + UMAP rho/sigma search -> (dist|None, idx, P, rho, sigma)."""
     Xq, Xdb = _dev_f32(Xq, "Xq"), _dev_f32(Xdb, "Xdb")
