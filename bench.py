@@ -222,6 +222,8 @@ def build_graph(X, rank, world, max_iter, full_sweep=True):
         if full_sweep:
             ops.knn_set_prune(False)
             _, knn["full_ms"] = timed_knn()
+        ops.knn_set_prune(True, None)
+        timed_knn()  # warm-up: the first call pays the allocation of the (up to 10 GB) workspace
         ops.knn_set_prune(True, sweep)
         (dist_, idx, P, rho, sigma), knn["ms"] = timed_knn()
         knn["tile_pairs_swept"], knn["tile_pairs_all"] = (int(v) for v in sweep.tolist())

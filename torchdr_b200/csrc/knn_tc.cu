@@ -729,11 +729,36 @@ __global__ void __launch_bounds__(256) maxnorm_kernel(const float* __restrict__ 
     if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_int(m));
 }
 
-// one warp per query tile, lanes = 32 consecutive database tiles; 16 dimensions at a time with a warp-uniform
-// early exit (a far tile is settled by its first few dimensions)
+// boxes of super-tiles (32 consecutive tiles = 4096 rows), same transposed layout [d][ld_s]
+__global__ void __launch_bounds__(256) super_box_kernel(const float* __restrict__ lo_t, const float* __restrict__ hi_t,
+                                                        int64_t ld_t, int64_t n_super, int64_t ld_s, int d,
+                                                        float* __restrict__ slo_t, float* __restrict__ shi_t) {
+    // one warp per (dimension, super-tile): lanes = the 32 member tiles (empty boxes beyond the last real tile)
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= (int64_t)d * ld_s) return;
+    const int64_t j = w / ld_s, sidx = w - j * ld_s;
+    float mn = INFINITY, mx = -INFINITY;
+    if (sidx < n_super) {
+        mn = __ldg(lo_t + j * ld_t + sidx * 32 + lane);
+        mx = __ldg(hi_t + j * ld_t + sidx * 32 + lane);
+    }
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    if (lane == 0) {
+        slo_t[j * ld_s + sidx] = mn;
+        shi_t[j * ld_s + sidx] = mx;
+    }
+}
+
+// One warp per query tile.  Two levels: lanes first test 32 consecutive SUPER-tiles (32 tiles = 4096 rows each)
+// against the query box, then the member tiles of every surviving super-tile (lanes = its 32 tiles).  16
+// dimensions at a time with a warp-uniform early exit (a far box is settled by its first few dimensions).
+// Survivors are appended in ascending tile order.
 __global__ void __launch_bounds__(256)
 tile_prune_kernel(const float* __restrict__ qlo, const float* __restrict__ qhi, const float* __restrict__ dlo_t,
-                  const float* __restrict__ dhi_t, int64_t n_qtiles, int64_t n_tiles, int64_t ld_t, int d,
+                  const float* __restrict__ dhi_t, const float* __restrict__ slo_t, const float* __restrict__ shi_t,
+                  int64_t n_qtiles, int64_t n_tiles, int64_t ld_t, int64_t n_super, int64_t ld_s, int d,
                   const float* __restrict__ tau, int64_t nq, const int* __restrict__ maxnorm_bits,
                   int* __restrict__ list, int* __restrict__ count, int cap) {
     __shared__ float s_box[8][2][MAX_ATOMS * KATOM];
@@ -757,28 +782,41 @@ tile_prune_kernel(const float* __restrict__ qlo, const float* __restrict__ qhi, 
     const float* lo_a = s_box[warp][0];
     const float* hi_a = s_box[warp][1];
     const unsigned lt_mask = (1u << lane) - 1u;
-    int cnt = 0;
-    int* my_list = list + qt * cap;
-    for (int64_t t0 = 0; t0 < n_tiles; t0 += 32) {
-        const int64_t t = t0 + lane;  // < ld_t (multiple of 32); tiles >= n_tiles hold empty boxes
+    // squared box distance of this lane's box (column `col` of the transposed arrays) from the query box; true =
+    // "cannot hold a neighbour".  The early exit is warp-uniform, so all lanes run the same number of chunks.
+    auto too_far = [&](const float* __restrict__ lo_t, const float* __restrict__ hi_t, int64_t ld, int64_t col) {
         float acc = 0.0f;
         for (int c = 0; c < d; c += 16) {
             const int c_end = min(c + 16, d);
 #pragma unroll 4
             for (int j = c; j < c_end; ++j) {
-                const float lb = __ldg(dlo_t + (int64_t)j * ld_t + t), hb = __ldg(dhi_t + (int64_t)j * ld_t + t);
+                const float lb = __ldg(lo_t + (int64_t)j * ld + col), hb = __ldg(hi_t + (int64_t)j * ld + col);
                 const float g = fmaxf(fmaxf(lb - hi_a[j], lo_a[j] - hb), 0.0f);
                 acc = fmaf(g, g, acc);
             }
             if (__all_sync(FULL, acc * 0.9999f > bound)) break;
         }
-        const bool keep = t < n_tiles && !(acc * 0.9999f > bound);
-        const unsigned m = __ballot_sync(FULL, keep);
-        if (keep) {
-            const int pos = cnt + __popc(m & lt_mask);
-            if (pos < cap) my_list[pos] = (int)t;
+        return acc * 0.9999f > bound;
+    };
+    int cnt = 0;
+    int* my_list = list + qt * cap;
+    for (int64_t s0 = 0; s0 < n_super; s0 += 32) {
+        const int64_t sidx = s0 + lane;  // < ld_s (multiple of 32); super-tiles >= n_super hold empty boxes
+        const bool s_far = too_far(slo_t, shi_t, ld_s, sidx);  // every lane takes part in its votes
+        unsigned sm = __ballot_sync(FULL, sidx < n_super && !s_far);
+        while (sm) {
+            const int b = __ffs(sm) - 1;
+            sm &= sm - 1;
+            const int64_t t = (s0 + b) * 32 + lane;  // < ld_t; tiles >= n_tiles hold empty boxes
+            const bool t_far = too_far(dlo_t, dhi_t, ld_t, t);
+            const bool keep = t < n_tiles && !t_far;
+            const unsigned m = __ballot_sync(FULL, keep);
+            if (keep) {
+                const int pos = cnt + __popc(m & lt_mask);
+                if (pos < cap) my_list[pos] = (int)t;
+            }
+            cnt += __popc(m);
         }
-        cnt += __popc(m);
     }
     if (lane == 0) count[qt] = cnt;
 }
@@ -843,23 +881,26 @@ void knn_tc_set_prune(int on, unsigned long long* stats) {
 
 namespace tc {
 struct PruneLayout {
-    int64_t n_tiles, ld_t, n_qtiles;
+    int64_t n_tiles, ld_t, n_super, ld_s, n_qtiles;
     int cap;
-    size_t box_t, qbox, tau, count, list, dist, total;
+    size_t box_t, sbox_t, qbox, tau, count, list, dist, total;
 };
 static PruneLayout prune_layout(int64_t nq, int64_t ndb, int d, int k) {
     PruneLayout L;
     L.n_tiles = (ndb + BN - 1) / BN;
     L.ld_t = (int64_t)align_up((size_t)L.n_tiles, 32);
+    L.n_super = L.ld_t / 32;
+    L.ld_s = (int64_t)align_up((size_t)L.n_super, 32);
     L.n_qtiles = (nq + BM - 1) / BM;
     L.cap = (int)std::min<int64_t>(L.n_tiles, kListCap);
     L.box_t = align_up((size_t)d * L.ld_t * 4, 256);
+    L.sbox_t = align_up((size_t)d * L.ld_s * 4, 256);
     L.qbox = align_up((size_t)L.n_qtiles * d * 4, 256);
     L.tau = align_up((size_t)nq * 4, 256);
     L.count = align_up((size_t)L.n_qtiles * 4, 256);
     L.list = align_up((size_t)L.n_qtiles * L.cap * 4, 256);
     L.dist = align_up((size_t)nq * k * 4, 256);  // distances for the sigma/rho kernel when the caller wants none
-    L.total = 256 + 2 * L.box_t + 2 * L.qbox + L.tau + L.count + L.list + L.dist;
+    L.total = 256 + 2 * L.box_t + 2 * L.sbox_t + 2 * L.qbox + L.tau + L.count + L.list + L.dist;
     return L;
 }
 }  // namespace tc
@@ -996,6 +1037,10 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
         w += L.box_t;
         float* dhi_t = (float*)w;
         w += L.box_t;
+        float* slo_t = (float*)w;
+        w += L.sbox_t;
+        float* shi_t = (float*)w;
+        w += L.sbox_t;
         float* qlo = (float*)w;
         w += L.qbox;
         float* qhi = (float*)w;
@@ -1009,6 +1054,8 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
         float* dist_scratch = (float*)w;
         TDR_CUDA(cudaMemsetAsync(maxnorm, 0, 4, st));
         tile_box_kernel<<<(unsigned)L.ld_t, 128, 0, st>>>(Xdb, 0, ndb, d, dlo_t, dhi_t, L.ld_t);
+        super_box_kernel<<<(unsigned)(((int64_t)d * L.ld_s * 32 + 255) / 256), 256, 0, st>>>(dlo_t, dhi_t, L.ld_t, L.n_super,
+                                                                                             L.ld_s, d, slo_t, shi_t);
         tile_box_kernel<<<(unsigned)L.n_qtiles, 128, 0, st>>>(Xdb, q_row0, q_row0 + nq, d, qlo, qhi, 0);
         maxnorm_kernel<<<(unsigned)std::min<int64_t>((int64_t)kNumSMs * 8, (ndb + 255) / 256), 256, 0, st>>>(dbn, ndb, maxnorm);
         Params pa = prm;
@@ -1018,8 +1065,9 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
         pa.out_dist = nullptr;
         pa.out_idx = nullptr;
         knn_tc_kernel<<<grid, threads, smem, st>>>(mq_hi, mq_lo, mdb_hi, mdb_lo, pa);
-        tile_prune_kernel<<<(unsigned)((L.n_qtiles + 7) / 8), 256, 0, st>>>(qlo, qhi, dlo_t, dhi_t, L.n_qtiles, L.n_tiles,
-                                                                           L.ld_t, d, tau, nq, maxnorm, list, count, L.cap);
+        tile_prune_kernel<<<(unsigned)((L.n_qtiles + 7) / 8), 256, 0, st>>>(qlo, qhi, dlo_t, dhi_t, slo_t, shi_t, L.n_qtiles,
+                                                                           L.n_tiles, L.ld_t, L.n_super, L.ld_s, d, tau, nq,
+                                                                           maxnorm, list, count, L.cap);
         TDR_LAUNCH_CHECK();
         prm.tau_seed = tau;
         prm.tile_list = list;
