@@ -66,7 +66,8 @@ TDR_API int tdr_knn_f32(const float* Xq, int64_t nq, int64_t q_row0,
                 void* ws, size_t ws_bytes, tdr_stream_t stream);
 
 /* Kernel selection for the two kNN entry points: 0 = auto, 1 = fp32 SIMT kernel,
- * 2 = tcgen05 tensor-core kernel (fp16 hi/lo split, d <= 128, k <= 32).  Process-wide; meant
+ * 2 = tcgen05 tensor-core kernel (fp16 hi/lo split, d <= 128, lists + tiles <= 227 KB of shared memory:
+ * k <= 33 at d = 128, k <= 96 at d <= 64).  Process-wide; meant
  * for tests and profiling.  The environment variable TDR_KNN_PATH seeds it at load time. */
 TDR_API int tdr_knn_set_path(int path);
 

@@ -68,8 +68,18 @@ def main():
             nc = n // 1000
             centers = torch.randn(nc, d, generator=g) * 10
             X = (centers.repeat_interleave(1000, 0) + torch.randn(n, d, generator=g) * 0.5).numpy()
-        if kind == "shuffled":
+        if kind.endswith("shuffled") or kind.endswith("reordered"):
             X = X[np.random.default_rng(0).permutation(n)]
+        if kind.endswith("reordered"):  # coarse-quantiser pass: nearest of C sampled points, stable sort by cell
+            rng = np.random.default_rng(1)
+            C = max(64, n // int(__import__("os").environ.get("CELL", "256")))
+            cen = X[rng.choice(n, C, replace=False)].astype(np.float64)
+            cn = (cen ** 2).sum(1)
+            cell = np.empty(n, np.int64)
+            for a in range(0, n, 8192):
+                blk = X[a:a + 8192].astype(np.float64)
+                cell[a:a + 8192] = ((blk ** 2).sum(1)[:, None] + cn[None, :] - 2 * blk @ cen.T).argmin(1)
+            X = X[np.argsort(cell, kind="stable")]
     survive, T = plan(X, k)
     nt = survive.shape[0]
     per = survive.sum(1)

@@ -94,6 +94,8 @@ def test_knn_cross_and_chunk(ops):
 
 
 @pytest.mark.parametrize("kind,n,d,k", [("clustered", 60_000, 128, 15), ("clustered", 20_000, 50, 90),
+                                        ("clustered", 30_000, 128, 32), ("clustered", 24_000, 64, 20),
+                                        ("clustered", 9_000, 128, 1),
                                         ("uniform", 12_000, 64, 15), ("shuffled", 16_000, 128, 15)])
 def test_knn_pruned_sweep_is_bit_identical(ops, kind, n, d, k):
     """The tile-pruned sweep (csrc/knn_tc.cu) must return exactly what the full sweep returns — distances,

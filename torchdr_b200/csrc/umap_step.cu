@@ -320,13 +320,13 @@ __global__ void __launch_bounds__(kV2Threads, 4) umap_step_kernel_v2(const UmapS
 #include "umap_step_fast4.cuh"
 namespace tdr {
 
-template <int OCC, int CAP, bool NEG_CG>
+template <int OCC, int CAP, bool NEG_CG, bool L2H = false>
 static cudaError_t launch_fast4(const UmapStepParams& p, unsigned blocks, cudaStream_t st) {
     constexpr size_t smem = sizeof(Warp4Smem<CAP>) * kWarps4;
-    static const cudaError_t attr = cudaFuncSetAttribute(umap_step_kernel_fast4<OCC, CAP, NEG_CG>,
+    static const cudaError_t attr = cudaFuncSetAttribute(umap_step_kernel_fast4<OCC, CAP, NEG_CG, L2H>,
                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (attr != cudaSuccess) return attr;
-    umap_step_kernel_fast4<OCC, CAP, NEG_CG><<<blocks, kFastThreads, smem, st>>>(p);
+    umap_step_kernel_fast4<OCC, CAP, NEG_CG, L2H><<<blocks, kFastThreads, smem, st>>>(p);
     return cudaSuccess;
 }
 
@@ -361,6 +361,7 @@ static int launch_step(const UmapStepParams& p, int precise, cudaStream_t st) {
             case 2: err = launch_fast4<4, 320, true>(p, g4, st); break;
             case 3: err = launch_fast4<4, 256, false>(p, g4, st); break;
             case 4: err = launch_fast4<4, 288, true>(p, g4, st); break;
+            case 5: err = launch_fast4<4, 256, true, true>(p, g4, st); break;  // L2 eviction hints
             default: err = launch_fast4<4, 256, true>(p, g4, st); break;
         }
         TDR_CUDA(err);

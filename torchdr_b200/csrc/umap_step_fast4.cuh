@@ -36,7 +36,8 @@ struct Warp4Smem {
 
 // NEG_CG: gather the (uniformly random) negatives with ld.global.cg so they do not evict the neighbour
 // rows and edge streams from L1
-template <int MIN_CTAS, int kCap4, bool NEG_CG>
+// L2H: L2 eviction hints (umap_step_math.cuh) — edge streams evict-first, gathered rows of Z evict-last
+template <int MIN_CTAS, int kCap4, bool NEG_CG, bool L2H = false>
 __global__ void __launch_bounds__(kFastThreads, MIN_CTAS) umap_step_kernel_fast4(const UmapStepParams p) {
     extern __shared__ __align__(16) unsigned char s_raw4[];
     constexpr unsigned FULL = 0xffffffffu;
@@ -46,6 +47,7 @@ __global__ void __launch_bounds__(kFastThreads, MIN_CTAS) umap_step_kernel_fast4
     const int64_t warp_global = ((int64_t)blockIdx.x * kFastThreads + threadIdx.x) >> 5;
     const int64_t n_warps = (int64_t)gridDim.x * kWarps4;
     const float due_before = (float)(p.n_iter + 1);  // umap.py:251
+    const uint64_t pol_keep = L2H ? l2_policy_evict_last() : 0, pol_stream = L2H ? l2_policy_evict_first() : 0;
     const Philox rng(p.seed);
     const uint32_t nm1 = (uint32_t)(p.n_total - 1);
     const uint32_t c0 = (uint32_t)p.n_iter, c1 = (uint32_t)(p.n_iter >> 32);
@@ -92,7 +94,7 @@ __global__ void __launch_bounds__(kFastThreads, MIN_CTAS) umap_step_kernel_fast4
                 in.valid = t < nd;
                 const int cj = in.valid ? sm.a[t].x : gi;
                 in.z = in.valid ? sm.b[t] : zi;
-                in.zj = __ldg(p.Zin + cj);
+                in.zj = L2H ? ldg_f2_hint(p.Zin + cj, pol_keep) : __ldg(p.Zin + cj);
                 return in;
             };
             auto eval_edge = [&](const EdgeIn& in, int t) {
@@ -125,9 +127,15 @@ __global__ void __launch_bounds__(kFastThreads, MIN_CTAS) umap_step_kernel_fast4
                 for (int u = 0; u < FU; ++u) {
                     const int c = cb + u * 32 + lane;
                     const bool ok = c < total;
-                    nxt[u] = ok ? eons_w[c] : INFINITY;
-                    cj[u] = ok ? __ldg(col_w + c) : 0;
-                    ep[u] = ok ? __ldg(eps_w + c) : 0.0f;
+                    if (L2H) {
+                        nxt[u] = ok ? ld_f32_hint(eons_w + c, pol_stream) : INFINITY;
+                        cj[u] = ok ? ldg_s32_hint(col_w + c, pol_stream) : 0;
+                        ep[u] = ok ? ldg_f32_hint(eps_w + c, pol_stream) : 0.0f;
+                    } else {
+                        nxt[u] = ok ? eons_w[c] : INFINITY;
+                        cj[u] = ok ? __ldg(col_w + c) : 0;
+                        ep[u] = ok ? __ldg(eps_w + c) : 0.0f;
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < FU; ++u) {
@@ -194,7 +202,9 @@ __global__ void __launch_bounds__(kFastThreads, MIN_CTAS) umap_step_kernel_fast4
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u)  // unused slot: dx = dy = 0
-                    in.zn[u] = (u < nval) ? (NEG_CG ? __ldcg(p.Zin + jn[u]) : __ldg(p.Zin + jn[u])) : in.z;
+                    in.zn[u] = (u < nval) ? (L2H ? ldcg_f2_hint(p.Zin + jn[u], pol_keep)
+                                                 : (NEG_CG ? __ldcg(p.Zin + jn[u]) : __ldg(p.Zin + jn[u])))
+                                          : in.z;
                 return in;
             };
             auto eval_quad = [&](const QuadIn& in, int w) {

@@ -35,6 +35,45 @@ __device__ __forceinline__ float pow_fast(float x, float y) {
     return __int_as_float(__float_as_int(r) + ((int)n << 23));
 }
 
+// L2 eviction-priority hints (createpolicy + ld.global.L2::cache_hint).  At 10 M points the embedding (80 MB) and
+// the edge streams (3.2 GB per iteration) compete for the 126 MB L2: the streams are read once per iteration and
+// are marked evict-first, the gathered rows of Z are marked evict-last.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float2 ldg_f2_hint(const float2* a, uint64_t pol) {
+    float2 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(a), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float2 ldcg_f2_hint(const float2* a, uint64_t pol) {
+    float2 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(a), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float ld_f32_hint(const float* a, uint64_t pol) {
+    float v;
+    asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(a), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ldg_f32_hint(const float* a, uint64_t pol) {
+    float v;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(a), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ int ldg_s32_hint(const int* a, uint64_t pol) {
+    int v;
+    asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
+    return v;
+}
+
 __device__ __forceinline__ float rcp_fast(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
