@@ -29,6 +29,8 @@ from .knn import (  # noqa: F401
     knn_chunked,
     pairwise_full,
     knn_ambiguity,
+    tile_prune_plan,
+    knn_with_tile_mask,
 )
 from .root_search import bisect_rows  # noqa: F401
 from .affinity import (  # noqa: F401

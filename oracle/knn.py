@@ -114,3 +114,60 @@ def knn_ambiguity(X, k, tau_rel=4e-6, block=2048, q_start=0, q_end=None):
         idx_out.append(i[:, :k])
         d_out.append(v[:, :k])
     return torch.cat(idx_out), torch.cat(d_out), torch.cat(e_ok), torch.cat(s_ok)
+
+
+# --------------------------------------------------------------------------------------------------
+# Restatement of the ENGINE's tile-pruning rule (torchdr_b200/csrc/knn_tc.cu, "pruned sweep").  The
+# reference has no such step (distance/torch.py:81-122 always forms the full N x N matrix); this is
+# test infrastructure that states, on the CPU, the rule the CUDA path must obey: a database tile may be
+# skipped for a query tile only if no row of the query tile can have a neighbour in it.
+def tile_prune_plan(X, k, tile=128, window=4, exclude_self=True):
+    """Surviving-tile mask ``keep[n_tiles, n_tiles]`` (query tile x database tile) and the per-row bounds tau.
+
+    tau_i: k-th smallest expanded-form distance of row i inside the +-``window`` tiles around its own
+    tile (any upper bound on the k-th neighbour distance is admissible; the kernel uses group minima).
+    keep[A, B] = box_distance^2(A, B) * 0.9999 <= max_{i in A} tau_i * 1.001 + 2e-5 * 2 * max ||x||^2,
+    the same margins as ``tile_prune_kernel``."""
+    X = X.float()
+    n = X.shape[0]
+    nt = (n + tile - 1) // tile
+    nx = (X**2).sum(-1)
+    lo = torch.stack([X[t * tile:(t + 1) * tile].min(0).values for t in range(nt)])
+    hi = torch.stack([X[t * tile:(t + 1) * tile].max(0).values for t in range(nt)])
+    tau = torch.empty(n)
+    for t in range(nt):
+        a, b = max(0, t - window), min(nt, t + window + 1)
+        rows = slice(t * tile, min((t + 1) * tile, n))
+        cols = slice(a * tile, min(b * tile, n))
+        C = _expanded_sq(X[rows], X[cols], nx[rows], nx[cols])
+        if exclude_self:
+            r = torch.arange(C.shape[0])
+            C[r, r + (rows.start - cols.start)] = float("inf")
+        tau[rows] = C.kthvalue(k, dim=1).values
+    bound = torch.stack([tau[t * tile:(t + 1) * tile].max() for t in range(nt)]) * 1.001 + 2e-5 * 2 * float(nx.max())
+    keep = torch.zeros(nt, nt, dtype=torch.bool)
+    for A in range(nt):
+        gap = torch.maximum(torch.maximum(lo - hi[A], lo[A] - hi), torch.zeros(()))
+        keep[A] = (gap * gap).sum(1) * 0.9999 <= bound[A]
+    return keep, tau
+
+
+def knn_with_tile_mask(X, k, keep, tile=128, exclude_self=True):
+    """Exact kNN restricted to the database tiles ``keep`` allows (ascending, ties to the lower index)."""
+    X = X.float()
+    n = X.shape[0]
+    nx = (X**2).sum(-1)
+    nt = keep.shape[0]
+    out_v, out_i = [], []
+    for A in range(nt):
+        rows = slice(A * tile, min((A + 1) * tile, n))
+        C = _expanded_sq(X[rows], X, nx[rows], nx)
+        if exclude_self:
+            r = torch.arange(C.shape[0])
+            C[r, r + rows.start] = float("inf")
+        mask = keep[A].repeat_interleave(tile)[:n]
+        C = torch.where(mask.unsqueeze(0), C, torch.full((), float("inf")))
+        order = torch.argsort(C, dim=1, stable=True)[:, :k]
+        out_v.append(C.gather(1, order))
+        out_i.append(order.int())
+    return torch.cat(out_v), torch.cat(out_i)

@@ -174,3 +174,44 @@ def test_collectives_world_size_2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_tile_prune_rule_is_exact_on_cpu():
+    """The rule the CUDA pruned sweep implements (oracle/knn.py:tile_prune_plan, same margins): kNN restricted to
+    the surviving tiles equals the dense kNN of the reference path, on index-local clusters (where it prunes),
+    on shuffled rows (where it cannot) and with clusters smaller than a tile (every tile straddles several)."""
+    import oracle
+    from helpers import clustered
+
+    for n, d, k, shuffle in ((6000, 32, 15, False), (6000, 32, 15, True), (4000, 16, 5, False)):
+        X = clustered(n, d)  # min(1000, n // 100) clusters of ~100 points, contiguous
+        if shuffle:
+            X = X[torch.randperm(n, generator=torch.Generator().manual_seed(0))].contiguous()
+        keep, tau = oracle.tile_prune_plan(X, k)
+        C_ref, I_ref = oracle.knn_dense(X, k)
+        C, I = oracle.knn_with_tile_mask(X, k, keep)
+        idx64, _, entry_ok, _ = oracle.knn_ambiguity(X, k)
+        assert torch.equal(I.long()[entry_ok], I_ref.long()[entry_ok])
+        # blockwise and full sgemm may round differently: distances on the scale of the norms (knn_ambiguity's gap)
+        assert float((C - C_ref).abs().max()) <= 4e-6 * 2 * float((X**2).sum(1).max())
+        assert bool((tau >= C_ref[:, k - 1] - 1e-3).all())  # tau bounds the k-th neighbour distance
+        frac = float(keep.float().mean())
+        assert bool(keep.diagonal().all())
+        if not shuffle:
+            assert frac < 0.5, frac
+        else:
+            assert frac > 0.9, frac
+
+
+def test_knn_prune_switch_validates_without_a_gpu():
+    from torchdr_b200 import _lib
+
+    lib = _lib.load()
+    assert lib.tdr_knn_set_prune(1, None) == 0
+    assert lib.tdr_knn_set_prune(2, None) == _lib.TDR_E_INVALID
+    assert "tdr_knn_set_prune" in _lib.last_error()
+    assert lib.tdr_knn_set_prune(1, None) == 0
+    # the workspace query covers the pruned sweep's buffers (boxes, bounds, tile lists) once there are >= 64 tiles
+    small = lib.tdr_knn_workspace_bytes(64 * 128 - 1, 64 * 128 - 128, 128, 15)
+    big = lib.tdr_knn_workspace_bytes(64 * 128, 64 * 128, 128, 15)
+    assert big > small + 64 * 64 * 4
