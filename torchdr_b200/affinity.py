@@ -12,6 +12,8 @@ estimator consumes directly instead of the padded layout.
 
 import logging
 import math
+import os
+import time
 
 import torch
 
@@ -150,6 +152,10 @@ class UMAPAffinity(_SparseAffinityBase):
         if self.verbose:
             self.logger.info(f"Sparsity mode enabled, computing {k} nearest neighbors...")
         s, e = self._chunk(n)
+        timing = os.environ.get("TDR_TIMING") == "1"  # stage timers of scripts/e2e_breakdown.py
+        if timing:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
         if self.metric == "sqeuclidean":
             dist, idx, P, rho, sigma = ops.knn_umap_fused(X[s:e], X, k, q_row0=s, exclude_self=bool(self.zero_diag),
                                                           max_iter=self.max_iter)
@@ -158,6 +164,9 @@ class UMAPAffinity(_SparseAffinityBase):
             P, rho, sigma = ops.umap_affinity_rows(dist, self.max_iter)
         self.rho_, self.eps_ = rho, sigma
         self.knn_ = (dist, idx)
+        if timing:
+            torch.cuda.synchronize()
+            self.timings_ = {"knn+sigma": time.perf_counter() - t0}
         if not self.symmetrize:
             self.csr_ = None
             return P, idx
