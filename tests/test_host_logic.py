@@ -215,3 +215,33 @@ def test_knn_prune_switch_validates_without_a_gpu():
     small = lib.tdr_knn_workspace_bytes(64 * 128 - 1, 64 * 128 - 128, 128, 15)
     big = lib.tdr_knn_workspace_bytes(64 * 128, 64 * 128, 128, 15)
     assert big > small + 64 * 64 * 4
+
+
+def test_voronoi_tree_order_restores_locality_on_cpu():
+    """torchdr_b200/reorder.py (experimental): a valid permutation; on shuffled clustered rows the re-ordered tiles
+    are spatially compact again, so the pruning rule (oracle/knn.py:tile_prune_plan) drops most tile pairs, and a kNN
+    run on the re-ordered rows maps back to the kNN of the original rows."""
+    import oracle
+    from helpers import clustered
+    from torchdr_b200.reorder import knn_in_any_order, voronoi_tree_order
+
+    n, d, k = 6000, 32, 10
+    X = clustered(n, d)
+    Xs = X[torch.randperm(n, generator=torch.Generator().manual_seed(0))].contiguous()
+    g = torch.Generator().manual_seed(1)
+    perm = voronoi_tree_order(Xs, generator=g)
+    assert perm.dtype == torch.long and torch.equal(perm.sort().values, torch.arange(n))
+    keep_shuffled, _ = oracle.tile_prune_plan(Xs, k)
+    keep_sorted, _ = oracle.tile_prune_plan(Xs[perm], k)
+    assert float(keep_shuffled.float().mean()) > 0.9
+    assert float(keep_sorted.float().mean()) < 0.35, float(keep_sorted.float().mean())
+    # duplicates cannot be split: the recursion must still terminate and return a permutation
+    Xdup = torch.cat([Xs[:300], Xs[:1].repeat(700, 1)])
+    pd = voronoi_tree_order(Xdup, generator=g)
+    assert torch.equal(pd.sort().values, torch.arange(1000))
+    # kNN through the permutation == kNN of the original rows
+    C_ref, I_ref = oracle.knn_dense(Xs, k)
+    C, I, _ = knn_in_any_order(Xs, k, lambda Xp: oracle.knn_dense(Xp, k), perm=perm)
+    _, _, entry_ok, _ = oracle.knn_ambiguity(Xs, k)
+    assert torch.equal(I.long()[entry_ok], I_ref.long()[entry_ok])
+    assert float((C - C_ref).abs().max()) <= 4e-6 * 2 * float((Xs**2).sum(1).max())
