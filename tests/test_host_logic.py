@@ -245,3 +245,95 @@ def test_voronoi_tree_order_restores_locality_on_cpu():
     _, _, entry_ok, _ = oracle.knn_ambiguity(Xs, k)
     assert torch.equal(I.long()[entry_ok], I_ref.long()[entry_ok])
     assert float((C - C_ref).abs().max()) <= 4e-6 * 2 * float((Xs**2).sum(1).max())
+
+
+def test_umap_loop_bookkeeping_without_a_gpu(monkeypatch):
+    """The batched UMAP loop (torchdr_b200/neighbor_embedding.py:UMAP._loop) with the native call replaced by a
+    recorder: batches end at the reference's check points (affinity_matcher.py:331-349), the learning rates handed
+    to the kernels are the reference's LinearLR sequence although they are produced one batch ahead, and the loop
+    stops at the first check whose gradient norm is below min_grad_norm."""
+    import oracle
+    from torchdr_b200 import neighbor_embedding as ne
+    from torchdr_b200 import ops
+
+    calls = []
+
+    def fake_run(Za, Zb, rowptr, col, eps, eons, n_iter0, lrs, a, b, gnorm_sq=None, **kw):
+        calls.append((int(n_iter0), [float(x) for x in lrs], gnorm_sq is not None))
+        if gnorm_sq is not None:
+            gnorm_sq.fill_(fake_run.gnorm_sq)
+        return Za if len(lrs) % 2 == 0 else Zb
+
+    monkeypatch.setattr(ops, "umap_run", fake_run)
+
+    def run(max_iter, check_interval, gnorm_sq, min_grad_norm=1e-7):
+        calls.clear()
+        fake_run.gnorm_sq = gnorm_sq
+        m = ne.UMAP(n_neighbors=5, max_iter=max_iter, check_interval=check_interval, min_grad_norm=min_grad_norm,
+                    a=1.5, b=0.9, random_state=0, distributed=False)
+        m.n_samples_in_, m.chunk_start_, m.chunk_end_ = 8, 0, 8
+        m.early_exaggeration_coeff_ = 1
+        m._graph = (torch.zeros(9, dtype=torch.long), torch.zeros(0, dtype=torch.int32), torch.zeros(0), torch.zeros(0))
+        m.embedding_ = torch.zeros(8, 2)
+        m._gnorm, m._nan = torch.zeros(1, dtype=torch.float64), torch.zeros(1, dtype=torch.int32)
+        m._dummy = torch.nn.Parameter(torch.zeros(1))
+        m.params_ = [{"params": [m._dummy]}]
+        m._set_learning_rate()
+        m._configure_optimizer()
+        m._configure_scheduler()
+        m._loop()
+        return m
+
+    m = run(130, 50, gnorm_sq=1.0)
+    assert [(c[0], len(c[1]), c[2]) for c in calls] == [(0, 1, True), (1, 50, True), (51, 50, True), (101, 29, False)]
+    lrs = np.asarray([x for c in calls for x in c[1]], dtype=np.float32)
+    assert np.array_equal(lrs, oracle.linear_lr_sequence(1.0, 130, 130))  # umap.py:139, NE base.py:175-182
+    assert m._last_step == 129
+    m = run(400, 20, gnorm_sq=1e-20)  # converged at the very first check
+    assert [(c[0], len(c[1])) for c in calls] == [(0, 1)] and m._last_step == 0
+    m = run(75, 25, gnorm_sq=1.0)
+    assert [(c[0], len(c[1])) for c in calls] == [(0, 1), (1, 25), (26, 25), (51, 24)]
+
+
+def test_momentum_loop_bookkeeping_matches_reference_sequences(monkeypatch):
+    """The gradient + momentum-SGD loop shared by LargeVis / TSNE / InfoTSNE / SNE with the two native calls replaced
+    by recorders: the (lr, momentum, buffer-restart) triple handed to `tdr_sgd_momentum_f32` at every step must be the
+    sequence the REFERENCE run produced (lr captured in tests/golden/*.npz by make_golden*.py), including the quirk
+    that the optimiser rebuilt after early exaggeration keeps the first build's lr and momentum
+    (affinity_matcher.py:588-590, oracle/tsne.py) and the LinearLR restart of InfoTSNE."""
+    from torchdr_b200 import neighbor_embedding as ne
+    from torchdr_b200 import ops
+
+    steps = []
+    monkeypatch.setattr(ops, "sgd_momentum",
+                        lambda Z, mom, grad, lr, mu, first, **kw: steps.append((float(lr), float(mu), bool(first))))
+
+    def run(cls, name, **kw):
+        steps.clear()
+        g = golden(name)
+        m = cls(perplexity=10, init="normal", random_state=0, min_grad_norm=0.0, distributed=False, **kw)
+        m._compute_gradient = lambda Z, step: None
+        m.n_samples_in_, m.chunk_start_, m.chunk_end_ = 300, 0, 300
+        m.early_exaggeration_coeff_ = m.early_exaggeration_coeff
+        m.embedding_ = torch.zeros(300, 2)
+        m._gnorm, m._nan = torch.ones(1, dtype=torch.float64), torch.zeros(1, dtype=torch.int32)
+        m._dummy = torch.nn.Parameter(torch.zeros(1))
+        m.params_ = [{"params": [m._dummy]}]
+        m._set_learning_rate()
+        m._configure_optimizer()
+        m._configure_scheduler()
+        m._loop()
+        lr_ref = np.asarray(g["lr"], dtype=np.float64)
+        assert len(steps) == len(lr_ref)
+        np.testing.assert_allclose([s[0] for s in steps], lr_ref, rtol=1e-7)
+        return [s[1] for s in steps], [s[2] for s in steps]
+
+    mu, first = run(ne.LargeVis, "largevis_n300_d16_p10", max_iter=30)
+    assert set(mu) == {0.8} and first == [True] + [False] * 29
+    mu, first = run(ne.TSNE, "tsne_n300_d16_p10", max_iter=20, early_exaggeration_iter=10)
+    assert set(mu) == {0.5}  # the rebuilt optimiser keeps momentum 0.5 (and lr 50)
+    assert [i for i, f in enumerate(first) if f] == [0, 11]  # momentum buffer restarts after the switch at step 10
+    mu, first = run(ne.InfoTSNE, "infotsne_n300_d16_p10", max_iter=20, early_exaggeration_iter=10, n_negatives=50)
+    assert set(mu) == {0.5} and [i for i, f in enumerate(first) if f] == [0, 11]
+    mu, first = run(ne.SNE, "sne_n300_d16_p10", max_iter=20)
+    assert set(mu) == {0.8} and first == [True] + [False] * 19
