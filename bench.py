@@ -299,13 +299,10 @@ def gpu_arm(args):
             cur = ops.umap_run_p2p(peer, cur, s, e - s, rowptr, col, eps, eons, t0, lr_all[t0:t0 + count], a, b,
                                    n_neg=N_NEG, seed=1234, nan_flag=nan_flag)
             return peer.bufs[cur], peer.bufs[1 - cur]
-        for t in range(t0, t0 + count):
-            if False:
-                pass
-            else:
-                ops.umap_step(Za, Zb, s, e - s, rowptr, col, eps, eons, t, a, b, float(lr_all[t]), neg=None,
-                              n_neg=N_NEG, seed=1234, nan_flag=nan_flag, stats=stats_t)
-                all_gather_rows(Zb, bounds, rank)
+        for t in range(t0, t0 + count):  # fallback exchange: one NCCL all-gather of the updated rows per iteration
+            ops.umap_step(Za, Zb, s, e - s, rowptr, col, eps, eons, t, a, b, float(lr_all[t]), neg=None,
+                          n_neg=N_NEG, seed=1234, nan_flag=nan_flag, stats=stats_t)
+            all_gather_rows(Zb, bounds, rank)
             Za, Zb = Zb, Za
         return Za, Zb
 
@@ -352,7 +349,7 @@ def gpu_arm(args):
     except Exception:
         pass
     kernel_ms = ms_per_step  # N=1: the timed region contains only the K step-kernel launches
-    achieved = alg_bytes / world / (kernel_ms * 1e-3) / 1e9 if world == 1 else alg_bytes / world / (kernel_ms * 1e-3) / 1e9
+    achieved = alg_bytes / world / (kernel_ms * 1e-3) / 1e9  # per GPU
     traffic = None
     prof = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
     if os.path.exists(prof):
@@ -401,7 +398,7 @@ def gpu_arm(args):
                        "l2": "per-iteration working set (CSR edge state %.0f MB) exceeds the 126 MB L2; no flush" %
                              (nnz * 12 / 1e6 / world)},
             "roofline": roofline, "affinity_kernel": affinity,
-            "gpu_launches": K if world == 1 else K,
+            "gpu_launches": K,  # per rank: one step-kernel launch per iteration (+ one flag-barrier kernel at N > 1)
             "clocks": clk.summary(),
             "graph": {"nnz_symmetrised": nnz_sym, "nnz_live": nnz, "sampled_edges_per_iter": act,
                       "negatives_per_iter": negs},
