@@ -74,7 +74,9 @@ TDR_API int tdr_knn_set_path(int path);
 /* Tile-pruned sweep of the tensor-core kNN (queries that are rows of the database, >= 64 database tiles):
  * database tiles whose bounding box is farther from the query tile's box than a bound on the tile's k-th
  * neighbour distances are not swept.  Results are bit-identical to the full sweep.  on = 1 (default; the
- * environment variable TDR_KNN_PRUNE seeds it) / 0.  sweep_stats: optional device pointer to two uint64
+ * environment variable TDR_KNN_PRUNE seeds it) / 0; on = 2 is EXPERIMENTAL (not yet verified on hardware):
+ * thresholds that ignore outlier rows, then a certification pass and a second sweep of the uncertified query
+ * tiles.  sweep_stats: optional device pointer to two uint64
  * counters, [0] += tiles swept, [1] += tiles a full sweep would visit (per kNN call, summed over query tiles);
  * null disables the counters.  Process-wide. */
 TDR_API int tdr_knn_set_prune(int on, uint64_t* sweep_stats);

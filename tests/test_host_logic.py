@@ -208,7 +208,7 @@ def test_knn_prune_switch_validates_without_a_gpu():
 
     lib = _lib.load()
     assert lib.tdr_knn_set_prune(1, None) == 0
-    assert lib.tdr_knn_set_prune(2, None) == _lib.TDR_E_INVALID
+    assert lib.tdr_knn_set_prune(3, None) == _lib.TDR_E_INVALID
     assert "tdr_knn_set_prune" in _lib.last_error()
     assert lib.tdr_knn_set_prune(1, None) == 0
     # the workspace query covers the pruned sweep's buffers (boxes, bounds, tile lists) once there are >= 64 tiles

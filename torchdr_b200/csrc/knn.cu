@@ -531,7 +531,7 @@ extern "C" TDR_API int tdr_knn_set_path(int path) {
 }
 
 extern "C" TDR_API int tdr_knn_set_prune(int on, uint64_t* sweep_stats) {
-    TDR_CHECK_ARG(on == 0 || on == 1, "tdr_knn_set_prune: on must be 0 or 1");
+    TDR_CHECK_ARG(on >= 0 && on <= 2, "tdr_knn_set_prune: on must be 0, 1 or 2");
     knn_tc_set_prune(on, reinterpret_cast<unsigned long long*>(sweep_stats));
     return TDR_OK;
 }

@@ -237,6 +237,9 @@ struct Params {
     float* kth_out;          // phase A: only a bound on the k-th distance of every row is written (squared domain)
     const float* tau_seed;   // phase B: that bound; the row's threshold starts there instead of at +inf
     unsigned long long* sweep_stats;  // optional: [0] += tiles swept, [1] += tiles of a full sweep
+    // re-sweep of selected query tiles (robust mode): CTA b works on query tile qtile_map[b]; CTAs >= *qtile_count exit
+    const int* qtile_map;
+    const int* qtile_count;
     float* out_dist;
     int32_t* out_idx;
     float* P;
@@ -244,6 +247,9 @@ struct Params {
     float* sigma;
 };
 
+// REDO: the robust mode's second sweep (CTA -> query tile through prm.qtile_map); a separate instantiation so that
+// the default kernel keeps its register allocation (168, no spills)
+template <bool REDO>
 __global__ void __launch_bounds__(384, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
               const __grid_constant__ CUtensorMap map_db_hi, const __grid_constant__ CUtensorMap map_db_lo,
@@ -262,7 +268,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 5);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t q0 = (int64_t)blockIdx.x * BM;
+    int64_t qtile = blockIdx.x;
+    if (REDO) {  // uniform over the CTA, before any barrier or allocation
+        if ((int)blockIdx.x >= __ldg(prm.qtile_count)) return;
+        qtile = __ldg(prm.qtile_map + blockIdx.x);
+    }
+    const int64_t q0 = qtile * BM;
     const int64_t n_tiles = (prm.ndb + BN - 1) / BN;
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
@@ -275,9 +286,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
         t_first = max((int64_t)0, r0 / BN - prm.win);
         n_sweep = min(n_tiles, (r0 + BM - 1) / BN + prm.win + 1) - t_first;
     } else if (prm.tile_count) {
-        const int c = __ldg(prm.tile_count + blockIdx.x);
+        const int c = __ldg(prm.tile_count + qtile);
         if (c <= prm.list_cap) {
-            my_list = prm.tile_list + (int64_t)blockIdx.x * prm.list_cap;
+            my_list = prm.tile_list + qtile * prm.list_cap;
             n_sweep = c;
         }
     }
@@ -760,24 +771,65 @@ tile_prune_kernel(const float* __restrict__ qlo, const float* __restrict__ qhi, 
                   const float* __restrict__ dhi_t, const float* __restrict__ slo_t, const float* __restrict__ shi_t,
                   int64_t n_qtiles, int64_t n_tiles, int64_t ld_t, int64_t n_super, int64_t ld_s, int d,
                   const float* __restrict__ tau, int64_t nq, const int* __restrict__ maxnorm_bits,
-                  int* __restrict__ list, int* __restrict__ count, int cap) {
+                  int* __restrict__ list, int* __restrict__ count, int cap,
+                  // robust mode (all zero / null in the default path):
+                  int tau_stride, int tau_is_sqrt, int robust, float* __restrict__ bound_out,
+                  const int* __restrict__ qtile_map, const int* __restrict__ qtile_count) {
     __shared__ float s_box[8][2][MAX_ATOMS * KATOM];
+    __shared__ float s_tau[8][BM];
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t qt = (int64_t)blockIdx.x * 8 + warp;
+    int64_t qt = (int64_t)blockIdx.x * 8 + warp;
+    if (qtile_map) {
+        if (qt >= (int64_t)__ldg(qtile_count)) return;  // whole warp
+        qt = __ldg(qtile_map + qt);
+    }
     if (qt >= n_qtiles) return;  // whole warp
     for (int j = lane; j < d; j += 32) {
         s_box[warp][0][j] = __ldg(qlo + qt * d + j);
         s_box[warp][1][j] = __ldg(qhi + qt * d + j);
     }
+    const int64_t stride = tau_stride > 0 ? tau_stride : 1;
     float tm = 0.0f;
     for (int r = lane; r < BM; r += 32) {
         const int64_t gr = qt * BM + r;
-        if (gr < nq) tm = fmaxf(tm, __ldg(tau + gr));
+        float v = -1.0f;  // rows beyond nq never decide anything
+        if (gr < nq) {
+            v = __ldg(tau + gr * stride);
+            if (tau_is_sqrt) v = v * v;
+            tm = fmaxf(tm, v);
+        }
+        s_tau[warp][r] = v;
     }
     tm = warp_max(tm);
+    __syncwarp();
+    if (robust) {
+        // Outlier rejection: a row whose bound is far above the tile's median (its neighbours are not inside the
+        // phase-A window) must not decide what the other 127 rows sweep.  tm = largest bound <= 4 x the median; rows
+        // above it are caught by knn_certify_kernel after the sweep and their tile is swept again.
+        const int n_valid = (int)min((int64_t)BM, nq - qt * BM);
+        float med = 0.0f;
+        for (int e = 0; e < BM / 32; ++e) {
+            const int me = lane + 32 * e;
+            const float v = s_tau[warp][me];
+            int rank = 0;
+            for (int q = 0; q < n_valid; ++q) {
+                const float x = s_tau[warp][q];
+                rank += (x < v || (x == v && q < me)) ? 1 : 0;
+            }
+            const unsigned hit = __ballot_sync(FULL, me < n_valid && rank == n_valid / 2);
+            if (hit) med = __shfl_sync(FULL, v, __ffs(hit) - 1);
+        }
+        float t2 = 0.0f;
+        for (int r = lane; r < n_valid; r += 32) {
+            const float v = s_tau[warp][r];
+            if (v <= 4.0f * med) t2 = fmaxf(t2, v);
+        }
+        tm = warp_max(t2);
+    }
     // margin: 1e-3 relative + 5 x the documented fp32 gap of the kernel's distances on the scale of the norms
     const float bound = fmaf(tm, 1.001f, 2e-5f * 2.0f * __int_as_float(__ldg(maxnorm_bits)));
+    if (bound_out && lane == 0) bound_out[qt] = bound;
     __syncwarp();
     const float* lo_a = s_box[warp][0];
     const float* hi_a = s_box[warp][1];
@@ -819,6 +871,31 @@ tile_prune_kernel(const float* __restrict__ qlo, const float* __restrict__ qhi, 
         }
     }
     if (lane == 0) count[qt] = cnt;
+}
+
+// Robust mode, after the sweep: row i is certified exact iff kth_i * 1.001 + margin <= the bound its tile was swept
+// with — every database tile within that box distance of the query TILE was swept, and the distance of a point to a
+// box is at least the distance between the boxes.  Query tiles with an uncertified row are queued for a second sweep.
+__global__ void __launch_bounds__(256)
+knn_certify_kernel(const float* __restrict__ out_dist, int k, int dist_is_sqrt, int64_t nq, int64_t n_qtiles,
+                   const float* __restrict__ bound_used, const int* __restrict__ maxnorm_bits,
+                   const int* __restrict__ tile_count, int cap, int* __restrict__ redo_map,
+                   int* __restrict__ redo_count) {
+    const int lane = threadIdx.x & 31;
+    const int64_t qt = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (qt >= n_qtiles) return;
+    if (__ldg(tile_count + qt) > cap) return;  // the list overflowed: this tile swept everything, it is exact
+    const float margin = 2e-5f * 2.0f * __int_as_float(__ldg(maxnorm_bits));
+    const float used = __ldg(bound_used + qt);
+    bool bad = false;
+    for (int r = lane; r < BM; r += 32) {
+        const int64_t gr = qt * BM + r;
+        if (gr >= nq) continue;
+        float v = __ldg(out_dist + gr * k + (k - 1));
+        if (dist_is_sqrt) v = v * v;
+        bad |= !(fmaf(v, 1.001f, margin) <= used);  // NaN / inf count as uncertified
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) redo_map[atomicAdd(redo_count, 1)] = (int)qt;
 }
 
 // ------------------------------------------------------------------ host side
@@ -883,7 +960,7 @@ namespace tc {
 struct PruneLayout {
     int64_t n_tiles, ld_t, n_super, ld_s, n_qtiles;
     int cap;
-    size_t box_t, sbox_t, qbox, tau, count, list, dist, total;
+    size_t box_t, sbox_t, qbox, tau, count, list, dist, bound, redo, total;
 };
 static PruneLayout prune_layout(int64_t nq, int64_t ndb, int d, int k) {
     PruneLayout L;
@@ -900,7 +977,9 @@ static PruneLayout prune_layout(int64_t nq, int64_t ndb, int d, int k) {
     L.count = align_up((size_t)L.n_qtiles * 4, 256);
     L.list = align_up((size_t)L.n_qtiles * L.cap * 4, 256);
     L.dist = align_up((size_t)nq * k * 4, 256);  // distances for the sigma/rho kernel when the caller wants none
-    L.total = 256 + 2 * L.box_t + 2 * L.sbox_t + 2 * L.qbox + L.tau + L.count + L.list + L.dist;
+    L.bound = align_up((size_t)L.n_qtiles * 4, 256);       // robust mode: bound every query tile was swept with
+    L.redo = 256 + align_up((size_t)L.n_qtiles * 4, 256);  // robust mode: counter + query tiles to sweep again
+    L.total = 256 + 2 * L.box_t + 2 * L.sbox_t + 2 * L.qbox + L.tau + L.count + L.list + L.dist + L.bound + L.redo;
     return L;
 }
 }  // namespace tc
@@ -1018,7 +1097,8 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
     prm.stages = stages;
     const size_t smem = fixed + (size_t)stages * stage_bytes;
     // per call: the attribute belongs to the current device's context (a process may drive several GPUs)
-    TDR_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TDR_CUDA(cudaFuncSetAttribute(knn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TDR_CUDA(cudaFuncSetAttribute(knn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const unsigned grid = (unsigned)((nq + BM - 1) / BM);
     const unsigned threads = prm.dual ? 384 : 256;
 
@@ -1052,6 +1132,12 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
         int* list = (int*)w;
         w += L.list;
         float* dist_scratch = (float*)w;
+        w += L.dist;
+        float* bound_used = (float*)w;
+        w += L.bound;
+        int* redo_count = (int*)w;
+        int* redo_map = (int*)(w + 256);
+        const int robust = g_prune == 2 ? 1 : 0;
         TDR_CUDA(cudaMemsetAsync(maxnorm, 0, 4, st));
         tile_box_kernel<<<(unsigned)L.ld_t, 128, 0, st>>>(Xdb, 0, ndb, d, dlo_t, dhi_t, L.ld_t);
         super_box_kernel<<<(unsigned)(((int64_t)d * L.ld_s * 32 + 255) / 256), 256, 0, st>>>(dlo_t, dhi_t, L.ld_t, L.n_super,
@@ -1064,28 +1150,53 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
         pa.fused = 0;
         pa.out_dist = nullptr;
         pa.out_idx = nullptr;
-        knn_tc_kernel<<<grid, threads, smem, st>>>(mq_hi, mq_lo, mdb_hi, mdb_lo, pa);
-        tile_prune_kernel<<<(unsigned)((L.n_qtiles + 7) / 8), 256, 0, st>>>(qlo, qhi, dlo_t, dhi_t, slo_t, shi_t, L.n_qtiles,
-                                                                           L.n_tiles, L.ld_t, L.n_super, L.ld_s, d, tau, nq,
-                                                                           maxnorm, list, count, L.cap);
+        knn_tc_kernel<false><<<grid, threads, smem, st>>>(mq_hi, mq_lo, mdb_hi, mdb_lo, pa);
+        const unsigned pgrid = (unsigned)((L.n_qtiles + 7) / 8);
+        tile_prune_kernel<<<pgrid, 256, 0, st>>>(qlo, qhi, dlo_t, dhi_t, slo_t, shi_t, L.n_qtiles, L.n_tiles, L.ld_t,
+                                                 L.n_super, L.ld_s, d, tau, nq, maxnorm, list, count, L.cap, 1, 0, robust,
+                                                 robust ? bound_used : nullptr, nullptr, nullptr);
         TDR_LAUNCH_CHECK();
         prm.tau_seed = tau;
         prm.tile_list = list;
         prm.tile_count = count;
         prm.list_cap = L.cap;
         prm.sweep_stats = g_sweep_stats;
+        if (robust) {
+            // EXPERIMENTAL (tdr_knn_set_prune(2, ..)): thresholds that ignore outlier rows, then
+            // certify every row against the bound its tile was swept with and sweep the uncertified tiles again with
+            // the (by then tight) k-th distances found.  Device-side queue, no host synchronisation.
+            const int fused_req = prm.fused;
+            prm.fused = 0;
+            if (!prm.out_dist) prm.out_dist = dist_scratch;
+            knn_tc_kernel<false><<<grid, threads, smem, st>>>(mq_hi, mq_lo, mdb_hi, mdb_lo, prm);
+            TDR_CUDA(cudaMemsetAsync(redo_count, 0, 4, st));
+            const int is_sqrt = metric == TDR_METRIC_EUCLIDEAN ? 1 : 0;
+            knn_certify_kernel<<<pgrid, 256, 0, st>>>(prm.out_dist, k, is_sqrt, nq, L.n_qtiles, bound_used, maxnorm, count,
+                                                      L.cap, redo_map, redo_count);
+            tile_prune_kernel<<<pgrid, 256, 0, st>>>(qlo, qhi, dlo_t, dhi_t, slo_t, shi_t, L.n_qtiles, L.n_tiles, L.ld_t,
+                                                     L.n_super, L.ld_s, d, prm.out_dist + (k - 1), nq, maxnorm, list, count,
+                                                     L.cap, k, is_sqrt, 0, nullptr, redo_map, redo_count);
+            Params pr = prm;
+            pr.qtile_map = redo_map;
+            pr.qtile_count = redo_count;
+            pr.tau_seed = nullptr;
+            knn_tc_kernel<true><<<grid, threads, smem, st>>>(mq_hi, mq_lo, mdb_hi, mdb_lo, pr);
+            TDR_LAUNCH_CHECK();
+            if (fused_req) return tdr_umap_affinity_f32(prm.out_dist, nq, k, max_iter, P, rho, sigma, (tdr_stream_t)st);
+            return TDR_OK;
+        }
         if (prm.fused) {
             // With a handful of tiles per CTA the in-kernel sigma/rho search (12 warps per SM walking dependent
             // bisection chains) would take longer than the sweep itself: 8.4 ms of 18.8 ms at 1 M x 128, against
             // 3.5 ms for the standalone row kernel at full occupancy.  Same arithmetic, bit-identical rows.
             prm.fused = 0;
             if (!prm.out_dist) prm.out_dist = dist_scratch;
-            knn_tc_kernel<<<grid, threads, smem, st>>>(mq_hi, mq_lo, mdb_hi, mdb_lo, prm);
+            knn_tc_kernel<false><<<grid, threads, smem, st>>>(mq_hi, mq_lo, mdb_hi, mdb_lo, prm);
             TDR_LAUNCH_CHECK();
             return tdr_umap_affinity_f32(prm.out_dist, nq, k, max_iter, P, rho, sigma, (tdr_stream_t)st);
         }
     }
-    knn_tc_kernel<<<grid, threads, smem, st>>>(mq_hi, mq_lo, mdb_hi, mdb_lo, prm);
+    knn_tc_kernel<false><<<grid, threads, smem, st>>>(mq_hi, mq_lo, mdb_hi, mdb_lo, prm);
     TDR_LAUNCH_CHECK();
     return TDR_OK;
 }

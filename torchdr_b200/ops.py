@@ -42,7 +42,7 @@ def knn_set_prune(on=True, stats=None):
     CUDA tensor that accumulates (tiles swept, tiles of a full sweep); keep it alive while it is registered."""
     if stats is not None:
         assert stats.is_cuda and stats.dtype == torch.int64 and stats.numel() >= 2 and stats.is_contiguous()
-    check(_lib.load().tdr_knn_set_prune(int(bool(on)), ptr(stats)), "tdr_knn_set_prune")
+    check(_lib.load().tdr_knn_set_prune(int(on), ptr(stats)), "tdr_knn_set_prune")  # True -> 1; 2 = experimental robust mode
 
 
 def knn_umap_fused(Xq, Xdb, k, q_row0=0, exclude_self=True, max_iter=100, want_dist=True):
