@@ -1,0 +1,91 @@
+"""Test infrastructure: a CPU stand-in for ``torchdr_b200.ops`` built on the oracle.
+
+It lets the HOST code of the package (estimators, affinities, the optimisation-loop bookkeeping) run in the CPU
+suite, so that its orchestration can be held against the reference's golden runs without a GPU.  It is never
+importable from the product (tests/test_layout.py) and implements only what UMAP needs.
+"""
+
+import numpy as np
+import torch
+
+import oracle
+
+
+def install(monkeypatch):
+    """Point the package at the CPU stand-ins (and let CPU tensors through the device checks)."""
+    from torchdr_b200 import _lib, affinity, distance, neighbor_embedding, ops
+
+    def to_cpu_tensor(X, device="auto"):
+        return torch.from_numpy(X) if isinstance(X, np.ndarray) else X
+
+    for mod in (distance, affinity, neighbor_embedding):
+        monkeypatch.setattr(mod, "_to_device_tensor", to_cpu_tensor)
+    monkeypatch.setattr(_lib, "require_device", lambda device: (0, 10, 0))
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    for name, fn in (("knn_umap_fused", knn_umap_fused), ("symmetrize_csr", symmetrize_csr), ("max_value", max_value),
+                     ("umap_schedule", umap_schedule), ("umap_compact", umap_compact), ("umap_step", umap_step),
+                     ("umap_run", umap_run)):
+        monkeypatch.setattr(ops, name, fn)
+
+
+def knn_umap_fused(Xq, Xdb, k, q_row0=0, exclude_self=True, max_iter=100, want_dist=True):
+    assert Xq.shape[0] == Xdb.shape[0] and q_row0 == 0 and exclude_self
+    C, I = oracle.knn_dense(Xdb, k)
+    P, rho, sigma = oracle.umap_affinity_rows(C, k, max_iter=max_iter)
+    return C, I, P, rho, sigma
+
+
+def symmetrize_csr(Pm, idx, row0, n_total, ext=None, transpose_local=True):
+    assert ext is None and row0 == 0
+    V, J = oracle.symmetrize_ell(Pm, idx)
+    return oracle.ell_to_csr(V, J)
+
+
+def max_value(val):
+    return val.max().reshape(1)
+
+
+def umap_schedule(val, a_max, max_iter):
+    per, nxt = oracle.umap_edge_schedule(val.unsqueeze(0), max_iter)  # elementwise: the layout does not matter
+    return per.squeeze(0), nxt.squeeze(0)
+
+
+def umap_compact(rowptr, col, eps):
+    live = torch.isfinite(eps)
+    n = rowptr.numel() - 1
+    row = torch.repeat_interleave(torch.arange(n), rowptr[1:] - rowptr[:-1])
+    cnt = torch.zeros(n, dtype=torch.long).index_add_(0, row[live], torch.ones(int(live.sum()), dtype=torch.long))
+    rp = torch.zeros(n + 1, dtype=torch.long)
+    rp[1:] = cnt.cumsum(0)
+    return rp, col[live].contiguous(), eps[live].contiguous(), eps[live].clone()
+
+
+def _ell(rowptr, col, eps, eons):
+    V, J = oracle.csr_to_ell(rowptr, col, eps, pad_val=float("inf"))
+    N, _ = oracle.csr_to_ell(rowptr, col, eons, pad_val=float("inf"))
+    return J, V, N
+
+
+def umap_step(Z_in, Z_out, row0, n_local, rowptr, col, eps, eons, n_iter, a, b, lr, neg=None, n_neg=75, rate=5,
+              seed=0, lam=1.0, repulsion=1.0, precise=False, grad_out=None, gnorm_sq=None, nan_flag=None, stats=None):
+    assert neg is not None and row0 == 0 and n_local == Z_in.shape[0], "the stand-in needs injected negatives"
+    J, per, nxt = _ell(rowptr, col, eps, eons)
+    G = oracle.umap_step(Z_in, J, per, nxt, neg, n_iter, a, b, negative_sample_rate=rate, lam=lam, repulsion=repulsion)
+    # write the advanced edge state back into the CSR array (row-major ELL order == CSR order)
+    eons.copy_(nxt[J >= 0])
+    Z_out.copy_(Z_in.add(G, alpha=-float(lr)))
+    if gnorm_sq is not None:
+        gnorm_sq += float((G.double() ** 2).sum())
+
+
+def umap_run(Z_a, Z_b, rowptr, col, eps, eons, n_iter0, lrs, a, b, n_neg=75, rate=5, seed=0, lam=1.0, repulsion=1.0,
+             precise=False, gnorm_sq=None, nan_flag=None, stats=None):
+    g = torch.Generator().manual_seed(int(seed) * 7919 + int(n_iter0))
+    src, dst = Z_a, Z_b
+    n = Z_a.shape[0]
+    for t, lr in enumerate(lrs):
+        neg = oracle.adjust_negatives(torch.randint(0, n - 1, (n, n_neg), generator=g), torch.arange(n))
+        umap_step(src, dst, 0, n, rowptr, col, eps, eons, n_iter0 + t, a, b, lr, neg=neg, n_neg=n_neg, rate=rate,
+                  lam=lam, repulsion=repulsion, gnorm_sq=gnorm_sq if t == len(lrs) - 1 else None)
+        src, dst = dst, src
+    return src

@@ -337,3 +337,45 @@ def test_momentum_loop_bookkeeping_matches_reference_sequences(monkeypatch):
     assert set(mu) == {0.5} and [i for i, f in enumerate(first) if f] == [0, 11]
     mu, first = run(ne.SNE, "sne_n300_d16_p10", max_iter=20)
     assert set(mu) == {0.8} and first == [True] + [False] * 19
+
+
+def test_umap_estimator_host_flow_reproduces_reference_run_on_cpu(monkeypatch):
+    """The public estimator with the native calls replaced by oracle-backed stand-ins (tests/fake_ops.py): what is
+    left under test is the HOST code — fit_transform, UMAPAffinity, the edge schedule hand-over, the per-step hook
+    path and the batched path, the LinearLR bookkeeping.  Driven like the reference's golden run (same init, same
+    negatives through the hook) it must land on the reference's embedding bit for bit."""
+    import fake_ops
+    from helpers import negative_table
+
+    import torchdr_b200 as tb
+
+    fake_ops.install(monkeypatch)
+    g = golden("umap_n300_d16_k15")
+    seed = int(g["seed"])
+    snaps = {}
+
+    class Injected(tb.UMAP):
+        def on_training_step_start(self):
+            self.neg_indices_ = negative_table(seed, int(self.n_iter_), 300, 75)
+
+        def on_training_step_end(self):
+            if int(self.n_iter_) + 1 in (1, 2, 5, 20):
+                snaps[int(self.n_iter_) + 1] = self.embedding_.clone()
+
+    m = Injected(n_neighbors=15, max_iter=int(g["max_iter"]), init=t(g["Zinit"]), random_state=0,
+                 process_duplicates=False, min_grad_norm=0.0, check_interval=20)
+    # stop after the 20th step without touching max_iter (it sets the schedule and the edge threshold)
+    m._converged = lambda step, gn: step >= 20
+    Z = m.fit_transform(t(g["X"]).numpy())
+    assert isinstance(Z, np.ndarray) and Z.shape == (300, 2)
+    for T in (1, 2, 5, 20):
+        assert torch.equal(snaps[T], t(g[f"Z_{T}"])), T
+    # batched path (no hooks): in-kernel negatives are the stand-in's own draws, so only the bookkeeping is checked —
+    # finite result, iteration count, early stop at the first check
+    m2 = tb.UMAP(n_neighbors=15, max_iter=60, init="normal", random_state=0, process_duplicates=False, check_interval=25)
+    Z2 = m2.fit_transform(t(g["X"]))
+    assert Z2.shape == (300, 2) and bool(torch.isfinite(Z2).all()) and int(m2.n_iter_) == 59
+    m3 = tb.UMAP(n_neighbors=15, max_iter=60, init="normal", random_state=0, process_duplicates=False,
+                 check_interval=25, min_grad_norm=1e9)
+    m3.fit_transform(t(g["X"]))
+    assert int(m3.n_iter_) == 0
