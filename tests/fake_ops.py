@@ -89,3 +89,73 @@ def umap_run(Z_a, Z_b, rowptr, col, eps, eons, n_iter0, lrs, a, b, n_neg=75, rat
                   lam=lam, repulsion=repulsion, gnorm_sq=gnorm_sq if t == len(lrs) - 1 else None)
         src, dst = dst, src
     return src
+
+
+# ---- entropic-affinity estimators (LargeVis, TSNE): gradients by autograd of the oracle's losses, as in the reference
+def knn(Xq, Xdb, k, q_row0=0, exclude_self=True, metric="sqeuclidean"):
+    assert Xq.shape[0] == Xdb.shape[0] and q_row0 == 0
+    return oracle.knn_dense(Xdb, k, metric, exclude_self)
+
+
+def entropic_affinity_rows(C, target_entropy, log_n_total, bounds=None, max_iter=100):
+    perp = int(round(float(np.exp(target_entropy - 1))))
+    n_total = int(round(float(np.exp(log_n_total))))
+    return oracle.entropic_affinity_rows(C, perp, n_total=n_total, max_iter=max_iter, use_bounds=bounds is not None)
+
+
+def largevis_grad(Z, row0, n_local, Pm, idx, grad, n_iter, neg=None, n_neg=5, seed=0, lam=1.0, repulsion=1.0):
+    assert neg is not None and row0 == 0 and n_local == Z.shape[0]
+    from oracle.largevis import largevis_loss
+
+    Zp = Z.detach().clone().requires_grad_(True)
+    largevis_loss(Zp, Pm, idx, neg, torch.arange(n_local), Z.shape[0], lam, repulsion).backward()
+    grad += Zp.grad
+
+
+def tsne_workspace(n_local, device):
+    return torch.zeros(8, dtype=torch.uint8)
+
+
+def tsne_grad(Z, row0, n_local, Pm, idx, lam, phase, grad, ws):
+    if phase == 0:
+        return
+    from oracle.tsne import tsne_loss
+
+    Zp = Z.detach().clone().requires_grad_(True)
+    tsne_loss(Zp, Pm, idx, torch.arange(n_local), lam).backward()
+    grad += Zp.grad
+
+
+def sgd_momentum(Z, buf, grad, lr, momentum, first, gnorm_sq=None, nan_flag=None):
+    # torch.optim.SGD: buf = grad (first use) | momentum * buf + grad ; param -= lr * buf
+    if first:
+        buf.copy_(grad)
+    else:
+        buf.mul_(momentum).add_(grad)
+    Z.add_(buf, alpha=-lr)
+    if gnorm_sq is not None:
+        gnorm_sq += float((grad.double() ** 2).sum())
+
+
+def infotsne_grad(Z, row0, n_local, Pm, idx, grad, n_iter, neg=None, n_neg=300, seed=0, lam=1.0, repulsion=1.0):
+    assert neg is not None and row0 == 0 and n_local == Z.shape[0]
+    Zp = Z.detach().clone().requires_grad_(True)
+    oracle.infotsne_loss(Zp, Pm, idx, neg, torch.arange(n_local), Z.shape[0], lam, repulsion).backward()
+    grad += Zp.grad
+
+
+def sne_grad(Z, row0, n_local, Pm, idx, lam, repulsion, phase, grad, row_sums):
+    if phase == 0:
+        return
+    Zp = Z.detach().clone().requires_grad_(True)
+    oracle.sne_loss(Zp, Pm, idx, torch.arange(n_local), lam, repulsion).backward()
+    grad += Zp.grad
+
+
+def install_entropic(monkeypatch):
+    from torchdr_b200 import ops
+
+    for name, fn in (("knn", knn), ("entropic_affinity_rows", entropic_affinity_rows), ("largevis_grad", largevis_grad),
+                     ("tsne_workspace", tsne_workspace), ("tsne_grad", tsne_grad), ("infotsne_grad", infotsne_grad),
+                     ("sne_grad", sne_grad), ("sgd_momentum", sgd_momentum)):
+        monkeypatch.setattr(ops, name, fn)

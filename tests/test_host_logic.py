@@ -379,3 +379,50 @@ def test_umap_estimator_host_flow_reproduces_reference_run_on_cpu(monkeypatch):
                  check_interval=25, min_grad_norm=1e9)
     m3.fit_transform(t(g["X"]))
     assert int(m3.n_iter_) == 0
+
+
+def test_momentum_estimators_host_flow_reproduce_reference_runs_on_cpu(monkeypatch):
+    """Same arrangement for the autograd-mode estimators: public API + host loop (early exaggeration switch, optimiser
+    rebuild, LinearLR, momentum buffer) on oracle-backed stand-ins must reproduce the reference's LargeVis, t-SNE,
+    InfoTSNE and SNE runs captured in tests/golden bit for bit (same init; negatives injected through the hook)."""
+    import fake_ops
+    from helpers import negative_table
+
+    import torchdr_b200 as tb
+
+    fake_ops.install(monkeypatch)
+    fake_ops.install_entropic(monkeypatch)
+
+    def snapshots(cls, g, steps, **kw):
+        snaps = {}
+        n_neg = int(g["n_neg"]) if "n_neg" in g else 5
+
+        class Captured(cls):
+            def on_training_step_start(self):
+                if "seed" in g:
+                    self.neg_indices_ = negative_table(int(g["seed"]), int(self.n_iter_), 300, n_neg)
+
+            def on_training_step_end(self):
+                if int(self.n_iter_) + 1 in steps:
+                    snaps[int(self.n_iter_) + 1] = self.embedding_.clone()
+
+        m = Captured(perplexity=10, init=t(g["Zinit"]), random_state=0, process_duplicates=False, min_grad_norm=0.0, **kw)
+        m.fit_transform(t(g["X"]))
+        return snaps
+
+    g = golden("largevis_n300_d16_p10")
+    snaps = snapshots(tb.LargeVis, g, (1, 2, 5, 10, 30), max_iter=30)
+    for T in (1, 2, 5, 10, 30):
+        assert torch.equal(snaps[T], t(g[f"Z_{T}"])), ("largevis", T)
+    g = golden("tsne_n300_d16_p10")
+    snaps = snapshots(tb.TSNE, g, (1, 2, 5, 10, 11, 12, 20), max_iter=20, early_exaggeration_iter=10)
+    for T in (1, 2, 5, 10, 11, 12, 20):
+        assert torch.equal(snaps[T], t(g[f"Z_{T}"])), ("tsne", T)
+    g = golden("infotsne_n300_d16_p10")
+    snaps = snapshots(tb.InfoTSNE, g, (1, 2, 5, 10, 11, 12, 20), max_iter=20, early_exaggeration_iter=10, n_negatives=50)
+    for T in (1, 2, 5, 10, 11, 12, 20):
+        assert torch.equal(snaps[T], t(g[f"Z_{T}"])), ("infotsne", T)
+    g = golden("sne_n300_d16_p10")
+    snaps = snapshots(tb.SNE, g, (1, 2, 5, 10, 20), max_iter=20)
+    for T in (1, 2, 5, 10, 20):
+        assert torch.equal(snaps[T], t(g[f"Z_{T}"])), ("sne", T)
