@@ -37,7 +37,11 @@ struct Warp4Smem {
 // NEG_CG: gather the (uniformly random) negatives with ld.global.cg so they do not evict the neighbour
 // rows and edge streams from L1
 // L2H: L2 eviction hints (umap_step_math.cuh) — edge streams evict-first, gathered rows of Z evict-last
-template <int MIN_CTAS, int kCap4, bool NEG_CG, bool L2H = false>
+// PF: persistent grid (the host launches one wave of CTAs; every warp walks several 32-row blocks) and, while a block's
+//     attraction runs, L2 prefetch of the NEXT block's edge streams — the ncu capture of the default configuration
+//     shows 31 % long-scoreboard stalls, the largest on the compare that consumes the epoch_of_next_sample stream
+//     (profiles/r1_step_fast4_hotspots.txt).  EXPERIMENTAL (TDR_STEP_CFG=6), not yet measured.
+template <int MIN_CTAS, int kCap4, bool NEG_CG, bool L2H = false, bool PF = false>
 __global__ void __launch_bounds__(kFastThreads, MIN_CTAS) umap_step_kernel_fast4(const UmapStepParams p) {
     extern __shared__ __align__(16) unsigned char s_raw4[];
     constexpr unsigned FULL = 0xffffffffu;
@@ -68,6 +72,17 @@ __global__ void __launch_bounds__(kFastThreads, MIN_CTAS) umap_step_kernel_fast4
         const float* const eps_w = p.eps + E0;
         const int32_t* const col_w = p.col + E0;
 
+        if (PF) {
+            const int64_t rbn = rb + n_warps * 32;
+            if (rbn < p.n_local) {
+                const int64_t e0 = __ldg(p.rowptr + rbn), e1 = __ldg(p.rowptr + min(rbn + 32, p.n_local));
+                for (int64_t o = e0 + lane * 32; o < e1; o += 32 * 32) {  // one 128-byte line per lane and array
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.eons + o));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.col + o));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.eps + o));
+                }
+            }
+        }
         // ---- attraction (umap.py:236-264)
         float gx = 0.0f, gy = 0.0f;
         int active = 0, nd = 0;
