@@ -24,7 +24,7 @@ def install(monkeypatch):
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
     for name, fn in (("knn_umap_fused", knn_umap_fused), ("symmetrize_csr", symmetrize_csr), ("max_value", max_value),
                      ("umap_schedule", umap_schedule), ("umap_compact", umap_compact), ("umap_step", umap_step),
-                     ("umap_run", umap_run)):
+                     ("umap_run", umap_run), ("csr_to_ell", csr_to_ell)):
         monkeypatch.setattr(ops, name, fn)
 
 
@@ -39,6 +39,10 @@ def symmetrize_csr(Pm, idx, row0, n_total, ext=None, transpose_local=True):
     assert ext is None and row0 == 0
     V, J = oracle.symmetrize_ell(Pm, idx)
     return oracle.ell_to_csr(V, J)
+
+
+def csr_to_ell(rowptr, col, val, pad_val=0.0):
+    return oracle.csr_to_ell(rowptr, col, val, pad_val=pad_val)
 
 
 def max_value(val):

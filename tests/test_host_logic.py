@@ -426,3 +426,26 @@ def test_momentum_estimators_host_flow_reproduce_reference_runs_on_cpu(monkeypat
     snaps = snapshots(tb.SNE, g, (1, 2, 5, 10, 20), max_iter=20)
     for T in (1, 2, 5, 10, 20):
         assert torch.equal(snaps[T], t(g[f"Z_{T}"])), ("sne", T)
+
+
+def test_reordered_affinity_equals_plain_affinity_on_cpu(monkeypatch):
+    """TDR_KNN_REORDER=1 (experimental): searching in the Voronoi-tree order and mapping the rows back must give the
+    same symmetrised graph as searching in the input order (host logic on the CPU stand-ins)."""
+    import fake_ops
+
+    import torchdr_b200 as tb
+    from torchdr_b200 import ops
+
+    fake_ops.install(monkeypatch)
+    monkeypatch.setattr(ops, "knn_set_prune", lambda on=True, stats=None: None)
+    g = golden("umap_n300_d16_k15")
+    X = t(g["X"])
+    plain = tb.UMAPAffinity(n_neighbors=15, max_iter=100).compute_csr(X)
+    monkeypatch.setenv("TDR_KNN_REORDER", "1")
+    aff = tb.UMAPAffinity(n_neighbors=15, max_iter=100)
+    reordered = aff.compute_csr(X)
+    for a, b in zip(plain, reordered):
+        assert torch.equal(a, b)
+    assert torch.equal(aff.eps_, t(g["sigma"])) and torch.equal(aff.rho_, t(g["rho"]))
+    vals, idx = aff(X)
+    assert torch.equal(idx, t(g["sym_idx"]).long()) and torch.equal(vals, t(g["sym_vals"]))

@@ -156,7 +156,23 @@ class UMAPAffinity(_SparseAffinityBase):
         if timing:
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-        if self.metric == "sqeuclidean":
+        if self.metric == "sqeuclidean" and not self.is_multi_gpu and os.environ.get("TDR_KNN_REORDER") == "1":
+            # EXPERIMENTAL: create the index locality the pruned sweep needs, search in that
+            # order with the certified sweep, map the rows back.  Off by default until verified on hardware.
+            from .reorder import unpermute_knn_rows, unpermute_rows, voronoi_tree_order
+
+            perm = voronoi_tree_order(X)
+            Xp = X[perm].contiguous()
+            ops.knn_set_prune(2)
+            try:
+                dist, idx, P, rho, sigma = ops.knn_umap_fused(Xp, Xp, k, q_row0=0, exclude_self=bool(self.zero_diag),
+                                                              max_iter=self.max_iter)
+            finally:
+                ops.knn_set_prune(1)
+            idx, dist, P = unpermute_knn_rows(perm, idx, dist, P)
+            rho, sigma = unpermute_rows(perm, rho, sigma)
+            del Xp
+        elif self.metric == "sqeuclidean":
             dist, idx, P, rho, sigma = ops.knn_umap_fused(X[s:e], X, k, q_row0=s, exclude_self=bool(self.zero_diag),
                                                           max_iter=self.max_iter)
         else:  # euclidean rows go through the two-kernel route

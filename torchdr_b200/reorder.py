@@ -1,4 +1,4 @@
-"""EXPERIMENTAL (not wired into the estimators yet): spatial re-ordering for the pruned kNN sweep.
+"""EXPERIMENTAL (opt-in: ``TDR_KNN_REORDER=1`` in ``UMAPAffinity``, single GPU): spatial re-ordering for the pruned kNN sweep.
 
 The pruned sweep of ``csrc/knn_tc.cu`` skips database tiles whose bounding box is too far from the query
 tile's box, which only pays when rows that are close in space are close in index.  ``voronoi_tree_order``
@@ -11,8 +11,8 @@ callable on the re-ordered rows and maps the result back.  Design study and meas
 pruning rule itself is exact for any order.
 
 Level-synchronous and device-agnostic (plain tensor ops: sort, gather, index_add, batched dot products),
-so the host logic is unit-tested on the CPU; the per-level nearest-of-16 search is the piece that becomes a
-CUDA kernel when this is wired in.
+so the host logic is unit-tested on the CPU (``tests/test_host_logic.py``: same graph as the plain path, bit for
+bit); the per-level nearest-of-16 search is the piece that becomes a CUDA kernel once the path has been measured.
 """
 
 import torch
@@ -88,6 +88,35 @@ def voronoi_tree_order(X, branch=16, leaf=128, lloyd=1, generator=None):
     return torch.argsort(key, stable=True)
 
 
+def unpermute_knn_rows(perm, idx_p, dist_p, *aligned):
+    """Map kNN rows computed on ``X[perm]`` back: neighbour ids become original ids, equal distances within a row
+    are put in ascending original id (the tie order of every kernel of this engine), ``aligned`` tensors ([n, k],
+    entry-aligned with dist_p, e.g. the affinity values) follow their entries, and row r of the result is the row of
+    original point r.  Returns (idx, dist, *aligned) — idx in idx_p's dtype."""
+    idx_o = perm[idx_p.long()]
+    o1 = torch.argsort(idx_o, dim=1, stable=True)
+    o2 = torch.argsort(dist_p.gather(1, o1), dim=1, stable=True)
+    order = o1.gather(1, o2)
+    out = []
+    for tns in (idx_o, dist_p) + tuple(aligned):
+        rows = tns.gather(1, order)
+        back = torch.empty_like(rows)
+        back[perm] = rows
+        out.append(back)
+    out[0] = out[0].to(idx_p.dtype)
+    return tuple(out)
+
+
+def unpermute_rows(perm, *per_row):
+    """Row r of every result = the entry computed for original point r (per-row scalars such as rho, sigma)."""
+    out = []
+    for tns in per_row:
+        back = torch.empty_like(tns)
+        back[perm] = tns
+        out.append(back)
+    return tuple(out)
+
+
 def knn_in_any_order(X, k, knn_fn, perm=None, **tree_kwargs):
     """Run ``knn_fn(Xp) -> (dist[n, k], idx[n, k])`` on the re-ordered rows ``Xp = X[perm]`` and return the result in
     the original row order with original indices.  Equal distances within a row are put back in ascending original
@@ -95,13 +124,5 @@ def knn_in_any_order(X, k, knn_fn, perm=None, **tree_kwargs):
     if perm is None:
         perm = voronoi_tree_order(X, **tree_kwargs)
     dist_p, idx_p = knn_fn(X[perm].contiguous())
-    idx_o = perm[idx_p.long()]  # original ids of the neighbours
-    o1 = torch.argsort(idx_o, dim=1, stable=True)
-    dist1, idx1 = dist_p.gather(1, o1), idx_o.gather(1, o1)
-    o2 = torch.argsort(dist1, dim=1, stable=True)
-    dist2, idx2 = dist1.gather(1, o2), idx1.gather(1, o2)
-    dist = torch.empty_like(dist2)
-    idx = torch.empty_like(idx2)
-    dist[perm] = dist2
-    idx[perm] = idx2
-    return dist, idx.to(idx_p.dtype), perm
+    idx, dist = unpermute_knn_rows(perm, idx_p, dist_p)
+    return dist, idx, perm
