@@ -261,6 +261,8 @@ def gpu_arm(args):
     _lib.require_device(dev)
     n, d, K, W = args.points, args.dim, args.steps, max(args.warmup, 3)
     X = clustered(n, d, dev)
+    if args.order == "shuffled":  # same points without the generator's index locality (kNN sweeps every tile)
+        X = X[torch.randperm(n, generator=torch.Generator(device=dev).manual_seed(7), device=dev)].contiguous()
     sched = max(MAX_ITER, W + K + 16)  # schedule length: the timed iterations are the head of one LinearLR 1 -> 0 run
     full_sweep = args.full_sweep or n <= 2_000_000
     (rowptr, col, eps, eons), bounds, knn, nnz_sym = build_graph(X, rank, world, sched, full_sweep)
@@ -393,7 +395,7 @@ def gpu_arm(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"UMAP n_neighbors={K_NEIGHBORS} on {n}x{d} clustered synthetic (BASELINE configs[1])",
-                       "points": n, "dim": d, "n_negatives": N_NEG, "schedule_max_iter": sched,
+                       "points": n, "dim": d, "row_order": args.order, "n_negatives": N_NEG, "schedule_max_iter": sched,
                        "negatives": "in-kernel Philox4x32-10", "parallelism": f"rows sharded x{world}", "exchange": exchange,
                        "l2": "per-iteration working set (CSR edge state %.0f MB) exceeds the 126 MB L2; no flush" %
                              (nnz * 12 / 1e6 / world)},
@@ -413,7 +415,11 @@ def e2e_arm(args, dev):
     from torchdr_b200 import UMAP
 
     n, d = args.points, args.dim
-    Xh = clustered(n, d, dev).cpu().pin_memory().numpy()
+    Xd = clustered(n, d, dev)
+    if args.order == "shuffled":
+        Xd = Xd[torch.randperm(n, generator=torch.Generator(device=dev).manual_seed(7), device=dev)]
+    Xh = Xd.cpu().pin_memory().numpy()
+    del Xd
     torch.cuda.synchronize()
     m = UMAP(n_neighbors=K_NEIGHBORS, max_iter=E2E_ITERS, init="normal", random_state=0, process_duplicates=False)
     m.fit_transform(Xh[:20000])  # warm-up of allocator / library load
@@ -440,6 +446,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--full-sweep", action="store_true", help="also time the unpruned kNN sweep above 2 M points")
+    ap.add_argument("--order", default="generator", choices=["generator", "shuffled"],
+                    help="row order of the synthetic points: the reference generator's (clusters contiguous) or shuffled")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     # NCCL prints its version banner to STDOUT when NCCL_DEBUG=VERSION; the contract is ONE JSON line there
