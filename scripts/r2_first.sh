@@ -7,13 +7,13 @@ set -u
 O=gpurun_out; mkdir -p $O
 echo "== [1] experimental kNN tests"; TDR_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -s -k "robust" 2>&1 | tail -8
 echo "== [2] step kernel variants"
-for cfg in 0 6 5; do
+for cfg in 0 6 7 8 5; do
   TDR_STEP_CFG=$cfg timeout 200 python bench.py --steps 1000 --warmup 20 --no-e2e --no-cpu 2>/dev/null | python -c "
 import json,sys; d=json.loads(sys.stdin.read()); print('1M cfg $cfg:', round(d['value'],1), 'it/s', round(d['ms_per_step'],4), 'ms')"
   TDR_STEP_CFG=$cfg timeout 300 python bench.py --points 10000000 --steps 200 --warmup 10 --no-e2e --no-cpu 2>/dev/null | python -c "
 import json,sys; d=json.loads(sys.stdin.read()); print('10M cfg $cfg:', round(d['value'],1), 'it/s', round(d['ms_per_step'],4), 'ms', d['clocks']['sm_mhz'])"
 done
-TDR_STEP_CFG=6 timeout 200 python -m pytest tests/test_gpu_parity.py -x -q -k "umap" 2>&1 | tail -2
+for cfg in 6 7 8; do TDR_STEP_CFG=$cfg timeout 200 python -m pytest tests/test_gpu_parity.py -x -q -k "umap" 2>&1 | tail -2; done
 echo "== [3] shuffled rows"
 for re in 0 1; do
   TDR_KNN_REORDER=$re timeout 300 python bench.py --order shuffled --steps 200 --warmup 10 --no-cpu 2>$O/shuffled_$re.err | python -c "

@@ -320,14 +320,14 @@ __global__ void __launch_bounds__(kV2Threads, 4) umap_step_kernel_v2(const UmapS
 #include "umap_step_fast4.cuh"
 namespace tdr {
 
-template <int OCC, int CAP, bool NEG_CG, bool L2H = false, bool PF = false>
+template <int OCC, int CAP, bool NEG_CG, bool L2H = false, bool PF = false, bool CHEAP = false>
 static cudaError_t launch_fast4(const UmapStepParams& p, unsigned blocks, cudaStream_t st) {
     constexpr size_t smem = sizeof(Warp4Smem<CAP>) * kWarps4;
-    static const cudaError_t attr = cudaFuncSetAttribute(umap_step_kernel_fast4<OCC, CAP, NEG_CG, L2H, PF>,
+    static const cudaError_t attr = cudaFuncSetAttribute(umap_step_kernel_fast4<OCC, CAP, NEG_CG, L2H, PF, CHEAP>,
                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (attr != cudaSuccess) return attr;
     if (PF && blocks > (unsigned)(kNumSMs * OCC)) blocks = (unsigned)(kNumSMs * OCC);  // one resident wave
-    umap_step_kernel_fast4<OCC, CAP, NEG_CG, L2H, PF><<<blocks, kFastThreads, smem, st>>>(p);
+    umap_step_kernel_fast4<OCC, CAP, NEG_CG, L2H, PF, CHEAP><<<blocks, kFastThreads, smem, st>>>(p);
     return cudaSuccess;
 }
 
@@ -364,6 +364,8 @@ static int launch_step(const UmapStepParams& p, int precise, cudaStream_t st) {
             case 4: err = launch_fast4<4, 288, true>(p, g4, st); break;
             case 5: err = launch_fast4<4, 256, true, true>(p, g4, st); break;  // L2 eviction hints
             case 6: err = launch_fast4<4, 256, true, false, true>(p, g4, st); break;  // persistent + stream prefetch
+            case 7: err = launch_fast4<4, 256, true, false, false, true>(p, g4, st); break;  // Philox-7 + cheap pow
+            case 8: err = launch_fast4<4, 256, true, false, true, true>(p, g4, st); break;   // 6 + 7
             default: err = launch_fast4<4, 256, true>(p, g4, st); break;
         }
         TDR_CUDA(err);

@@ -41,7 +41,9 @@ struct Warp4Smem {
 //     attraction runs, L2 prefetch of the NEXT block's edge streams — the ncu capture of the default configuration
 //     shows 31 % long-scoreboard stalls, the largest on the compare that consumes the epoch_of_next_sample stream
 //     (profiles/r1_step_fast4_hotspots.txt).  EXPERIMENTAL (TDR_STEP_CFG=6), not yet measured.
-template <int MIN_CTAS, int kCap4, bool NEG_CG, bool L2H = false, bool PF = false>
+// CHEAP: Philox4x32-7 instead of -10 and pow_cheap instead of pow_fast (fewer issue slots per negative).  EXPERIMENTAL
+//     (TDR_STEP_CFG=7), not yet measured; changes the in-kernel negative stream, not its distribution.
+template <int MIN_CTAS, int kCap4, bool NEG_CG, bool L2H = false, bool PF = false, bool CHEAP = false>
 __global__ void __launch_bounds__(kFastThreads, MIN_CTAS) umap_step_kernel_fast4(const UmapStepParams p) {
     extern __shared__ __align__(16) unsigned char s_raw4[];
     constexpr unsigned FULL = 0xffffffffu;
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(kFastThreads, MIN_CTAS) umap_step_kernel_fast4
             auto eval_edge = [&](const EdgeIn& in, int t) {
                 const float dx = __fsub_rn(in.z.x, in.zj.x), dy = __fsub_rn(in.z.y, in.zj.y);
                 const float D = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));  // distance/base.py:384-385
-                const float pw = pow_fast(D, p.bm1);                              // D^(b-1); D^b = D * D^(b-1)
+                const float pw = CHEAP ? pow_cheap(D, p.bm1) : pow_fast(D, p.bm1);  // D^(b-1); D^b = D * D^(b-1)
                 const float den = __fadd_rn(1.0f, __fmul_rn(p.a, __fmul_rn(pw, D)));
                 float coef = __fmul_rn(__fmul_rn(pw, p.two_ab), rcp_fast(den));
                 coef = (D > 0.0f) ? coef : 0.0f;  // umap.py:243-247
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(kFastThreads, MIN_CTAS) umap_step_kernel_fast4
 #pragma unroll
                     for (int u = 0; u < 4; ++u) jn[u] = (u < nval) ? (uint32_t)__ldg(nr + u) : gj;
                 } else {
-                    const uint4 wd = rng(c0, c1, gj, (uint32_t)quad);
+                    const uint4 wd = CHEAP ? rng.rounds<7>(c0, c1, gj, (uint32_t)quad) : rng(c0, c1, gj, (uint32_t)quad);
                     jn[0] = __umulhi(wd.x, nm1); jn[1] = __umulhi(wd.y, nm1);
                     jn[2] = __umulhi(wd.z, nm1); jn[3] = __umulhi(wd.w, nm1);
 #pragma unroll
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(kFastThreads, MIN_CTAS) umap_step_kernel_fast4
                 for (int u = 0; u < 4; ++u) {
                     const float dx = __fsub_rn(in.z.x, in.zn[u].x), dy = __fsub_rn(in.z.y, in.zn[u].y);
                     const float D = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-                    const float den = __fadd_rn(1.0f, __fmul_rn(p.a, pow_fast(D, p.b)));  // umap.py:273
+                    const float den = __fadd_rn(1.0f, __fmul_rn(p.a, CHEAP ? pow_cheap(D, p.b) : pow_fast(D, p.b)));  // umap.py:273
                     const float coef = __fmul_rn(rcp_fast(__fmul_rn(__fadd_rn(D, 1e-3f), den)), p.neg_two_b);  // :274-276
                     sx = fmaf(dx, coef, sx);
                     sy = fmaf(dy, coef, sy);

@@ -74,6 +74,16 @@ __device__ __forceinline__ int ldg_s32_hint(const int* a, uint64_t pol) {
     return v;
 }
 
+// x^y = 2^(y log2 x) without the hi + lo product: 3 instructions; the rounding of y * log2 x (|.| up to ~30 for the
+// distances of the first iterations) costs ~1e-6 relative instead of ~4e-7.  x = 0 gives 0 for y > 0 and +inf for
+// y < 0 — the callers multiply by D or add 1e-3 / 1, as with pow_fast.  EXPERIMENTAL (TDR_STEP_CFG=7).
+__device__ __forceinline__ float pow_cheap(float x, float y) {
+    float lg, r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y * fmaxf(lg, -100.0f)));
+    return r;
+}
+
 __device__ __forceinline__ float rcp_fast(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
