@@ -449,3 +449,30 @@ def test_reordered_affinity_equals_plain_affinity_on_cpu(monkeypatch):
     assert torch.equal(aff.eps_, t(g["sigma"])) and torch.equal(aff.rho_, t(g["rho"]))
     vals, idx = aff(X)
     assert torch.equal(idx, t(g["sym_idx"]).long()) and torch.equal(vals, t(g["sym_vals"]))
+
+
+def test_baseline_config_1_host_flow_on_cpu(monkeypatch):
+    """BASELINE.json configs[0] through the public estimator on the CPU stand-ins: TSNE(perplexity=30) on the
+    reference's 2000 x 50 blobs run.  Tolerances as in tests/test_oracle_golden.py (the reference's own backward is not
+    bit-reproducible at this size)."""
+    import fake_ops
+    from helpers import rel_fro
+
+    import torchdr_b200 as tb
+
+    fake_ops.install(monkeypatch)
+    fake_ops.install_entropic(monkeypatch)
+    g = golden("tsne_c1_n2000_d50_p30")
+    snaps = {}
+
+    class Captured(tb.TSNE):
+        def on_training_step_end(self):
+            if int(self.n_iter_) + 1 in (1, 5, 20):
+                snaps[int(self.n_iter_) + 1] = self.embedding_.clone()
+
+    m = Captured(perplexity=30, max_iter=20, init=t(g["Zinit"]), random_state=0, process_duplicates=False,
+                 min_grad_norm=0.0)
+    Z = m.fit_transform(g["X"])
+    assert isinstance(Z, np.ndarray) and Z.shape == (2000, 2)
+    for T, tol in ((1, 2e-6), (5, 5e-6), (20, 2e-5)):
+        assert rel_fro(snaps[T], g[f"Z_{T}"]) < tol, T

@@ -212,3 +212,27 @@ def test_partition():
             if e > s:
                 assert oracle.owner_of(s, n, w) == r and oracle.owner_of(e - 1, n, w) == r
         assert prev == n
+
+
+def test_baseline_config_1_tsne_2000x50_cpu_run():
+    """BASELINE.json configs[0]: TSNE(perplexity=30, backend=None, device="cpu") on make_blobs(2000, 50).  The oracle
+    starts from X alone (kNN k = 90 -> entropic affinity with the Vladymyrov bracket -> 50 early-exaggerated momentum
+    steps; fixture: tests/golden/make_golden_c1.py).  Neighbours, affinities and the rescaled initialisation are
+    bit-identical.  The loop is not bit-reproducible at this size even for the reference itself: above ATen's
+    parallel grain size the backward of the gathers accumulates with CPU atomics, so two runs of the same code differ
+    (measured: oracle vs fixture 2e-7 at T = 1, 1.5e-6 at T = 10, 1.2e-5 at T = 50, varying from run to run; at
+    N = 300, below the grain size, every fixture is matched with torch.equal)."""
+    g = golden("tsne_c1_n2000_d50_p30")
+    X = t(g["X"])
+    C, I = oracle.knn_dense(X, 90)
+    assert torch.equal(I[:8], t(g["I_head"]))
+    logP, eps, _ = oracle.entropic_affinity_rows(C, 30)
+    P = logP.exp()
+    assert torch.equal(P[:8], t(g["P_head"]))
+    Z0 = 1e-4 * t(g["Zinit"]) / t(g["Zinit"])[:, 0].std()  # affinity_matcher.py:522-525
+    assert torch.equal(Z0, t(g["Z0"]))
+    np.testing.assert_array_equal(g["lr"], np.full(50, 50.0))  # max(2000 / 12 / 4, 50)
+    from oracle.tsne import tsne_run
+
+    for T, tol in ((1, 2e-6), (2, 2e-6), (5, 5e-6), (10, 1e-5), (20, 2e-5), (50, 1e-4)):
+        assert rel_fro(tsne_run(Z0, P, I, T), g[f"Z_{T}"]) < tol, T
