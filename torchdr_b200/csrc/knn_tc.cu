@@ -237,14 +237,16 @@ struct Params {
     float* kth_out;          // phase A: only a bound on the k-th distance of every row is written (squared domain)
     const float* tau_seed;   // phase B: that bound; the row's threshold starts there instead of at +inf
     unsigned long long* sweep_stats;  // optional: [0] += tiles swept, [1] += tiles of a full sweep
-    // re-sweep of selected query tiles (robust mode): CTA b works on query tile qtile_map[b]; CTAs >= *qtile_count exit
-    const int* qtile_map;
-    const int* qtile_count;
     float* out_dist;
     int32_t* out_idx;
     float* P;
     float* rho;
     float* sigma;
+    // re-sweep of selected query tiles (robust mode, knn_tc_kernel<true> only): CTA b works on query tile
+    // qtile_map[b]; CTAs >= *qtile_count exit.  Kept at the end so that the default kernel's argument layout is
+    // the one that was verified on hardware.
+    const int* qtile_map;
+    const int* qtile_count;
 };
 
 // REDO: the robust mode's second sweep (CTA -> query tile through prm.qtile_map); a separate instantiation so that
@@ -268,12 +270,13 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 5);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int64_t qtile = blockIdx.x;
+    int qtile_redo = 0;
     if (REDO) {  // uniform over the CTA, before any barrier or allocation
         if ((int)blockIdx.x >= __ldg(prm.qtile_count)) return;
-        qtile = __ldg(prm.qtile_map + blockIdx.x);
+        qtile_redo = __ldg(prm.qtile_map + blockIdx.x);
     }
-    const int64_t q0 = qtile * BM;
+#define TDR_QTILE (REDO ? (unsigned)qtile_redo : blockIdx.x)
+    const int64_t q0 = (int64_t)TDR_QTILE * BM;
     const int64_t n_tiles = (prm.ndb + BN - 1) / BN;
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
@@ -286,12 +289,13 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
         t_first = max((int64_t)0, r0 / BN - prm.win);
         n_sweep = min(n_tiles, (r0 + BM - 1) / BN + prm.win + 1) - t_first;
     } else if (prm.tile_count) {
-        const int c = __ldg(prm.tile_count + qtile);
+        const int c = __ldg(prm.tile_count + TDR_QTILE);
         if (c <= prm.list_cap) {
-            my_list = prm.tile_list + qtile * prm.list_cap;
+            my_list = prm.tile_list + (int64_t)TDR_QTILE * prm.list_cap;
             n_sweep = c;
         }
     }
+#undef TDR_QTILE
     auto tile_of = [&](int64_t t) -> int64_t { return my_list ? (int64_t)__ldg(my_list + t) : t_first + t; };
     if (prm.sweep_stats && tid == 0 && prm.win == 0) {
         atomicAdd(prm.sweep_stats + 0, (unsigned long long)n_sweep);
@@ -766,6 +770,9 @@ __global__ void __launch_bounds__(256) super_box_kernel(const float* __restrict_
 // against the query box, then the member tiles of every surviving super-tile (lanes = its 32 tiles).  16
 // dimensions at a time with a warp-uniform early exit (a far box is settled by its first few dimensions).
 // Survivors are appended in ascending tile order.
+// EXT: the robust mode's extras (strided / square-rooted bounds, outlier rejection, bound output, query-tile queue);
+// EXT = false is the default path exactly as it was verified on hardware.
+template <bool EXT>
 __global__ void __launch_bounds__(256)
 tile_prune_kernel(const float* __restrict__ qlo, const float* __restrict__ qhi, const float* __restrict__ dlo_t,
                   const float* __restrict__ dhi_t, const float* __restrict__ slo_t, const float* __restrict__ shi_t,
@@ -776,11 +783,11 @@ tile_prune_kernel(const float* __restrict__ qlo, const float* __restrict__ qhi, 
                   int tau_stride, int tau_is_sqrt, int robust, float* __restrict__ bound_out,
                   const int* __restrict__ qtile_map, const int* __restrict__ qtile_count) {
     __shared__ float s_box[8][2][MAX_ATOMS * KATOM];
-    __shared__ float s_tau[8][BM];
+    __shared__ float s_tau[EXT ? 8 : 1][EXT ? BM : 1];
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int64_t qt = (int64_t)blockIdx.x * 8 + warp;
-    if (qtile_map) {
+    if (EXT && qtile_map) {
         if (qt >= (int64_t)__ldg(qtile_count)) return;  // whole warp
         qt = __ldg(qtile_map + qt);
     }
@@ -789,21 +796,28 @@ tile_prune_kernel(const float* __restrict__ qlo, const float* __restrict__ qhi, 
         s_box[warp][0][j] = __ldg(qlo + qt * d + j);
         s_box[warp][1][j] = __ldg(qhi + qt * d + j);
     }
-    const int64_t stride = tau_stride > 0 ? tau_stride : 1;
     float tm = 0.0f;
-    for (int r = lane; r < BM; r += 32) {
-        const int64_t gr = qt * BM + r;
-        float v = -1.0f;  // rows beyond nq never decide anything
-        if (gr < nq) {
-            v = __ldg(tau + gr * stride);
-            if (tau_is_sqrt) v = v * v;
-            tm = fmaxf(tm, v);
+    if (!EXT) {
+        for (int r = lane; r < BM; r += 32) {
+            const int64_t gr = qt * BM + r;
+            if (gr < nq) tm = fmaxf(tm, __ldg(tau + gr));
         }
-        s_tau[warp][r] = v;
+    } else {
+        const int64_t stride = tau_stride > 0 ? tau_stride : 1;
+        for (int r = lane; r < BM; r += 32) {
+            const int64_t gr = qt * BM + r;
+            float v = -1.0f;  // rows beyond nq never decide anything
+            if (gr < nq) {
+                v = __ldg(tau + gr * stride);
+                if (tau_is_sqrt) v = v * v;
+                tm = fmaxf(tm, v);
+            }
+            s_tau[warp][r] = v;
+        }
     }
     tm = warp_max(tm);
-    __syncwarp();
-    if (robust) {
+    if (EXT) __syncwarp();
+    if (EXT && robust) {
         // Outlier rejection: a row whose bound is far above the tile's median (its neighbours are not inside the
         // phase-A window) must not decide what the other 127 rows sweep.  tm = largest bound <= 4 x the median; rows
         // above it are caught by knn_certify_kernel after the sweep and their tile is swept again.
@@ -829,7 +843,7 @@ tile_prune_kernel(const float* __restrict__ qlo, const float* __restrict__ qhi, 
     }
     // margin: 1e-3 relative + 5 x the documented fp32 gap of the kernel's distances on the scale of the norms
     const float bound = fmaf(tm, 1.001f, 2e-5f * 2.0f * __int_as_float(__ldg(maxnorm_bits)));
-    if (bound_out && lane == 0) bound_out[qt] = bound;
+    if (EXT && bound_out && lane == 0) bound_out[qt] = bound;
     __syncwarp();
     const float* lo_a = s_box[warp][0];
     const float* hi_a = s_box[warp][1];
@@ -1152,9 +1166,14 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
         pa.out_idx = nullptr;
         knn_tc_kernel<false><<<grid, threads, smem, st>>>(mq_hi, mq_lo, mdb_hi, mdb_lo, pa);
         const unsigned pgrid = (unsigned)((L.n_qtiles + 7) / 8);
-        tile_prune_kernel<<<pgrid, 256, 0, st>>>(qlo, qhi, dlo_t, dhi_t, slo_t, shi_t, L.n_qtiles, L.n_tiles, L.ld_t,
-                                                 L.n_super, L.ld_s, d, tau, nq, maxnorm, list, count, L.cap, 1, 0, robust,
-                                                 robust ? bound_used : nullptr, nullptr, nullptr);
+        if (robust)
+            tile_prune_kernel<true><<<pgrid, 256, 0, st>>>(qlo, qhi, dlo_t, dhi_t, slo_t, shi_t, L.n_qtiles, L.n_tiles, L.ld_t,
+                                                           L.n_super, L.ld_s, d, tau, nq, maxnorm, list, count, L.cap, 1, 0, 1,
+                                                           bound_used, nullptr, nullptr);
+        else
+            tile_prune_kernel<false><<<pgrid, 256, 0, st>>>(qlo, qhi, dlo_t, dhi_t, slo_t, shi_t, L.n_qtiles, L.n_tiles,
+                                                            L.ld_t, L.n_super, L.ld_s, d, tau, nq, maxnorm, list, count, L.cap,
+                                                            1, 0, 0, nullptr, nullptr, nullptr);
         TDR_LAUNCH_CHECK();
         prm.tau_seed = tau;
         prm.tile_list = list;
@@ -1173,9 +1192,9 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
             const int is_sqrt = metric == TDR_METRIC_EUCLIDEAN ? 1 : 0;
             knn_certify_kernel<<<pgrid, 256, 0, st>>>(prm.out_dist, k, is_sqrt, nq, L.n_qtiles, bound_used, maxnorm, count,
                                                       L.cap, redo_map, redo_count);
-            tile_prune_kernel<<<pgrid, 256, 0, st>>>(qlo, qhi, dlo_t, dhi_t, slo_t, shi_t, L.n_qtiles, L.n_tiles, L.ld_t,
-                                                     L.n_super, L.ld_s, d, prm.out_dist + (k - 1), nq, maxnorm, list, count,
-                                                     L.cap, k, is_sqrt, 0, nullptr, redo_map, redo_count);
+            tile_prune_kernel<true><<<pgrid, 256, 0, st>>>(qlo, qhi, dlo_t, dhi_t, slo_t, shi_t, L.n_qtiles, L.n_tiles, L.ld_t,
+                                                           L.n_super, L.ld_s, d, prm.out_dist + (k - 1), nq, maxnorm, list,
+                                                           count, L.cap, k, is_sqrt, 0, nullptr, redo_map, redo_count);
             Params pr = prm;
             pr.qtile_map = redo_map;
             pr.qtile_count = redo_count;
