@@ -1,0 +1,182 @@
+"""The oracle against the REAL reference, live, on inputs beyond the committed fixtures.
+
+Runs only where the reference tree is mounted (the build container, /root/reference); on the GPU box — which has no
+reference — every test here is skipped, and nothing in the `-m gpu` suite, smoke() or bench.py reads that path.
+Each case draws fresh seeded inputs (several shapes, duplicates, tiny n) and requires bit-identical outputs of the
+reference's `backend=None, device="cpu"` functions and of their restatements in oracle/.
+"""
+
+import os
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from helpers import blobs
+
+REF = os.environ.get("TORCHDR_REFERENCE", "/root/reference")
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "torchdr")), reason="reference tree not mounted")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    stub = tempfile.mkdtemp(prefix="mplstub_")
+    os.makedirs(os.path.join(stub, "matplotlib"))
+    for f in ("__init__.py", "pylab.py", "pyplot.py"):  # torchdr/utils/visu.py:9 imports matplotlib unconditionally
+        open(os.path.join(stub, "matplotlib", f), "w").close()
+    sys.path.insert(0, stub)
+    sys.path.insert(0, REF)
+    try:
+        import torchdr
+    finally:
+        sys.path.remove(REF)
+        sys.path.remove(stub)
+    torch.set_num_threads(min(8, torch.get_num_threads()))
+    return torchdr
+
+
+CASES = [(64, 3, 5, 0), (257, 17, 15, 1), (500, 50, 90, 2), (1000, 128, 15, 3), (130, 8, 30, 4)]
+
+
+def _data(n, d, seed, duplicates=False):
+    X = blobs(n, d, max(2, n // 60), seed)
+    if duplicates:
+        X[n // 2:n // 2 + 7] = X[:7]
+    return X
+
+
+@pytest.mark.parametrize("n,d,k,seed", CASES)
+@pytest.mark.parametrize("metric", ["sqeuclidean", "euclidean"])
+def test_knn_equals_reference(ref, n, d, k, seed, metric):
+    from torchdr.distance import pairwise_distances
+
+    X = _data(n, d, seed)
+    C_ref, I_ref = pairwise_distances(X, metric=metric, backend=None, exclude_diag=True, k=k, return_indices=True)
+    C, I = oracle.knn_dense(X, k, metric, True)
+    assert torch.equal(I, I_ref) and torch.equal(C, C_ref)
+    full_ref = pairwise_distances(X, metric=metric, backend=None)
+    assert torch.equal(oracle.pairwise_full(X, None, metric), full_ref)
+
+
+@pytest.mark.parametrize("n,d,k,seed", CASES)
+@pytest.mark.parametrize("duplicates", [False, True])
+def test_umap_affinity_equals_reference(ref, n, d, k, seed, duplicates):
+    from torchdr.affinity import UMAPAffinity
+
+    X = _data(n, d, seed, duplicates)
+    kk = min(k, n - 2)
+    aff = UMAPAffinity(n_neighbors=kk, max_iter=100, backend=None, device="cpu")
+    V_ref, J_ref = aff(X, return_indices=True)
+    C, I = oracle.knn_dense(X, kk)
+    P, rho, sigma = oracle.umap_affinity_rows(C, kk, max_iter=100)
+    assert torch.equal(rho, aff.rho_.squeeze(-1) if aff.rho_.dim() > 1 else aff.rho_)
+    assert torch.equal(sigma, aff.eps_.squeeze(-1) if aff.eps_.dim() > 1 else aff.eps_)
+    V, J = oracle.symmetrize_ell(P, I)
+    assert torch.equal(J, J_ref.long()) and torch.equal(V, V_ref)
+    # the CSR form the engine uses carries the same entries
+    rp, col, val = oracle.ell_to_csr(V, J)
+    V2, J2 = oracle.csr_to_ell(rp, col, val)
+    assert torch.equal(V2, V) and torch.equal(J2, J)
+
+
+@pytest.mark.parametrize("n,d,perp,seed", [(64, 3, 5, 0), (300, 16, 10, 1), (700, 50, 30, 2), (200, 128, 40, 3)])
+def test_entropic_affinity_equals_reference(ref, n, d, perp, seed):
+    from torchdr.affinity import EntropicAffinity
+
+    X = _data(n, d, seed)
+    aff = EntropicAffinity(perplexity=perp, max_iter=100, backend=None, device="cpu")
+    logP_ref, I_ref = aff(X, log=True, return_indices=True)
+    p = oracle.clamp_neighbor_param(perp, n)
+    k = oracle.clamp_neighbor_param(3 * p, n)
+    C, I = oracle.knn_dense(X, k)
+    logP, eps, log_norm = oracle.entropic_affinity_rows(C, p, n_total=n, max_iter=100)
+    assert torch.equal(I, I_ref) and torch.equal(logP, logP_ref)
+    assert torch.equal(eps, aff.eps_.reshape(-1))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_umap_schedule_and_steps_equal_reference(ref, seed):
+    """Edge schedule (umap.py:215-234) and three optimisation steps from a shared state: the reference's own
+    _compute_gradients on its ELL arrays vs oracle.umap_step."""
+    from torchdr import UMAP
+
+    n, d, k, T = 200, 12, 10, 3
+    X = _data(n, d, 10 + seed)
+    g = torch.Generator().manual_seed(seed)
+    Zinit = torch.randn(n, 2, generator=g)
+    snaps, negs = {}, {}
+
+    class Cap(UMAP):
+        def on_training_step_start(self):
+            super().on_training_step_start()
+            negs[int(self.n_iter_)] = self.neg_indices_.clone()
+
+        def on_training_step_end(self):
+            snaps[int(self.n_iter_) + 1] = self.embedding_.detach().clone()
+            super().on_training_step_end()
+
+    m = Cap(n_neighbors=k, max_iter=T, init=Zinit, backend=None, device="cpu", random_state=seed,
+            process_duplicates=False, min_grad_norm=0.0)
+    m.fit_transform(X)
+    C, I = oracle.knn_dense(X, k)
+    P, _, _ = oracle.umap_affinity_rows(C, k, max_iter=100)
+    V, J = oracle.symmetrize_ell(P, I)
+    per, nxt = oracle.umap_edge_schedule(V, T)
+    Z0 = 1e-4 * Zinit / Zinit[:, 0].std()
+    a, b = oracle.find_ab()
+    lrs = oracle.linear_lr_sequence(1.0, T, T)
+    Z, nx = Z0, nxt
+    for t_ in range(T):
+        Z, nx = oracle.umap_run(Z, J, per, nx, [negs[t_]], [lrs[t_]], a, b, n_iter0=t_)
+        assert torch.equal(Z, snaps[t_ + 1]), t_
+
+
+@pytest.mark.parametrize("name,seed", [("LargeVis", 0), ("LargeVis", 1), ("TSNE", 0), ("TSNE", 1), ("InfoTSNE", 0), ("SNE", 0)])
+def test_momentum_estimators_equal_reference(ref, name, seed):
+    """Four steps of the autograd-mode estimators (below ATen's parallel grain size, where the reference is itself
+    bit-reproducible), across the early-exaggeration switch at step 2, with the negatives the reference drew."""
+    import torchdr
+
+    n, d, perp, T = 150, 10, 8, 4
+    X = _data(n, d, 20 + seed)
+    Zinit = torch.randn(n, 2, generator=torch.Generator().manual_seed(seed))
+    snaps, negs, cap = {}, {}, {}
+
+    class Cap(getattr(torchdr, name)):
+        def on_affinity_computation_end(self):
+            cap["P"], cap["I"] = self.affinity_in_.detach().clone(), self.NN_indices_.detach().clone()
+            super().on_affinity_computation_end()
+
+        def on_training_step_start(self):
+            super().on_training_step_start()
+            if hasattr(self, "neg_indices_"):
+                negs[int(self.n_iter_)] = self.neg_indices_.clone()
+
+        def on_training_step_end(self):
+            snaps[int(self.n_iter_) + 1] = self.embedding_.detach().clone()
+            super().on_training_step_end()
+
+    kw = {"early_exaggeration_iter": 2} if name in ("TSNE", "InfoTSNE") else {}
+    if name == "InfoTSNE":
+        kw["n_negatives"] = 20
+    m = Cap(perplexity=perp, max_iter=T, init=Zinit, backend=None, device="cpu", random_state=seed,
+            process_duplicates=False, min_grad_norm=0.0, **kw)
+    m.fit_transform(X)
+    p = oracle.clamp_neighbor_param(perp, n)
+    C, I = oracle.knn_dense(X, oracle.clamp_neighbor_param(3 * p, n))
+    P = oracle.entropic_affinity_rows(C, p, n_total=n, max_iter=100)[0].exp()
+    assert torch.equal(P, cap["P"]) and torch.equal(I, cap["I"])
+    Z0 = 1e-4 * Zinit / Zinit[:, 0].std()
+    for T_ in range(1, T + 1):
+        if name == "LargeVis":
+            Z = oracle.largevis_run(Z0, P, I, [negs[t_] for t_ in range(T_)], T_)[0]
+        elif name == "TSNE":
+            Z = oracle.tsne_run(Z0, P, I, T_, exag_iter=2)
+        elif name == "InfoTSNE":
+            Z = oracle.infotsne_run(Z0, P, I, [negs[t_] for t_ in range(T_)], T_, exag_iter=2)[0]
+        else:
+            Z = oracle.sne_run(Z0, P, I, T_)
+        assert torch.equal(Z, snaps[T_]), (name, T_)
