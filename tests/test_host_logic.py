@@ -476,3 +476,47 @@ def test_baseline_config_1_host_flow_on_cpu(monkeypatch):
     assert isinstance(Z, np.ndarray) and Z.shape == (2000, 2)
     for T, tol in ((1, 2e-6), (5, 5e-6), (20, 2e-5)):
         assert rel_fro(snaps[T], g[f"Z_{T}"]) < tol, T
+
+
+def test_duplicate_precheck_matches_torch_unique():
+    """The hash pre-check that spares the reference's torch.unique(X, dim=0) (base.py:132-146) when all rows differ:
+    it may only say "no duplicates" when unique() would keep every row."""
+    from torchdr_b200.neighbor_embedding import _may_have_duplicate_rows
+
+    g = torch.Generator().manual_seed(0)
+    for n, d in ((1, 3), (2, 1), (1000, 7), (5000, 128)):
+        X = torch.randn(n, d, generator=g)
+        assert not _may_have_duplicate_rows(X, chunk=1024)
+        assert torch.unique(X, dim=0).shape[0] == n
+    X = torch.randn(3000, 16, generator=g)
+    Xd = X.clone()
+    Xd[2999] = Xd[17]
+    assert _may_have_duplicate_rows(Xd, chunk=1000)
+    Xz = X.clone()
+    Xz[5, 3], Xz[6] = 0.0, Xz[5]
+    Xz[6, 3] = -0.0  # unique() compares values: -0.0 == +0.0
+    assert torch.unique(Xz, dim=0).shape[0] == 2999 and _may_have_duplicate_rows(Xz)
+    Xc = torch.zeros(50, 4)  # all equal
+    assert _may_have_duplicate_rows(Xc)
+    assert not _may_have_duplicate_rows(torch.arange(40.0).reshape(40, 1))
+
+
+def test_duplicates_share_their_embedding_on_cpu(monkeypatch):
+    """process_duplicates=True (the default) through the public estimator on the CPU stand-ins: duplicates are found,
+    the fit runs on the unique rows in unique()'s order and duplicates share their embedding (base.py:132-146); without
+    duplicates the rows are fitted in their own order."""
+    import fake_ops
+
+    import torchdr_b200 as tb
+
+    fake_ops.install(monkeypatch)
+    g = golden("umap_n300_d16_k15")
+    X = t(g["X"])
+    Xdup = torch.cat([X, X[:25]])
+    Z = tb.UMAP(n_neighbors=15, max_iter=12, init="normal", random_state=0, check_interval=5).fit_transform(Xdup)
+    assert Z.shape == (325, 2) and torch.equal(Z[:25], Z[300:])
+    calls = []
+    orig = torch.unique
+    monkeypatch.setattr(torch, "unique", lambda *a, **k: (calls.append(1) if k.get("dim") == 0 else None) or orig(*a, **k))
+    tb.UMAP(n_neighbors=15, max_iter=3, init="normal", random_state=0).fit_transform(X)
+    assert not calls  # no duplicates: the lexicographic row sort is never run

@@ -39,6 +39,26 @@ def find_ab_params(spread, min_dist):
     return params[0].item(), params[1].item()
 
 
+def _may_have_duplicate_rows(X, chunk=131072):
+    """False only if all rows of X are pairwise distinct.  The reference finds duplicates with ``torch.unique(X, dim=0)``
+    (base.py:132-146), a lexicographic sort of all rows that costs more than the whole fit at 1 M x 128; here every row
+    gets a 64-bit multiplicative hash of its bit pattern (-0.0 canonicalised to +0.0, which ``unique`` treats as equal;
+    the input is already checked finite), the hashes are sorted, and equal neighbours mean "maybe": equal rows always
+    collide, so distinct hashes prove distinct rows, and on any collision the caller runs the reference's
+    ``torch.unique`` unchanged."""
+    n, d = X.shape
+    if n < 2:
+        return False
+    g = torch.Generator().manual_seed(0x5DEECE66D)
+    w = (torch.randint(0, 2**62, (d,), generator=g, dtype=torch.int64) * 2 + 1).to(X.device)  # odd multipliers
+    h = torch.empty(n, dtype=torch.int64, device=X.device)
+    for a in range(0, n, chunk):
+        bits = (X[a:a + chunk] + 0.0).contiguous().view(torch.int32).to(torch.int64)
+        h[a:a + chunk] = (bits * w).sum(1)  # wraps modulo 2^64
+    hs = torch.sort(h).values
+    return bool((hs[1:] == hs[:-1]).any())
+
+
 class _NeighborEmbeddingB200:
     """Driver shared by the three methods (affinity_matcher.py + neighbor_embedding/base.py)."""
 
@@ -144,7 +164,7 @@ class _NeighborEmbeddingB200:
         if not bool(torch.isfinite(Xd).all()):
             raise ValueError("[TorchDR] ERROR : input contains NaN or infinite values.")
         self._tick("finite_check")
-        if self.process_duplicates:  # base.py:132-146
+        if self.process_duplicates and _may_have_duplicate_rows(Xd):  # base.py:132-146
             Xu, inverse = torch.unique(Xd, dim=0, return_inverse=True)
             if Xu.shape[0] < Xd.shape[0]:
                 self.logger.info(f"Detected {Xd.shape[0] - Xu.shape[0]} duplicate samples, performing DR on unique data.")
