@@ -871,6 +871,30 @@ def test_estimator_edge_cases():
     assert Zd.shape == (257, 2)
 
 
+@pytest.mark.skipif(__import__("os").environ.get("TDR_TEST_EXPERIMENTAL") != "1",
+                    reason="added after the round's last GPU minute; set TDR_TEST_EXPERIMENTAL=1 to run")
+def test_discard_nns_estimators_on_gpu():
+    """discard_NNs=True on the CUDA path: the host flow is verified against the live reference on the CPU stand-ins
+    (tests/test_oracle_vs_reference.py); here the injected tables must respect the exclusions and the fits must work."""
+    import torchdr_b200 as tb
+
+    X = blobs(400, 12, 4, 3)
+    seen = {}
+
+    class Cap(tb.UMAP):
+        def on_training_step_start(self):
+            super().on_training_step_start()
+            seen["neg"], seen["excl"] = self.neg_indices_.clone(), self.negative_exclusion_indices_.clone()
+
+    Z = Cap(n_neighbors=10, max_iter=20, init="normal", random_state=0, discard_NNs=True).fit_transform(X)
+    assert Z.shape == (400, 2) and bool(torch.isfinite(Z).all())
+    neg, excl = seen["neg"], seen["excl"]
+    assert neg.dtype == torch.int64 and neg.shape == (400, 50) and int(neg.min()) >= 0 and int(neg.max()) < 400
+    assert not bool((neg == torch.arange(400, device=neg.device).unsqueeze(1)).any())  # never the row itself
+    Zl = tb.LargeVis(perplexity=8, max_iter=20, init="normal", random_state=0, discard_NNs=True).fit_transform(X)
+    assert bool(torch.isfinite(Zl).all())
+
+
 def test_umap_estimator_parity_hooks():
     """Drive the estimator like the reference's golden run (injected init + negatives through the hook)."""
     import torchdr_b200 as tb

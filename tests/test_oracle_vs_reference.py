@@ -180,3 +180,43 @@ def test_momentum_estimators_equal_reference(ref, name, seed):
         else:
             Z = oracle.sne_run(Z0, P, I, T_)
         assert torch.equal(Z, snaps[T_]), (name, T_)
+
+
+@pytest.mark.parametrize("name", ["UMAP", "LargeVis"])
+def test_discard_nns_host_flow_equals_reference(ref, name, monkeypatch):
+    """discard_NNs=True: the engine's host flow (public estimator on the CPU stand-ins of tests/fake_ops.py) against the
+    reference, same seed: the exclusion table (NE base.py:578-615), the negatives of every step (:638-647, drawn from
+    the global generator right after seeding, as the reference does) and the embedding after 3 steps are identical."""
+    import fake_ops
+    import torchdr
+
+    import torchdr_b200 as tb
+
+    n, d, T = 160, 8, 3
+    X = _data(n, d, 31)
+    Zinit = torch.randn(n, 2, generator=torch.Generator().manual_seed(5))
+    kw = {"n_neighbors": 8} if name == "UMAP" else {"perplexity": 6}
+    seen = {"ref": {}, "eng": {}}
+
+    def capture(base, tag):
+        class Cap(base):
+            def on_training_step_start(self):
+                super().on_training_step_start()
+                if int(self.n_iter_) == 0:
+                    seen[tag]["excl"] = self.negative_exclusion_indices_.clone()
+                seen[tag][f"neg{int(self.n_iter_)}"] = self.neg_indices_.clone()
+
+        return Cap
+
+    mr = capture(getattr(torchdr, name), "ref")(max_iter=T, init=Zinit, backend=None, device="cpu", random_state=3,
+                                               process_duplicates=False, min_grad_norm=0.0, discard_NNs=True, **kw)
+    Zr = mr.fit_transform(X)
+    fake_ops.install(monkeypatch)
+    fake_ops.install_entropic(monkeypatch)
+    me = capture(getattr(tb, name), "eng")(max_iter=T, init=Zinit, random_state=3, process_duplicates=False,
+                                          min_grad_norm=0.0, discard_NNs=True, **kw)
+    Ze = me.fit_transform(X)
+    assert torch.equal(seen["eng"]["excl"], seen["ref"]["excl"])
+    for t_ in range(T):
+        assert torch.equal(seen["eng"][f"neg{t_}"], seen["ref"][f"neg{t_}"]), t_
+    assert torch.equal(Ze, Zr)

@@ -199,8 +199,28 @@ class _NeighborEmbeddingB200:
 
     def on_training_step_start(self):
         """Subclasses / tests may set ``self.neg_indices_`` (int64 [n_local, n_negatives], already
-        adjusted as in NE base.py:629-636); when left ``None`` negatives are drawn in-kernel."""
+        adjusted as in NE base.py:629-636); when left ``None`` negatives are drawn in-kernel.
+
+        ``discard_NNs=True``: the reference's own draw (NE base.py:638-647) — ``randint(1, N - width)`` shifted by
+        ``searchsorted`` into the sorted per-row exclusion table (self + neighbours) — made with the same torch calls
+        on the device and handed to the kernels as an injected table.  A functional path, not a fast one: like the
+        reference it keeps an [n_local, 1 + W] table and writes n_local x n_negatives indices per step."""
         self.neg_indices_ = None
+        excl = getattr(self, "negative_exclusion_indices_", None)
+        if excl is not None:
+            n_local = excl.shape[0]
+            raw = torch.randint(1, self.n_samples_in_ - excl.shape[1], (n_local, self.n_negatives), device=excl.device)
+            self.neg_indices_ = (raw + torch.searchsorted(excl, raw, right=True)).contiguous()
+
+    def _build_negative_exclusions(self, nn_rows):
+        """NE base.py:578-615: sorted [self, neighbours] per local row (the -1 padding of a symmetrised graph sorts
+        first, as it does in the reference)."""
+        me = self.chunk_indices_.unsqueeze(1)
+        excl = torch.cat([me, nn_rows.long()], dim=1).sort(dim=1).values
+        n_possible = self.n_samples_in_ - excl.shape[1]
+        if self.n_negatives > n_possible and self.verbose:
+            raise ValueError(f"[TorchDR] ERROR : requested {self.n_negatives} negatives but only {n_possible} available.")
+        self.negative_exclusion_indices_ = excl
 
     def on_training_step_end(self):
         pass
@@ -296,6 +316,8 @@ class _NeighborEmbeddingB200:
         self._compute_affinity(X)
         self._tick("affinity+graph")
         self.chunk_indices_ = torch.arange(self.chunk_start_, self.chunk_end_, device=X.device)  # NE base.py:406-408
+        if getattr(self, "discard_NNs", False):
+            self._build_negative_exclusions(self._neighbour_rows())
         self.on_affinity_computation_end()
 
         if self.verbose:
@@ -335,7 +357,7 @@ class _NeighborEmbeddingB200:
 
     def clear_memory(self):
         for name in ("_gnorm", "_nan", "optimizer_", "scheduler_", "params_", "_dummy", "neg_indices_", "_graph",
-                     "affinity_in_", "NN_indices_", "chunk_indices_", "_mom", "_grad"):
+                     "affinity_in_", "NN_indices_", "chunk_indices_", "_mom", "_grad", "negative_exclusion_indices_"):
             if hasattr(self, name):
                 delattr(self, name)
         if hasattr(self.affinity_in, "clear_memory"):
@@ -419,8 +441,6 @@ class UMAP(_NeighborEmbeddingB200):
             a, b = find_ab_params(spread, min_dist)
         self._a, self._b = a, b
         self.n_negatives = int(negative_sample_rate * n_neighbors)  # umap.py:177
-        if discard_NNs:
-            raise NotImplementedError("[TorchDR-B200] discard_NNs=True is not implemented in the step kernel.")
         self.discard_NNs = discard_NNs
         super().__init__(n_components=n_components, lr=lr, optimizer=optimizer, optimizer_kwargs=optimizer_kwargs,
                          scheduler=scheduler, scheduler_kwargs=scheduler_kwargs, min_grad_norm=min_grad_norm,
@@ -446,6 +466,11 @@ class UMAP(_NeighborEmbeddingB200):
         self._graph_full = (rowptr, col, val, eps)
         self._graph = ops.umap_compact(rowptr, col, eps)  # (rowptr, col, eps, eons) of live edges
 
+    def _neighbour_rows(self):
+        # the reference's NN_indices_ of UMAP: the symmetrised graph's padded index matrix (affinity/base.py:407-431)
+        rowptr, col, val, _ = self._graph_full
+        return ops.csr_to_ell(rowptr, col, val)[1]
+
     def clear_memory(self):
         if hasattr(self, "_graph_full"):
             del self._graph_full
@@ -466,7 +491,8 @@ class UMAP(_NeighborEmbeddingB200):
         step = 0
         stop = False
         hooks_per_step = type(self).on_training_step_start is not UMAP.on_training_step_start or \
-            type(self).on_training_step_end is not _NeighborEmbeddingB200.on_training_step_end
+            type(self).on_training_step_end is not _NeighborEmbeddingB200.on_training_step_end or \
+            getattr(self, "negative_exclusion_indices_", None) is not None
         # multi-GPU: fused step + exchange over NVLink peer stores (PeerEmbedding) when symmetric memory is
         # available, else one NCCL all-gather per iteration
         peer, cur = None, 0
@@ -555,6 +581,9 @@ class UMAP(_NeighborEmbeddingB200):
 
 
 class _EntropicInputMixin:
+    def _neighbour_rows(self):
+        return self.NN_indices_
+
     def _compute_affinity(self, X):
         P, idx = self.affinity_in(X, log=False, return_indices=True)
         self.affinity_in_ = P.contiguous()
@@ -575,8 +604,6 @@ class LargeVis(_EntropicInputMixin, _NeighborEmbeddingB200):
         self.max_iter_affinity = max_iter_affinity
         self.sparsity = sparsity
         self.n_negatives = n_negatives
-        if discard_NNs:
-            raise NotImplementedError("[TorchDR-B200] discard_NNs=True is not implemented in the step kernel.")
         self.discard_NNs = discard_NNs
         super().__init__(n_components=n_components, lr=lr, optimizer=optimizer, optimizer_kwargs=optimizer_kwargs,
                          scheduler=scheduler, scheduler_kwargs=scheduler_kwargs, min_grad_norm=min_grad_norm,
@@ -653,8 +680,6 @@ class InfoTSNE(_EntropicInputMixin, _NeighborEmbeddingB200):
         self.max_iter_affinity = max_iter_affinity
         self.sparsity = sparsity
         self.n_negatives = n_negatives
-        if discard_NNs:
-            raise NotImplementedError("[TorchDR-B200] discard_NNs=True is not implemented in the step kernel.")
         self.discard_NNs = discard_NNs
         super().__init__(n_components=n_components, lr=lr, optimizer=optimizer, optimizer_kwargs=optimizer_kwargs,
                          scheduler=scheduler, scheduler_kwargs=scheduler_kwargs, min_grad_norm=min_grad_norm,
