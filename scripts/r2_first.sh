@@ -5,7 +5,7 @@
 #   3. shuffled row order: plain (full sweep) vs TDR_KNN_REORDER=1 (Voronoi-tree order + certified sweep)
 set -u
 O=gpurun_out; mkdir -p $O
-echo "== [1] experimental kNN tests"; TDR_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -s -k "robust or discard_nns or baseline_config_1" 2>&1 | tail -12
+echo "== [1] experimental kNN tests"; TDR_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -s -k "robust or discard_nns or baseline_config_1 or generic_optimizers" 2>&1 | tail -12
 echo "== [2] step kernel variants"
 for cfg in 0 6 7 8 5; do
   TDR_STEP_CFG=$cfg timeout 200 python bench.py --steps 1000 --warmup 20 --no-e2e --no-cpu 2>/dev/null | python -c "

@@ -78,6 +78,8 @@ def umap_step(Z_in, Z_out, row0, n_local, rowptr, col, eps, eons, n_iter, a, b, 
     # write the advanced edge state back into the CSR array (row-major ELL order == CSR order)
     eons.copy_(nxt[J >= 0])
     Z_out.copy_(Z_in.add(G, alpha=-float(lr)))
+    if grad_out is not None:
+        grad_out.copy_(G)
     if gnorm_sq is not None:
         gnorm_sq += float((G.double() ** 2).sum())
 

@@ -273,6 +273,7 @@ def test_umap_loop_bookkeeping_without_a_gpu(monkeypatch):
                     a=1.5, b=0.9, random_state=0, distributed=False)
         m.n_samples_in_, m.chunk_start_, m.chunk_end_ = 8, 0, 8
         m.early_exaggeration_coeff_ = 1
+        m._native_opt = m._uses_native_sgd()
         m._graph = (torch.zeros(9, dtype=torch.long), torch.zeros(0, dtype=torch.int32), torch.zeros(0), torch.zeros(0))
         m.embedding_ = torch.zeros(8, 2)
         m._gnorm, m._nan = torch.zeros(1, dtype=torch.float64), torch.zeros(1, dtype=torch.int32)
@@ -315,6 +316,7 @@ def test_momentum_loop_bookkeeping_matches_reference_sequences(monkeypatch):
         m._compute_gradient = lambda Z, step: None
         m.n_samples_in_, m.chunk_start_, m.chunk_end_ = 300, 0, 300
         m.early_exaggeration_coeff_ = m.early_exaggeration_coeff
+        m._native_opt = m._uses_native_sgd()
         m.embedding_ = torch.zeros(300, 2)
         m._gnorm, m._nan = torch.ones(1, dtype=torch.float64), torch.zeros(1, dtype=torch.int32)
         m._dummy = torch.nn.Parameter(torch.zeros(1))

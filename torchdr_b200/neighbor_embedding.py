@@ -259,17 +259,36 @@ class _NeighborEmbeddingB200:
         else:
             self.lr_ = self.lr
 
-    def _configure_optimizer(self):
-        if self.optimizer != "SGD":
-            raise NotImplementedError("[TorchDR-B200] only optimizer='SGD' is implemented by the update kernels.")
+    def _optimizer_spec(self):
+        """(class, kwargs) exactly as NE base.py:312-343 resolves them."""
+        if isinstance(self.optimizer, str):
+            cls = getattr(torch.optim, self.optimizer, None)
+            if cls is None:
+                raise ValueError(f"[TorchDR] ERROR: Optimizer '{self.optimizer}' not found in torch.optim")
+        else:
+            if not (isinstance(self.optimizer, type) and issubclass(self.optimizer, torch.optim.Optimizer)):
+                raise ValueError("[TorchDR] ERROR: optimizer must be a string (name of an optimizer in "
+                                 "torch.optim) or a subclass of torch.optim.Optimizer")
+            cls = self.optimizer
         if self.optimizer_kwargs == "auto":  # NE base.py:331-338
-            kw = {"momentum": 0.5} if self.early_exaggeration_coeff_ > 1 else {"momentum": 0.8}
+            if self.optimizer == "SGD":
+                kw = {"momentum": 0.5} if self.early_exaggeration_coeff_ > 1 else {"momentum": 0.8}
+            else:
+                kw = {}
         else:
             kw = self.optimizer_kwargs or {}
-        extra = set(kw) - {"momentum"}
-        if extra:
-            raise NotImplementedError(f"[TorchDR-B200] SGD options {sorted(extra)} are not implemented.")
-        self.optimizer_ = torch.optim.SGD(self.params_, lr=self.lr_, **kw)  # NE base.py:343
+        return cls, kw
+
+    def _uses_native_sgd(self):
+        """The update kernels implement torch.optim.SGD with (only) a momentum option.  Every other optimiser or
+        option runs as the reference runs it: the torch optimiser itself, stepped on the embedding with the
+        gradient the kernels computed (torch library code on the device: plumbing around the gradient kernels)."""
+        cls, kw = self._optimizer_spec()
+        return cls is torch.optim.SGD and set(kw) <= {"momentum"}
+
+    def _configure_optimizer(self):
+        cls, kw = self._optimizer_spec()
+        self.optimizer_ = cls(self.params_, lr=self.lr_, **kw)  # NE base.py:343
         return self.optimizer_
 
     def _configure_scheduler(self):
@@ -288,6 +307,16 @@ class _NeighborEmbeddingB200:
         else:
             self.scheduler_ = self.scheduler(self.optimizer_, **(self.scheduler_kwargs or {}))
         return self.scheduler_
+
+    def _generic_step(self, grad, check):
+        """affinity_matcher.py:414-429 with the reference's own optimiser object: grad -> optimizer_.step()."""
+        self._dummy.grad = grad
+        self.optimizer_.step()
+        if self.scheduler_ is not None:
+            self.scheduler_.step()
+        if check:
+            self._gnorm.copy_(grad.double().pow(2).sum().reshape(1))
+            self._nan.copy_(torch.isnan(self._dummy.detach()).any().to(torch.int32).reshape(1))
 
     def _hyper(self):
         g = self.optimizer_.param_groups[0]
@@ -323,8 +352,11 @@ class _NeighborEmbeddingB200:
         if self.verbose:
             self.logger.info("----- Optimizing the embedding -----")
         Z = self._init_embedding(X)
-        self._dummy = torch.nn.Parameter(torch.zeros(1))
-        self.params_ = [{"params": [self._dummy]}]  # ONE dict reused by every rebuild (affinity_matcher.py:588-590)
+        self._native_opt = self._uses_native_sgd()
+        # native: the torch objects only keep the books (lr / momentum sequence) on a dummy parameter; generic: they
+        # own the embedding (same storage as Z).  ONE dict reused by every rebuild (affinity_matcher.py:588-590).
+        self._dummy = torch.nn.Parameter(torch.zeros(1) if self._native_opt else Z)
+        self.params_ = [{"params": [self._dummy]}]
         self._set_learning_rate()
         self._configure_optimizer()
         self._configure_scheduler()
@@ -380,13 +412,16 @@ class _NeighborEmbeddingB200:
             self._compute_gradient(Z, step)
             if self.world_size > 1:  # affinity_matcher.py:424-425
                 dist.all_reduce(self._grad, op=dist.ReduceOp.SUM)
-            lr, mom = self._hyper()
-            if check:
-                self._gnorm.zero_()
-            ops.sgd_momentum(Z, self._mom, self._grad, lr, mom, first or mom == 0.0,
-                             gnorm_sq=self._gnorm if check else None, nan_flag=self._nan)
-            first = False
-            self._advance_schedule()
+            if self._native_opt:
+                lr, mom = self._hyper()
+                if check:
+                    self._gnorm.zero_()
+                ops.sgd_momentum(Z, self._mom, self._grad, lr, mom, first or mom == 0.0,
+                                 gnorm_sq=self._gnorm if check else None, nan_flag=self._nan)
+                first = False
+                self._advance_schedule()
+            else:
+                self._generic_step(self._grad, check)
             # NE base.py:282-295 — end of early exaggeration: rebuild optimiser (+ scheduler)
             if self.early_exaggeration_coeff_ > 1 and step == self.early_exaggeration_iter:
                 self.early_exaggeration_coeff_ = 1
@@ -484,9 +519,10 @@ class UMAP(_NeighborEmbeddingB200):
         Zb = Za.clone()
         seed = int(self._actual_seed) if self.random_state is not None else int(torch.initial_seed() % (2**63))
         lam, rep = float(self.early_exaggeration_coeff_), float(self.repulsion_strength)
-        mom = self._hyper()[1]
-        if mom != 0.0:
-            raise NotImplementedError("[TorchDR-B200] UMAP step kernel implements plain SGD (umap.py:139).")
+        if not self._native_opt or self._hyper()[1] != 0.0:
+            # the step kernel fuses plain SGD (umap.py:139, the default); anything else takes the gradient from the
+            # kernel and lets the reference's optimiser object apply it (affinity_matcher.py:395-413)
+            return self._loop_generic_optimizer(seed, lam, rep)
         self._last_step = -1
         step = 0
         stop = False
@@ -578,6 +614,46 @@ class UMAP(_NeighborEmbeddingB200):
             if last % self.check_interval == 0:
                 stop = self._converged(last, float(self._gnorm.item()) ** 0.5)
         self.embedding_ = Za.clone() if peer is not None else Za  # leave symmetric memory before it is released
+
+
+def _umap_loop_generic_optimizer(self, seed, lam, rep):
+    """UMAP iterations with an arbitrary torch optimiser: gradient of the local rows from the step kernel
+    (`grad_out`), zero-padded to N x 2 and summed over ranks as in affinity_matcher.py:395-413, then
+    `optimizer_.step()` on the embedding; the kernel's own SGD output is scratch."""
+    rowptr, col, eps, eons = self._graph
+    s, e = self.chunk_start_, self.chunk_end_
+    if self._native_opt:  # SGD with momentum: give the torch objects the real embedding
+        self._native_opt = False
+        self._dummy = torch.nn.Parameter(self.embedding_)
+        self.params_[0]["params"] = [self._dummy]
+        self._configure_optimizer()
+        self._configure_scheduler()
+    Z = self.embedding_
+    scratch = torch.empty_like(Z)
+    G = torch.zeros_like(Z)
+    self._last_step = -1
+    for step in range(self.max_iter):
+        self.n_iter_ = torch.tensor(step, dtype=torch.long)
+        self._last_step = step
+        self.on_training_step_start()
+        check = step % self.check_interval == 0
+        if self.world_size > 1:
+            G.zero_()
+        ops.umap_step(Z, scratch, s, e - s, rowptr, col, eps, eons, step, self._a, self._b, 0.0,
+                      neg=getattr(self, "neg_indices_", None), n_neg=self.n_negatives, rate=self.negative_sample_rate,
+                      seed=seed, lam=lam, repulsion=rep, precise=self.precise, grad_out=G[s:e])
+        if self.world_size > 1:
+            dist.all_reduce(G, op=dist.ReduceOp.SUM)
+        self._generic_step(G, check)
+        self.on_training_step_end()
+        if check:
+            self._check_nan(step)
+            if self._converged(step, float(self._gnorm.item()) ** 0.5):
+                break
+    self._check_nan(self._last_step)
+
+
+UMAP._loop_generic_optimizer = _umap_loop_generic_optimizer
 
 
 class _EntropicInputMixin:
