@@ -72,7 +72,11 @@ def _ell(rowptr, col, eps, eons):
 
 def umap_step(Z_in, Z_out, row0, n_local, rowptr, col, eps, eons, n_iter, a, b, lr, neg=None, n_neg=75, rate=5,
               seed=0, lam=1.0, repulsion=1.0, precise=False, grad_out=None, gnorm_sq=None, nan_flag=None, stats=None):
-    assert neg is not None and row0 == 0 and n_local == Z_in.shape[0], "the stand-in needs injected negatives"
+    assert row0 == 0 and n_local == Z_in.shape[0]
+    if neg is None:  # the kernel would draw in place; the stand-in draws its own table (distribution only)
+        n = Z_in.shape[0]
+        g = torch.Generator().manual_seed(int(seed) * 7919 + int(n_iter))
+        neg = oracle.adjust_negatives(torch.randint(0, n - 1, (n, n_neg), generator=g), torch.arange(n))
     J, per, nxt = _ell(rowptr, col, eps, eons)
     G = oracle.umap_step(Z_in, J, per, nxt, neg, n_iter, a, b, negative_sample_rate=rate, lam=lam, repulsion=repulsion)
     # write the advanced edge state back into the CSR array (row-major ELL order == CSR order)
