@@ -113,8 +113,14 @@ def entropic_affinity_rows(C, target_entropy, log_n_total, bounds=None, max_iter
     return oracle.entropic_affinity_rows(C, perp, n_total=n_total, max_iter=max_iter, use_bounds=bounds is not None)
 
 
+def _own_negatives(n, n_neg, seed, n_iter):
+    g = torch.Generator().manual_seed(int(seed) * 7919 + int(n_iter))
+    return oracle.adjust_negatives(torch.randint(0, n - 1, (n, n_neg), generator=g), torch.arange(n))
+
+
 def largevis_grad(Z, row0, n_local, Pm, idx, grad, n_iter, neg=None, n_neg=5, seed=0, lam=1.0, repulsion=1.0):
-    assert neg is not None and row0 == 0 and n_local == Z.shape[0]
+    assert row0 == 0 and n_local == Z.shape[0]
+    neg = _own_negatives(n_local, n_neg, seed, n_iter) if neg is None else neg
     from oracle.largevis import largevis_loss
 
     Zp = Z.detach().clone().requires_grad_(True)
@@ -148,7 +154,8 @@ def sgd_momentum(Z, buf, grad, lr, momentum, first, gnorm_sq=None, nan_flag=None
 
 
 def infotsne_grad(Z, row0, n_local, Pm, idx, grad, n_iter, neg=None, n_neg=300, seed=0, lam=1.0, repulsion=1.0):
-    assert neg is not None and row0 == 0 and n_local == Z.shape[0]
+    assert row0 == 0 and n_local == Z.shape[0]
+    neg = _own_negatives(n_local, n_neg, seed, n_iter) if neg is None else neg
     Zp = Z.detach().clone().requires_grad_(True)
     oracle.infotsne_loss(Zp, Pm, idx, neg, torch.arange(n_local), Z.shape[0], lam, repulsion).backward()
     grad += Zp.grad
