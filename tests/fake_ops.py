@@ -176,3 +176,76 @@ def install_entropic(monkeypatch):
                      ("tsne_workspace", tsne_workspace), ("tsne_grad", tsne_grad), ("infotsne_grad", infotsne_grad),
                      ("sne_grad", sne_grad), ("sgd_momentum", sgd_momentum)):
         monkeypatch.setattr(ops, name, fn)
+
+
+# ---- row-sharded stand-ins (world_size > 1 under gloo): same semantics as the CUDA entry points for a row chunk
+def install_sharded(monkeypatch):
+    from torchdr_b200 import ops
+
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *a, **k: None)
+    for name, fn in (("knn_umap_fused", knn_umap_fused_chunk), ("symmetrize_export", symmetrize_export),
+                     ("symmetrize_csr", symmetrize_csr_chunk), ("umap_step", umap_step_chunk)):
+        monkeypatch.setattr(ops, name, fn)
+
+
+def knn_umap_fused_chunk(Xq, Xdb, k, q_row0=0, exclude_self=True, max_iter=100, want_dist=True):
+    C, I = oracle.knn_dense(Xdb, k)  # full problem, then this rank's rows: identical values for every partition
+    P, rho, sigma = oracle.umap_affinity_rows(C, k, max_iter=max_iter)
+    s, e = q_row0, q_row0 + Xq.shape[0]
+    return C[s:e].contiguous(), I[s:e].contiguous(), P[s:e].contiguous(), rho[s:e].contiguous(), sigma[s:e].contiguous()
+
+
+def symmetrize_export(Pm, idx, row0, n_total, world, rank):
+    """tdr_symmetrize_export_f32: edge (i -> j, v) of a local row i whose j lives on another rank is sent to owner(j)
+    as the transposed entry (row = j, col = i, val = v), packed by destination rank."""
+    n_local, k = Pm.shape
+    i = (torch.arange(n_local) + row0).repeat_interleave(k)
+    j = idx.reshape(-1).long()
+    v = Pm.reshape(-1)
+    owner = torch.tensor([oracle.owner_of(int(x), n_total, world) for x in j.tolist()], dtype=torch.long)
+    away = owner != rank
+    order = torch.argsort(owner[away], stable=True)
+    counts = torch.bincount(owner[away], minlength=world)
+    return counts, j[away][order].contiguous(), i[away][order].int().contiguous(), v[away][order].contiguous()
+
+
+def symmetrize_csr_chunk(Pm, idx, row0, n_total, ext=None, transpose_local=True):
+    """Q = P + P^T - P o P^T for the local rows; P^T entries come from local edges landing on local rows and from the
+    received triples.  Same three separately rounded fp32 operations as utils/sparse.py:163-164."""
+    n_local, k = Pm.shape
+    A = torch.zeros(n_local, n_total)
+    B = torch.zeros(n_local, n_total)
+    hasA = torch.zeros(n_local, n_total, dtype=torch.bool)
+    hasB = torch.zeros(n_local, n_total, dtype=torch.bool)
+    r = torch.arange(n_local).repeat_interleave(k)
+    j = idx.reshape(-1).long()
+    A[r, j] = Pm.reshape(-1)
+    hasA[r, j] = True
+    local = (j >= row0) & (j < row0 + n_local)
+    B[j[local] - row0, r[local] + row0] = Pm.reshape(-1)[local]
+    hasB[j[local] - row0, r[local] + row0] = True
+    if ext is not None and ext[0].numel() > 0:
+        er, ec, ev = ext
+        B[er - row0, ec.long()] = ev
+        hasB[er - row0, ec.long()] = True
+    Q = A + B - A * B
+    pattern = hasA | hasB
+    rowptr = torch.zeros(n_local + 1, dtype=torch.long)
+    rowptr[1:] = pattern.sum(1).cumsum(0)
+    rr, cc = pattern.nonzero(as_tuple=True)
+    return rowptr, cc.int().contiguous(), Q[rr, cc].contiguous()
+
+
+def umap_step_chunk(Z_in, Z_out, row0, n_local, rowptr, col, eps, eons, n_iter, a, b, lr, neg=None, n_neg=75, rate=5,
+                    seed=0, lam=1.0, repulsion=1.0, precise=False, grad_out=None, gnorm_sq=None, nan_flag=None,
+                    stats=None):
+    assert neg is not None
+    J, per, nxt = _ell(rowptr, col, eps, eons)
+    G = oracle.umap_step(Z_in, J, per, nxt, neg, n_iter, a, b, chunk_start=row0, chunk_size=n_local,
+                         negative_sample_rate=rate, lam=lam, repulsion=repulsion)
+    eons.copy_(nxt[J >= 0])
+    Z_out[row0:row0 + n_local] = Z_in[row0:row0 + n_local].add(G, alpha=-float(lr))
+    if grad_out is not None:
+        grad_out.copy_(G)
+    if gnorm_sq is not None:
+        gnorm_sq += float((G.double() ** 2).sum())
