@@ -265,3 +265,32 @@ def test_any_torch_optimizer_host_flow_equals_reference(ref, name, opt, okw, lr,
                 self.neg_indices_ = raw + (raw >= torch.arange(n).unsqueeze(1)).long()
     Ze = cls(**common).fit_transform(X)
     assert torch.equal(Ze, Zr), float((Ze - Zr).abs().max())
+
+
+def test_eval_metrics_host_flow_equals_reference(ref, monkeypatch):
+    """neighborhood_preservation / knn_label_accuracy (torchdr/eval): same values as the reference's CPU evaluation,
+    per sample, through the engine's seams on the CPU stand-ins."""
+    import fake_ops
+    from torchdr.eval import knn_label_accuracy as ref_acc
+    from torchdr.eval import neighborhood_preservation as ref_np
+
+    import torchdr_b200 as tb
+    from torchdr_b200 import eval as tb_eval
+
+    fake_ops.install(monkeypatch)
+    fake_ops.install_entropic(monkeypatch)
+    monkeypatch.setattr(tb_eval, "_to_device_tensor", lambda X, device="auto": torch.as_tensor(X))
+    n = 240
+    X = _data(n, 14, 51)
+    Z = torch.randn(n, 2, generator=torch.Generator().manual_seed(2)) + X[:, :2]
+    labels = torch.randint(0, 4, (n,), generator=torch.Generator().manual_seed(3))
+    for K in (5, 20):
+        a = tb.neighborhood_preservation(X, Z, K=K, return_per_sample=True)
+        b = ref_np(X, Z, K=K, backend=None, device="cpu", return_per_sample=True)
+        assert torch.equal(a, b)
+        assert float(tb.neighborhood_preservation(X, Z, K=K)) == float(ref_np(X, Z, K=K, backend=None, device="cpu"))
+    for k in (1, 10):
+        a = tb.knn_label_accuracy(X, labels, k=k, return_per_sample=True)
+        b = ref_acc(X, labels, k=k, backend=None, device="cpu", return_per_sample=True)
+        assert torch.equal(a, b)
+    assert isinstance(tb.neighborhood_preservation(X.numpy(), Z.numpy(), K=5), float)
