@@ -103,8 +103,26 @@ def umap_run(Z_a, Z_b, rowptr, col, eps, eons, n_iter0, lrs, a, b, n_neg=75, rat
 
 # ---- entropic-affinity estimators (LargeVis, TSNE): gradients by autograd of the oracle's losses, as in the reference
 def knn(Xq, Xdb, k, q_row0=0, exclude_self=True, metric="sqeuclidean"):
-    assert Xq.shape[0] == Xdb.shape[0] and q_row0 == 0
-    return oracle.knn_dense(Xdb, k, metric, exclude_self)
+    if Xq is Xdb or (Xq.shape == Xdb.shape and Xq.data_ptr() == Xdb.data_ptr()):
+        return oracle.knn_dense(Xdb, k, metric, exclude_self)
+    # cross / chunk queries: distance/torch.py:81-122 on (Xq, Xdb), self excluded by global id
+    C = oracle.pairwise_full(Xq, Xdb, metric)
+    if exclude_self:
+        r = torch.arange(Xq.shape[0])
+        C[r, r + q_row0] += 1e12
+    v, i = C.topk(k, dim=1, largest=False)
+    return v, i.int()
+
+
+def pairwise_full(X, Y=None, metric="sqeuclidean", exclude_diag=False):
+    return oracle.pairwise_full(X, Y, metric, exclude_diag)
+
+
+def indexed_distances(X, key_idx, Y=None, query_idx=None, metric="sqeuclidean"):
+    Y = X if Y is None else Y
+    Xq = X if query_idx is None else X[query_idx.long()]
+    D = torch.sum((Xq.unsqueeze(1) - Y[key_idx.long()]) ** 2, dim=-1)  # distance/base.py:384-385
+    return D.sqrt() if metric == "euclidean" else D
 
 
 def entropic_affinity_rows(C, target_entropy, log_n_total, bounds=None, max_iter=100):
@@ -172,7 +190,8 @@ def sne_grad(Z, row0, n_local, Pm, idx, lam, repulsion, phase, grad, row_sums):
 def install_entropic(monkeypatch):
     from torchdr_b200 import ops
 
-    for name, fn in (("knn", knn), ("entropic_affinity_rows", entropic_affinity_rows), ("largevis_grad", largevis_grad),
+    for name, fn in (("knn", knn), ("pairwise_full", pairwise_full), ("indexed_distances", indexed_distances),
+                     ("entropic_affinity_rows", entropic_affinity_rows), ("largevis_grad", largevis_grad),
                      ("tsne_workspace", tsne_workspace), ("tsne_grad", tsne_grad), ("infotsne_grad", infotsne_grad),
                      ("sne_grad", sne_grad), ("sgd_momentum", sgd_momentum)):
         monkeypatch.setattr(ops, name, fn)

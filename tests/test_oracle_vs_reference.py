@@ -294,3 +294,44 @@ def test_eval_metrics_host_flow_equals_reference(ref, monkeypatch):
         b = ref_acc(X, labels, k=k, backend=None, device="cpu", return_per_sample=True)
         assert torch.equal(a, b)
     assert isinstance(tb.neighborhood_preservation(X.numpy(), Z.numpy(), K=5), float)
+
+
+def test_distance_seams_equal_reference(ref, monkeypatch):
+    """`pairwise_distances` / `pairwise_distances_indexed` with the reference's signature: every argument combination
+    the path uses returns what the reference's backend=None call returns (values, index dtype, the (C, None) rule for
+    k >= n, error messages) — the engine's dispatch on the CPU stand-ins."""
+    import fake_ops
+    from torchdr.distance import pairwise_distances as ref_pd
+    from torchdr.distance import pairwise_distances_indexed as ref_pdi
+
+    import torchdr_b200 as tb
+
+    fake_ops.install(monkeypatch)
+    fake_ops.install_entropic(monkeypatch)
+    X, Y = _data(120, 7, 61), _data(90, 7, 62)
+    for metric in ("sqeuclidean", "euclidean"):
+        assert torch.equal(tb.pairwise_distances(X, metric=metric), ref_pd(X, metric=metric, backend=None))
+        assert torch.equal(tb.pairwise_distances(X, Y, metric=metric), ref_pd(X, Y, metric=metric, backend=None))
+        assert torch.equal(tb.pairwise_distances(X, metric=metric, exclude_diag=True),
+                           ref_pd(X, metric=metric, backend=None, exclude_diag=True))
+        for k in (1, 15):
+            C, I = tb.pairwise_distances(X, metric=metric, k=k, exclude_diag=True, return_indices=True)
+            Cr, Ir = ref_pd(X, metric=metric, backend=None, k=k, exclude_diag=True, return_indices=True)
+            assert torch.equal(C, Cr) and torch.equal(I, Ir) and I.dtype == Ir.dtype
+            C, I = tb.pairwise_distances(X, Y, metric=metric, k=k, return_indices=True)
+            Cr, Ir = ref_pd(X, Y, metric=metric, backend=None, k=k, return_indices=True)
+            assert torch.equal(C, Cr) and torch.equal(I, Ir)
+        C, I = tb.pairwise_distances(X, metric=metric, k=500, return_indices=True)  # k >= n: full matrix, no indices
+        Cr, Ir = ref_pd(X, metric=metric, backend=None, k=500, return_indices=True)
+        assert I is None and Ir is None and torch.equal(C, Cr)
+    for fn in (tb.pairwise_distances, lambda *a, **k: ref_pd(*a, backend=None, **k)):
+        with pytest.raises(ValueError, match="distance is not supported"):
+            fn(X, metric="chebyshev")
+    Z = torch.randn(120, 2, generator=torch.Generator().manual_seed(1))
+    key = torch.randint(0, 120, (120, 9), generator=torch.Generator().manual_seed(2))
+    q = torch.randperm(120, generator=torch.Generator().manual_seed(3))[:50]
+    for metric in ("sqeuclidean", "euclidean"):
+        assert torch.equal(tb.pairwise_distances_indexed(Z, key_indices=key, metric=metric),
+                           ref_pdi(Z, key_indices=key, metric=metric, backend=None))
+        assert torch.equal(tb.pairwise_distances_indexed(Z, query_indices=q, key_indices=key[:50], metric=metric),
+                           ref_pdi(Z, query_indices=q, key_indices=key[:50], metric=metric, backend=None))
