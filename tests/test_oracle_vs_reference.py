@@ -335,3 +335,36 @@ def test_distance_seams_equal_reference(ref, monkeypatch):
                            ref_pdi(Z, key_indices=key, metric=metric, backend=None))
         assert torch.equal(tb.pairwise_distances_indexed(Z, query_indices=q, key_indices=key[:50], metric=metric),
                            ref_pdi(Z, query_indices=q, key_indices=key[:50], metric=metric, backend=None))
+
+
+def test_affinity_seams_equal_reference(ref, monkeypatch):
+    """`UMAPAffinity` / `EntropicAffinity` called like the reference's classes (affinity/base.py:407-561): return
+    values, index dtypes and padding, and the fitted attributes the neighbor-embedding driver reads."""
+    import fake_ops
+    from torchdr.affinity import EntropicAffinity as RefEA
+    from torchdr.affinity import UMAPAffinity as RefUA
+
+    import torchdr_b200 as tb
+
+    fake_ops.install(monkeypatch)
+    fake_ops.install_entropic(monkeypatch)
+    X = _data(210, 11, 71)
+    ra = RefUA(n_neighbors=12, max_iter=100, backend=None, device="cpu")
+    Vr, Ir = ra(X, return_indices=True)
+    a = tb.UMAPAffinity(n_neighbors=12, max_iter=100)
+    V, I = a(X, return_indices=True)
+    assert torch.equal(V, Vr) and torch.equal(I, Ir) and I.dtype == Ir.dtype
+    assert torch.equal(a.rho_.reshape(-1), ra.rho_.reshape(-1)) and torch.equal(a.eps_.reshape(-1), ra.eps_.reshape(-1))
+    assert torch.equal(tb.UMAPAffinity(n_neighbors=12)(X, return_indices=False), RefUA(n_neighbors=12, backend=None, device="cpu")(X, return_indices=False))
+    rn = RefUA(n_neighbors=12, max_iter=100, backend=None, device="cpu", symmetrize=False)(X, return_indices=True)
+    en = tb.UMAPAffinity(n_neighbors=12, max_iter=100, symmetrize=False)(X, return_indices=True)
+    assert torch.equal(en[0], rn[0]) and torch.equal(en[1].long(), rn[1].long())
+    re_ = RefEA(perplexity=9, max_iter=100, backend=None, device="cpu")
+    ee = tb.EntropicAffinity(perplexity=9, max_iter=100)
+    for log in (True, False):
+        Pr, Jr = re_(X, log=log, return_indices=True)
+        P, J = ee(X, log=log, return_indices=True)
+        assert torch.equal(P, Pr) and torch.equal(J, Jr) and J.dtype == Jr.dtype
+    assert torch.equal(ee.eps_.reshape(-1), re_.eps_.reshape(-1))
+    assert ee.log_normalization_.shape == re_.log_normalization_.shape
+    assert torch.equal(ee.log_normalization_, re_.log_normalization_)
