@@ -368,3 +368,34 @@ def test_affinity_seams_equal_reference(ref, monkeypatch):
     assert torch.equal(ee.eps_.reshape(-1), re_.eps_.reshape(-1))
     assert ee.log_normalization_.shape == re_.log_normalization_.shape
     assert torch.equal(ee.log_normalization_, re_.log_normalization_)
+
+
+def test_pca_init_matches_reference_init(ref, monkeypatch):
+    """init="pca" (the estimators' default): the engine's covariance + eigh route against the reference's own
+    initialisation (full-SVD PCA with svd_flip, then 1e-4 / std rescale, affinity_matcher.py:535-550), captured from a
+    live fit.  Same subspace and sign convention; fp32 round-off of two different factorisations apart."""
+    import fake_ops
+    import torchdr
+    from helpers import rel_fro
+
+    import torchdr_b200 as tb
+
+    X = _data(400, 20, 81)
+    got = {}
+
+    def capture(base, tag):
+        class Cap(base):
+            def on_training_step_start(self):
+                if int(self.n_iter_) == 0:
+                    got[tag] = self.embedding_.detach().clone()
+                super().on_training_step_start()
+
+        return Cap
+
+    capture(torchdr.UMAP, "ref")(n_neighbors=10, max_iter=1, init="pca", backend=None, device="cpu", random_state=0,
+                                 process_duplicates=False).fit_transform(X)
+    fake_ops.install(monkeypatch)
+    capture(tb.UMAP, "eng")(n_neighbors=10, max_iter=1, init="pca", random_state=0,
+                            process_duplicates=False).fit_transform(X)
+    assert rel_fro(got["eng"], got["ref"]) < 1e-4
+    torch.testing.assert_close(got["eng"][:, 0].std(), torch.tensor(1e-4), rtol=1e-4, atol=0)
