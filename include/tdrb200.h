@@ -191,10 +191,10 @@ TDR_API int tdr_umap_compact_f32(const int64_t* rowptr, const int32_t* col, cons
  * SGD update z -= lr*g (affinity_matcher.py:427; plain SGD, umap.py:139).
  * Jacobi: reads Z_in (all N rows), writes Z_out[row0..] (may not alias Z_in).
  * neg: int64 [n_local, n_neg] adjusted negatives (NE base.py:629-636) or NULL to
- * draw them in-kernel with Philox4x32-10 keyed by (seed, n_iter, global row).
+ * draw them in-kernel with Philox4x32-7 keyed by (seed, n_iter, global row, slot / 4).
  * a, b are the python doubles of umap.py:19-36 (the kernel derives the fp32 constants
  * (float)a, (float)b, (float)(b-1), (float)(2ab), (float)(-2b) exactly as the torch ops do).
- * precise != 0 evaluates pow in fp64 (parity mode).
+ * precise = 1 evaluates pow in fp64, one warp per row (parity mode); 0 = throughput kernel.
  * grad_out (nullable) [n_local,2] receives the gradient; gnorm_sq (nullable,
  * device double) accumulates ||g||^2; nan_flag (nullable, device int) is set
  * if a NaN is written (check_NaNs, affinity_matcher.py:315); stats (nullable, device
@@ -208,8 +208,15 @@ TDR_API int tdr_umap_step_f32(const float* Z_in, float* Z_out, int64_t n_total, 
                       int precise, float* grad_out, double* gnorm_sq, int* nan_flag,
                       uint64_t* stats, tdr_stream_t stream);
 
-/* n_steps single-GPU iterations ping-ponging Z_a <-> Z_b (in-kernel negatives);
- * lrs is a HOST array [n_steps].  The result is in Z_a if n_steps is even, else Z_b. */
+/* n_steps single-GPU iterations ping-ponging Z_a <-> Z_b (in-kernel negatives) in ONE persistent
+ * cooperative launch per 128 iterations: the iterations are separated by a grid barrier inside the
+ * kernel.  lrs is a HOST array [n_steps].  The result is in Z_a if n_steps is even, else Z_b.
+ * sync_words: caller-owned device buffer of TDR_RUN_SYNC_WORDS uint32, zero-initialised once and
+ * reused by every call on the same embedding (barrier counters, work counters, status word
+ * sync_words[TDR_RUN_STATUS_WORD]: 0 = ok); epoch0 = total number of iterations already run on
+ * this sync buffer.  precise != 0 runs the parity kernel with one launch per iteration. */
+#define TDR_RUN_SYNC_WORDS 8
+#define TDR_RUN_STATUS_WORD 4
 TDR_API int tdr_umap_run_f32(float* Z_a, float* Z_b, int64_t n_total,
                      const int64_t* rowptr, const int32_t* col,
                      const float* epochs_per_sample, float* epoch_of_next_sample,
@@ -217,14 +224,13 @@ TDR_API int tdr_umap_run_f32(float* Z_a, float* Z_b, int64_t n_total,
                      int n_steps, const float* lrs_host,
                      double a, double b, float lam, float repulsion,
                      int precise, double* gnorm_sq, int* nan_flag, uint64_t* stats,
-                     tdr_stream_t stream);
+                     uint32_t* sync_words, uint32_t epoch0, tdr_stream_t stream);
 
-/* Fused step + exchange for the row-sharded multi-GPU loop: same iteration as tdr_umap_step_f32
- * (throughput kernel, in-kernel negatives), but every updated row is additionally stored into
- * the Z_out buffer of each peer GPU through NVLink peer mappings (peer_out_ptrs: HOST array of
- * n_peers <= 8 device addresses, e.g. torch symmetric-memory buffer_ptrs without this rank's
- * own).  Replaces the per-iteration collective of affinity_matcher.py:395-413; the caller only
- * needs a cross-GPU barrier before the next iteration reads the buffers. */
+/* Fused step + exchange for the row-sharded multi-GPU loop, one launch per iteration: same iteration
+ * as tdr_umap_step_f32 (throughput kernel, in-kernel negatives), but every updated row is additionally
+ * stored into the Z_out buffer of each peer GPU through NVLink peer mappings (peer_out_ptrs: HOST
+ * array of n_peers <= 8 device addresses, e.g. torch symmetric-memory buffer_ptrs without this
+ * rank's own).  The caller provides the cross-GPU barrier before the next iteration reads the buffers. */
 TDR_API int tdr_umap_step_p2p_f32(const float* Z_in, float* Z_out, int64_t n_total, int64_t row0, int64_t n_local,
                                   const int64_t* rowptr, const int32_t* col,
                                   const float* epochs_per_sample, float* epoch_of_next_sample,
@@ -233,22 +239,28 @@ TDR_API int tdr_umap_step_p2p_f32(const float* Z_in, float* Z_out, int64_t n_tot
                                   double* gnorm_sq, int* nan_flag,
                                   const uint64_t* peer_out_ptrs, int n_peers, tdr_stream_t stream);
 
-/* n_steps sharded iterations without returning to the host language: step kernel with fused peer
- * stores (above) + a one-warp barrier kernel on peer-mapped flags between iterations.  Z_a/Z_b are this
- * rank's two embedding buffers, peers_a/peers_b the peers' addresses of the same two buffers (HOST
- * arrays, n_peers = world - 1 entries, ranks ascending without this rank); my_flags is this rank's
- * zero-initialised uint32[world] flag buffer and peer_flags the peers' addresses of theirs; epoch0 is
- * the number of barriers already executed on these flags.  Result in Z_a if n_steps is even. */
+/* n_steps row-sharded iterations in ONE persistent cooperative launch per 128 iterations — step, exchange
+ * and barrier in the same kernel (replaces the per-iteration collective of affinity_matcher.py:395-413):
+ * every updated row is stored into the destination buffer of this rank AND of each NVLink peer; at the end
+ * of an iteration the last CTA of the rank announces it in the peers' flag words (st.release.sys) and waits
+ * for theirs (ld.acquire.sys) before it releases the local grid barrier.  Z_a/Z_b are this rank's two
+ * embedding buffers, peers_a/peers_b the peers' addresses of the same two buffers (HOST arrays,
+ * n_peers = world - 1 entries, ranks ascending without this rank); my_flags is this rank's zero-initialised
+ * uint32[world] flag buffer and peer_flags the peers' addresses of theirs; sync_words / epoch0 as in
+ * tdr_umap_run_f32 (epoch0 must be the same on every rank).  A peer that does not arrive within timeout_s
+ * seconds (<= 0: 60 s) aborts the run on this rank: sync_words[TDR_RUN_STATUS_WORD] becomes 1 (2 = a local
+ * CTA was missing) and the kernel exits instead of spinning forever; the buffers are then undefined.
+ * Result in Z_a if n_steps is even. */
 TDR_API int tdr_umap_run_p2p_f32(float* Z_a, float* Z_b, int64_t n_total, int64_t row0, int64_t n_local,
                                  const int64_t* rowptr, const int32_t* col,
                                  const float* epochs_per_sample, float* epoch_of_next_sample,
                                  int n_neg, int negative_sample_rate, uint64_t seed, int64_t n_iter0,
                                  int n_steps, const float* lrs_host,
                                  double a, double b, float lam, float repulsion,
-                                 double* gnorm_sq, int* nan_flag,
+                                 double* gnorm_sq, int* nan_flag, uint64_t* stats, uint32_t* sync_words,
                                  const uint64_t* peers_a, const uint64_t* peers_b,
                                  uint32_t* my_flags, const uint64_t* peer_flags, int n_peers,
-                                 int rank, int world, uint32_t epoch0, tdr_stream_t stream);
+                                 int rank, int world, uint32_t epoch0, double timeout_s, tdr_stream_t stream);
 
 /* LargeVis gradient (largevis.py:181-201 differentiated): accumulates into
  * grad[n_total,2] (zeroed by the caller) with atomics — the autograd scatter of

@@ -89,7 +89,7 @@ def umap_step(Z_in, Z_out, row0, n_local, rowptr, col, eps, eons, n_iter, a, b, 
 
 
 def umap_run(Z_a, Z_b, rowptr, col, eps, eons, n_iter0, lrs, a, b, n_neg=75, rate=5, seed=0, lam=1.0, repulsion=1.0,
-             precise=False, gnorm_sq=None, nan_flag=None, stats=None):
+             precise=False, gnorm_sq=None, nan_flag=None, stats=None, sync=None):
     g = torch.Generator().manual_seed(int(seed) * 7919 + int(n_iter0))
     src, dst = Z_a, Z_b
     n = Z_a.shape[0]
@@ -199,9 +199,11 @@ def install_entropic(monkeypatch):
 
 # ---- row-sharded stand-ins (world_size > 1 under gloo): same semantics as the CUDA entry points for a row chunk
 def install_sharded(monkeypatch):
-    from torchdr_b200 import ops
+    from torchdr_b200 import distributed, neighbor_embedding, ops
 
     monkeypatch.setattr(torch.cuda, "set_device", lambda *a, **k: None)
+    # the real sharded upload (own rows copied, the rest all-gathered), on CPU tensors over gloo
+    monkeypatch.setattr(neighbor_embedding, "upload_sharded", lambda X, device: distributed.upload_sharded(X, "cpu"))
     for name, fn in (("knn_umap_fused", knn_umap_fused_chunk), ("symmetrize_export", symmetrize_export),
                      ("symmetrize_csr", symmetrize_csr_chunk), ("umap_step", umap_step_chunk)):
         monkeypatch.setattr(ops, name, fn)

@@ -18,6 +18,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libtdrb200.so")
 TDR_OK = 0
 TDR_E_INVALID = -1
 TDR_MAX_K = 160
+TDR_RUN_SYNC_WORDS = 8
+TDR_RUN_STATUS_WORD = 4
 METRIC_IDS = {"sqeuclidean": 0, "euclidean": 1}
 
 P = c_void_p  # every device pointer
@@ -52,14 +54,15 @@ SIGNATURES = {
     "tdr_umap_step_f32": (c_int, [P, P, c_int64, c_int64, c_int64, P, P, P, P, P, c_int, c_int, c_uint64, c_int64,
                                   c_double, c_double, c_float, c_float, c_float, c_int, P, P, P, P, P]),
     "tdr_umap_run_f32": (c_int, [P, P, c_int64, P, P, P, P, c_int, c_int, c_uint64, c_int64, c_int,
-                                 ctypes.POINTER(c_float), c_double, c_double, c_float, c_float, c_int, P, P, P, P]),
+                                 ctypes.POINTER(c_float), c_double, c_double, c_float, c_float, c_int, P, P, P, P,
+                                 ctypes.c_uint32, P]),
     "tdr_umap_step_p2p_f32": (c_int, [P, P, c_int64, c_int64, c_int64, P, P, P, P, c_int, c_int, c_uint64, c_int64,
                                       c_double, c_double, c_float, c_float, c_float, P, P,
                                       ctypes.POINTER(c_uint64), c_int, P]),
     "tdr_umap_run_p2p_f32": (c_int, [P, P, c_int64, c_int64, c_int64, P, P, P, P, c_int, c_int, c_uint64, c_int64, c_int,
-                                     ctypes.POINTER(c_float), c_double, c_double, c_float, c_float, P, P,
+                                     ctypes.POINTER(c_float), c_double, c_double, c_float, c_float, P, P, P, P,
                                      ctypes.POINTER(c_uint64), ctypes.POINTER(c_uint64), P, ctypes.POINTER(c_uint64),
-                                     c_int, c_int, c_int, ctypes.c_uint32, P]),
+                                     c_int, c_int, c_int, ctypes.c_uint32, c_double, P]),
     "tdr_largevis_grad_f32": (c_int, [P, c_int64, c_int64, c_int64, P, P, c_int, P, c_int, c_uint64, c_int64,
                                       c_float, c_float, P, P]),
     "tdr_tsne_workspace_bytes": (c_size_t, [c_int64]),

@@ -21,7 +21,7 @@ import torch.distributed as dist
 from . import _lib, ops
 from .affinity import EntropicAffinity, UMAPAffinity
 from .distance import _to_device_tensor
-from .distributed import PeerEmbedding, all_bounds, all_gather_rows, is_distributed
+from .distributed import PeerEmbedding, all_bounds, all_gather_rows, is_distributed, upload_sharded
 
 
 def find_ab_params(spread, min_dist):
@@ -156,10 +156,15 @@ class _NeighborEmbeddingB200:
             self.timings_, self._t_last = {}, time.perf_counter()
         was_numpy = isinstance(X, np.ndarray)
         in_device = X.device if isinstance(X, torch.Tensor) else None
-        Xd = _to_device_tensor(X, self.device)
-        if Xd.dtype != torch.float32:
-            Xd = Xd.float()
-        Xd = Xd.contiguous()
+        host_input = was_numpy or (isinstance(X, torch.Tensor) and X.device.type == "cpu")
+        if self.world_size > 1 and host_input and getattr(X, "ndim", 0) == 2:
+            # row-sharded fit on host input: each rank uploads its own row chunk, NVLink all-gather builds the database
+            Xd = upload_sharded(torch.from_numpy(X) if was_numpy else X, self.device)
+        else:
+            Xd = _to_device_tensor(X, self.device)
+            if Xd.dtype != torch.float32:
+                Xd = Xd.float()
+            Xd = Xd.contiguous()
         self._tick("h2d")
         if not bool(torch.isfinite(Xd).all()):
             raise ValueError("[TorchDR] ERROR : input contains NaN or infinite values.")
@@ -374,6 +379,10 @@ class _NeighborEmbeddingB200:
         return self.embedding_
 
     def _check_nan(self, step):
+        """check_NaNs of affinity_matcher.py:315-319.  Row-sharded runs agree on the flag first (MAX over ranks): a
+        rank that alone saw a NaN must not leave its peers waiting in the next iteration's exchange."""
+        if self.world_size > 1:
+            dist.all_reduce(self._nan, op=dist.ReduceOp.MAX)
         if int(self._nan.item()):
             raise ValueError(f"[TorchDR] ERROR AffinityMatcher : NaNs in the embeddings at iter {step}.")
 
@@ -513,39 +522,42 @@ class UMAP(_NeighborEmbeddingB200):
 
     def _loop(self):
         rowptr, col, eps, eons = self._graph
-        n = self.n_samples_in_
         s, e = self.chunk_start_, self.chunk_end_
         Za = self.embedding_
-        Zb = Za.clone()
         seed = int(self._actual_seed) if self.random_state is not None else int(torch.initial_seed() % (2**63))
-        lam, rep = float(self.early_exaggeration_coeff_), float(self.repulsion_strength)
+        rep = float(self.repulsion_strength)
         if not self._native_opt or self._hyper()[1] != 0.0:
             # the step kernel fuses plain SGD (umap.py:139, the default); anything else takes the gradient from the
             # kernel and lets the reference's optimiser object apply it (affinity_matcher.py:395-413)
-            return self._loop_generic_optimizer(seed, lam, rep)
+            return self._loop_generic_optimizer(seed, rep)
         self._last_step = -1
         step = 0
         stop = False
         hooks_per_step = type(self).on_training_step_start is not UMAP.on_training_step_start or \
             type(self).on_training_step_end is not _NeighborEmbeddingB200.on_training_step_end or \
             getattr(self, "negative_exclusion_indices_", None) is not None
-        # multi-GPU: fused step + exchange over NVLink peer stores (PeerEmbedding) when symmetric memory is
-        # available, else one NCCL all-gather per iteration
+        # Batched branches run a whole check_interval of iterations in ONE persistent kernel launch
+        # (tdr_umap_run_f32 / tdr_umap_run_p2p_f32); row-sharded, the kernel also stores the updated rows into every
+        # peer over NVLink and runs the per-iteration barrier itself (PeerEmbedding).  Per-step branch: hooks that
+        # must run between iterations, injected negatives, the fp64 parity kernel, or no symmetric memory (then one
+        # NCCL all-gather per iteration).
         peer, cur = None, 0
         self.exchange_ = "none" if self.world_size == 1 else "nccl-allgather"
         if self.world_size > 1 and not hooks_per_step and not self.precise and os.environ.get("TDR_NO_P2P") != "1":
             try:
-                peer = PeerEmbedding(Za)
+                peer = PeerEmbedding.get(Za)
                 Za, Zb = peer.bufs[0], peer.bufs[1]
                 self.exchange_ = "p2p-fused"
             except Exception as exc:  # symmetric memory unavailable on this system
                 self.logger.warning(f"symmetric memory unavailable ({exc}); falling back to NCCL all-gather")
                 peer = None
+        if peer is None:
+            Zb = Za.clone()
+        sync = peer.sync if peer is not None else ops.RunSync(Za.device)
         # Learning rates come from the reference's own optimizer / scheduler objects (~25 us of host time per step).
         # In the batched branches they are produced one batch AHEAD, after the current batch has been launched and
-        # before its convergence check synchronises, so the bookkeeping overlaps the kernels instead of idling the GPU
-        # (22 ms of a 135 ms loop at 1 M points).  A batch that never runs leaves the objects advanced: harmless,
-        # they are discarded after the fit.
+        # before its convergence check synchronises, so the bookkeeping overlaps the kernels instead of idling the GPU.
+        # A batch that never runs leaves the objects advanced: harmless, they are discarded after the fit.
         lr_buf = []  # lr_buf[t] = learning rate of step t
 
         def lrs_for(a, b):
@@ -555,68 +567,73 @@ class UMAP(_NeighborEmbeddingB200):
             return lr_buf[a:b + 1]
 
         while step < self.max_iter and not stop:
-            # batch = steps up to (and including) the next one with n_iter % check_interval == 0
+            lam = float(self.early_exaggeration_coeff_)
+            # batch = steps up to (and including) the next one with n_iter % check_interval == 0 — or the last step
+            # of early exaggeration, after which the optimiser is rebuilt (NE base.py:282-295)
             nxt_check = step if step % self.check_interval == 0 else (step // self.check_interval + 1) * self.check_interval
             last = min(nxt_check, self.max_iter - 1)
+            exag_end = self.early_exaggeration_coeff_ > 1 and step <= self.early_exaggeration_iter <= last
+            if exag_end:
+                last = self.early_exaggeration_iter
             ahead = min(last + self.check_interval, self.max_iter - 1)
-            if peer is not None:
+            if self.early_exaggeration_coeff_ > 1 and last < self.early_exaggeration_iter:
+                ahead = min(ahead, self.early_exaggeration_iter)  # the optimiser is rebuilt there: no look-ahead past it
+            want = last % self.check_interval == 0
+            if want:
+                self._gnorm.zero_()
+            if peer is not None or not (self.world_size > 1 or hooks_per_step):
                 lrs = lrs_for(step, last)
-                want = last % self.check_interval == 0
-                if want:
-                    self._gnorm.zero_()
-                # one native call for the whole batch: step kernel (fused NVLink stores) + flag barrier per iteration
-                cur = ops.umap_run_p2p(peer, cur, s, e - s, rowptr, col, eps, eons, step, lrs, self._a, self._b,
+                if peer is not None:
+                    cur = ops.umap_run_p2p(peer, cur, s, e - s, rowptr, col, eps, eons, step, lrs, self._a, self._b,
+                                           n_neg=self.n_negatives, rate=self.negative_sample_rate, seed=seed, lam=lam,
+                                           repulsion=rep, gnorm_sq=self._gnorm if want else None, nan_flag=self._nan)
+                    Za, Zb = peer.bufs[cur], peer.bufs[1 - cur]
+                else:
+                    res = ops.umap_run(Za, Zb, rowptr, col, eps, eons, step, lrs, self._a, self._b,
                                        n_neg=self.n_negatives, rate=self.negative_sample_rate, seed=seed, lam=lam,
-                                       repulsion=rep, gnorm_sq=self._gnorm if want else None, nan_flag=self._nan)
-                if want:
-                    dist.all_reduce(self._gnorm, op=dist.ReduceOp.SUM)
-                Za, Zb = peer.bufs[cur], peer.bufs[1 - cur]
+                                       repulsion=rep, precise=self.precise, gnorm_sq=self._gnorm if want else None,
+                                       nan_flag=self._nan, sync=sync)
+                    if res is not Za:
+                        Za, Zb = Zb, Za
                 self.n_iter_ = torch.tensor(last, dtype=torch.long)
                 self.embedding_ = Za
-                lrs_for(last + 1, ahead)
-            elif self.world_size > 1 or hooks_per_step:
+                if not exag_end:
+                    lrs_for(last + 1, ahead)
+            else:
                 for t in range(step, last + 1):
                     self.n_iter_ = torch.tensor(t, dtype=torch.long)
                     self.on_training_step_start()
                     lr = self._hyper()[0]
-                    want = t == last and t % self.check_interval == 0
-                    if want:
-                        self._gnorm.zero_()
                     neg = getattr(self, "neg_indices_", None)
                     ops.umap_step(Za, Zb, s, e - s, rowptr, col, eps, eons, t, self._a, self._b, lr,
                                   neg=neg, n_neg=self.n_negatives, rate=self.negative_sample_rate, seed=seed, lam=lam,
-                                  repulsion=rep, precise=self.precise, gnorm_sq=self._gnorm if want else None,
-                                  nan_flag=self._nan)
+                                  repulsion=rep, precise=self.precise,
+                                  gnorm_sq=self._gnorm if (want and t == last) else None, nan_flag=self._nan)
                     if self.world_size > 1:
                         all_gather_rows(Zb, self._bounds, self.rank)
-                        if want:
-                            dist.all_reduce(self._gnorm, op=dist.ReduceOp.SUM)
                     Za, Zb = Zb, Za
                     self.embedding_ = Za
                     self._advance_schedule()
                     self.on_training_step_end()
-            else:
-                lrs = lrs_for(step, last)
-                want = last % self.check_interval == 0
-                if want:
-                    self._gnorm.zero_()
-                res = ops.umap_run(Za, Zb, rowptr, col, eps, eons, step, lrs, self._a, self._b,
-                                   n_neg=self.n_negatives, rate=self.negative_sample_rate, seed=seed, lam=lam,
-                                   repulsion=rep, precise=self.precise, gnorm_sq=self._gnorm if want else None,
-                                   nan_flag=self._nan)
-                if res is not Za:
-                    Za, Zb = Zb, Za
-                self.embedding_ = Za
-                lrs_for(last + 1, ahead)
+            if want and self.world_size > 1:
+                dist.all_reduce(self._gnorm, op=dist.ReduceOp.SUM)
             self._last_step = last
             step = last + 1
+            if peer is not None or self.world_size == 1:
+                sync.check()
             self._check_nan(last)
-            if last % self.check_interval == 0:
+            if exag_end:  # NE base.py:282-295: coefficient back to 1, fresh optimiser and scheduler
+                self.early_exaggeration_coeff_ = 1
+                self._set_learning_rate()
+                self._configure_optimizer()
+                self._configure_scheduler()
+                del lr_buf[step:]
+            if want:
                 stop = self._converged(last, float(self._gnorm.item()) ** 0.5)
-        self.embedding_ = Za.clone() if peer is not None else Za  # leave symmetric memory before it is released
+        self.embedding_ = Za.clone() if peer is not None else Za  # leave symmetric memory: the buffers are reused
 
 
-def _umap_loop_generic_optimizer(self, seed, lam, rep):
+def _umap_loop_generic_optimizer(self, seed, rep):
     """UMAP iterations with an arbitrary torch optimiser: gradient of the local rows from the step kernel
     (`grad_out`), zero-padded to N x 2 and summed over ranks as in affinity_matcher.py:395-413, then
     `optimizer_.step()` on the embedding; the kernel's own SGD output is scratch."""
@@ -641,10 +658,16 @@ def _umap_loop_generic_optimizer(self, seed, lam, rep):
             G.zero_()
         ops.umap_step(Z, scratch, s, e - s, rowptr, col, eps, eons, step, self._a, self._b, 0.0,
                       neg=getattr(self, "neg_indices_", None), n_neg=self.n_negatives, rate=self.negative_sample_rate,
-                      seed=seed, lam=lam, repulsion=rep, precise=self.precise, grad_out=G[s:e])
+                      seed=seed, lam=float(self.early_exaggeration_coeff_), repulsion=rep, precise=self.precise,
+                      grad_out=G[s:e])
         if self.world_size > 1:
             dist.all_reduce(G, op=dist.ReduceOp.SUM)
         self._generic_step(G, check)
+        if self.early_exaggeration_coeff_ > 1 and step == self.early_exaggeration_iter:  # NE base.py:282-295
+            self.early_exaggeration_coeff_ = 1
+            self._set_learning_rate()
+            self._configure_optimizer()
+            self._configure_scheduler()
         self.on_training_step_end()
         if check:
             self._check_nan(step)

@@ -261,9 +261,26 @@ def umap_step_p2p(Z_in, Z_out, row0, n_local, rowptr, col, eps, eons, n_iter, a,
               "tdr_umap_step_p2p_f32")
 
 
+class RunSync:
+    """Device words of the persistent step kernel's barriers (``sync_words`` of tdr_umap_run_f32): zero-initialised
+    once, reused by every call on the same embedding; ``epoch`` counts the iterations run on it."""
+
+    def __init__(self, device):
+        self.words = torch.zeros(_lib.TDR_RUN_SYNC_WORDS, dtype=torch.int32, device=device)
+        self.epoch = 0
+
+    def check(self):
+        """Host-side check of the status word (synchronises): a peer or a CTA that never reached a barrier."""
+        st = int(self.words[_lib.TDR_RUN_STATUS_WORD].item())
+        if st != 0:
+            who = "a peer GPU" if st == 1 else "a thread block of this GPU"
+            raise _lib.B200EngineError(f"[TorchDR-B200] the persistent UMAP loop was aborted: {who} did not reach the "
+                                       "iteration barrier within the time limit (is a rank dead?).")
+
+
 def umap_run_p2p(peer, cur, row0, n_local, rowptr, col, eps, eons, n_iter0, lrs, a, b, n_neg=75, rate=5, seed=0,
-                 lam=1.0, repulsion=1.0, gnorm_sq=None, nan_flag=None):
-    """len(lrs) sharded iterations in one native call (step kernel with fused peer stores + flag barrier).
+                 lam=1.0, repulsion=1.0, gnorm_sq=None, nan_flag=None, stats=None, timeout_s=60.0):
+    """len(lrs) sharded iterations in ONE persistent launch (step + NVLink peer stores + cross-GPU barrier in-kernel).
 
     ``peer`` is a distributed.PeerEmbedding, ``cur`` the index of the buffer holding the current embedding;
     returns the index of the buffer holding the result."""
@@ -275,24 +292,30 @@ def umap_run_p2p(peer, cur, row0, n_local, rowptr, col, eps, eons, n_iter0, lrs,
         check(_lib.load().tdr_umap_run_p2p_f32(ptr(Za), ptr(Zb), Za.shape[0], row0, n_local, ptr(rowptr), ptr(col),
                                                ptr(eps), ptr(eons), n_neg, rate, seed, n_iter0, n,
                                                lrs.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), float(a), float(b),
-                                               float(lam), float(repulsion), ptr(gnorm_sq), ptr(nan_flag), pa, pb,
-                                               ptr(peer.flags), peer.flag_ptr_array, peer.world - 1, peer.rank, peer.world,
-                                               peer.epoch, stream()), "tdr_umap_run_p2p_f32")
-    peer.epoch += n
+                                               float(lam), float(repulsion), ptr(gnorm_sq), ptr(nan_flag), ptr(stats),
+                                               ptr(peer.sync.words), pa, pb, ptr(peer.flags), peer.flag_ptr_array,
+                                               peer.world - 1, peer.rank, peer.world, peer.sync.epoch % (1 << 32),
+                                               float(timeout_s), stream()), "tdr_umap_run_p2p_f32")
+    peer.sync.epoch += n
     return cur if n % 2 == 0 else 1 - cur
 
 
 def umap_run(Z_a, Z_b, rowptr, col, eps, eons, n_iter0, lrs, a, b, n_neg=75, rate=5, seed=0, lam=1.0,
-             repulsion=1.0, precise=False, gnorm_sq=None, nan_flag=None, stats=None):
-    """len(lrs) iterations on one GPU; returns the tensor holding the result."""
+             repulsion=1.0, precise=False, gnorm_sq=None, nan_flag=None, stats=None, sync=None):
+    """len(lrs) iterations on one GPU (one persistent launch); returns the tensor holding the result.
+    ``sync``: a RunSync kept by the caller across calls (a fresh one is made when omitted)."""
     lrs = np.ascontiguousarray(lrs, dtype=np.float32)
     n = len(lrs)
+    if sync is None:
+        sync = RunSync(Z_a.device)
     with torch.cuda.device(Z_a.device):
         check(_lib.load().tdr_umap_run_f32(ptr(Z_a), ptr(Z_b), Z_a.shape[0], ptr(rowptr), ptr(col), ptr(eps),
                                            ptr(eons), n_neg, rate, seed, n_iter0, n,
                                            lrs.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), float(a), float(b),
                                            float(lam), float(repulsion), int(precise), ptr(gnorm_sq), ptr(nan_flag),
-                                           ptr(stats), stream()), "tdr_umap_run_f32")
+                                           ptr(stats), ptr(sync.words), sync.epoch % (1 << 32), stream()),
+              "tdr_umap_run_f32")
+    sync.epoch += n
     return Z_a if n % 2 == 0 else Z_b
 
 
