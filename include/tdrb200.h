@@ -12,8 +12,9 @@
  *     from tdr_last_error() (thread-local);
  *   - the library allocates nothing: scratch comes from a caller-provided
  *     workspace whose size the *_workspace_bytes twin reports;
- *   - no torch types, no global state, no NCCL dependency (collectives stay
- *     in the host language, torch.distributed).
+ *   - no torch types, no NCCL dependency (collectives stay in the host language,
+ *     torch.distributed), and no global state: every option is a per-call argument;
+ *     the only process-wide datum is the thread-local error string.
  */
 #ifndef TDRB200_H
 #define TDRB200_H
@@ -59,27 +60,32 @@ TDR_API int tdr_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * first.  Xq are rows [q_row0, q_row0+nq) of the database when exclude_self
  * (the distributed chunk of distance/base.py:184-186). */
 TDR_API size_t tdr_knn_workspace_bytes(int64_t nq, int64_t ndb, int d, int k);
+
+/* Per-call options of the two kNN entry points (no process-wide switches):
+ * path   kernel selection: AUTO = tcgen05 tensor-core kernel (fp16 hi/lo split) whenever the tile shapes fit
+ *        (d <= 128 and lists + tiles <= 227 KB of shared memory: k <= 33 at d = 128, k <= 96 at d <= 64), else
+ *        the fp32 SIMT kernel; SIMT / TC force one (TC returns TDR_E_UNSUPPORTED if the shape does not fit).
+ * prune  tile-pruned sweep of the tensor-core kernel (queries that are rows of the database, >= 64 database
+ *        tiles): database tiles whose bounding box is farther from the query tile's box than a bound on the
+ *        tile's k-th neighbour distances are not swept.  Results are bit-identical to the full sweep.
+ *        OFF = sweep every tile; ON (= DEFAULT); CERTIFIED = thresholds that ignore outlier rows, then a
+ *        certification pass and a second sweep of the uncertified query tiles — for inputs that were brought
+ *        into a locality-creating order first (torchdr_b200/reorder.py), also bit-identical.
+ * sweep_stats  optional device pointer to two uint64 counters, [0] += tiles swept, [1] += tiles a full sweep
+ *        would visit (summed over query tiles); NULL disables them. */
+#define TDR_KNN_PATH_AUTO 0
+#define TDR_KNN_PATH_SIMT 1
+#define TDR_KNN_PATH_TC 2
+#define TDR_KNN_PRUNE_DEFAULT (-1)
+#define TDR_KNN_PRUNE_OFF 0
+#define TDR_KNN_PRUNE_ON 1
+#define TDR_KNN_PRUNE_CERTIFIED 2
 TDR_API int tdr_knn_f32(const float* Xq, int64_t nq, int64_t q_row0,
                 const float* Xdb, int64_t ndb, int d, int k,
                 int exclude_self, int metric,
                 float* out_dist /*[nq,k]*/, int32_t* out_idx /*[nq,k]*/,
+                int path, int prune, uint64_t* sweep_stats,
                 void* ws, size_t ws_bytes, tdr_stream_t stream);
-
-/* Kernel selection for the two kNN entry points: 0 = auto, 1 = fp32 SIMT kernel,
- * 2 = tcgen05 tensor-core kernel (fp16 hi/lo split, d <= 128, lists + tiles <= 227 KB of shared memory:
- * k <= 33 at d = 128, k <= 96 at d <= 64).  Process-wide; meant
- * for tests and profiling.  The environment variable TDR_KNN_PATH seeds it at load time. */
-TDR_API int tdr_knn_set_path(int path);
-
-/* Tile-pruned sweep of the tensor-core kNN (queries that are rows of the database, >= 64 database tiles):
- * database tiles whose bounding box is farther from the query tile's box than a bound on the tile's k-th
- * neighbour distances are not swept.  Results are bit-identical to the full sweep.  on = 1 (default; the
- * environment variable TDR_KNN_PRUNE seeds it) / 0; on = 2 is EXPERIMENTAL (not yet verified on hardware):
- * thresholds that ignore outlier rows, then a certification pass and a second sweep of the uncertified query
- * tiles.  sweep_stats: optional device pointer to two uint64
- * counters, [0] += tiles swept, [1] += tiles a full sweep would visit (per kNN call, summed over query tiles);
- * null disables the counters.  Process-wide. */
-TDR_API int tdr_knn_set_prune(int on, uint64_t* sweep_stats);
 
 /* Full matrix C[n,m] (k=None path, distance/torch.py:81-116).  Y may equal X.
  * Workspace: tdr_knn_workspace_bytes(n, m, d, 1). */
@@ -134,6 +140,7 @@ TDR_API int tdr_knn_umap_fused_f32(const float* Xq, int64_t nq, int64_t q_row0,
                            int exclude_self, int max_iter,
                            float* out_dist /*[nq,k] or NULL*/, int32_t* out_idx /*[nq,k]*/,
                            float* P /*[nq,k]*/, float* rho /*[nq]*/, float* sigma /*[nq]*/,
+                           int path, int prune, uint64_t* sweep_stats,
                            void* ws, size_t ws_bytes, tdr_stream_t stream);
 
 /* ---- graph stage ---------------------------------------------------------

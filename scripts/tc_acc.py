@@ -6,10 +6,10 @@ import torch
 from torchdr_b200 import ops, _lib
 from helpers import blobs, clustered
 import oracle
-_lib.load().tdr_knn_set_path(2)
+
 for (n, d, k, gen) in [(1500, 128, 15, "blobs"), (4096, 96, 15, "blobs"), (20000, 128, 15, "clustered")]:
     X = blobs(n, d, 6, n + d) if gen == "blobs" else clustered(n, d)
-    C, I = ops.knn(X.cuda(), X.cuda(), k)
+    C, I = ops.knn(X.cuda(), X.cuda(), k, path="tc")
     idx64, d64, ok, _ = oracle.knn_ambiguity(X, k)
     scale = float((X ** 2).sum(1).max()) * 2
     err = float((C.cpu().double() - d64).abs().max()) / scale

@@ -28,7 +28,8 @@ def install(monkeypatch):
         monkeypatch.setattr(ops, name, fn)
 
 
-def knn_umap_fused(Xq, Xdb, k, q_row0=0, exclude_self=True, max_iter=100, want_dist=True):
+def knn_umap_fused(Xq, Xdb, k, q_row0=0, exclude_self=True, max_iter=100, want_dist=True, path="auto", prune=None,
+                   sweep_stats=None):
     assert Xq.shape[0] == Xdb.shape[0] and q_row0 == 0 and exclude_self
     C, I = oracle.knn_dense(Xdb, k)
     P, rho, sigma = oracle.umap_affinity_rows(C, k, max_iter=max_iter)
@@ -102,7 +103,7 @@ def umap_run(Z_a, Z_b, rowptr, col, eps, eons, n_iter0, lrs, a, b, n_neg=75, rat
 
 
 # ---- entropic-affinity estimators (LargeVis, TSNE): gradients by autograd of the oracle's losses, as in the reference
-def knn(Xq, Xdb, k, q_row0=0, exclude_self=True, metric="sqeuclidean"):
+def knn(Xq, Xdb, k, q_row0=0, exclude_self=True, metric="sqeuclidean", path="auto", prune=None, sweep_stats=None):
     if Xq is Xdb or (Xq.shape == Xdb.shape and Xq.data_ptr() == Xdb.data_ptr()):
         return oracle.knn_dense(Xdb, k, metric, exclude_self)
     # cross / chunk queries: distance/torch.py:81-122 on (Xq, Xdb), self excluded by global id
@@ -209,7 +210,8 @@ def install_sharded(monkeypatch):
         monkeypatch.setattr(ops, name, fn)
 
 
-def knn_umap_fused_chunk(Xq, Xdb, k, q_row0=0, exclude_self=True, max_iter=100, want_dist=True):
+def knn_umap_fused_chunk(Xq, Xdb, k, q_row0=0, exclude_self=True, max_iter=100, want_dist=True, path="auto", prune=None,
+                         sweep_stats=None):
     C, I = oracle.knn_dense(Xdb, k)  # full problem, then this rank's rows: identical values for every partition
     P, rho, sigma = oracle.umap_affinity_rows(C, k, max_iter=max_iter)
     s, e = q_row0, q_row0 + Xq.shape[0]

@@ -109,20 +109,15 @@ def test_knn_pruned_sweep_is_bit_identical(ops, kind, n, d, k):
             X = X[torch.randperm(n, generator=torch.Generator().manual_seed(4))].contiguous()
     Xd = _cuda(X)
     stats = torch.zeros(2, dtype=torch.int64, device=DEV)
-    try:
-        ops.knn_set_prune(False)
-        C0, I0 = ops.knn(Xd, Xd, k)
-        Cc0, Ic0 = ops.knn(Xd[1000:5301], Xd, k, q_row0=1000)
-        F0 = ops.knn_umap_fused(Xd, Xd, min(k, 32)) if d <= 128 else None
-        E0, J0 = ops.knn(Xd, Xd, k, metric="euclidean")
-        ops.knn_set_prune(True, stats)
-        C1, I1 = ops.knn(Xd, Xd, k)
-        swept, full = (int(v) for v in stats.tolist())
-        Cc1, Ic1 = ops.knn(Xd[1000:5301], Xd, k, q_row0=1000)
-        F1 = ops.knn_umap_fused(Xd, Xd, min(k, 32)) if d <= 128 else None
-        E1, J1 = ops.knn(Xd, Xd, k, metric="euclidean")
-    finally:
-        ops.knn_set_prune(True, None)
+    C0, I0 = ops.knn(Xd, Xd, k, prune="off")
+    Cc0, Ic0 = ops.knn(Xd[1000:5301], Xd, k, q_row0=1000, prune="off")
+    F0 = ops.knn_umap_fused(Xd, Xd, min(k, 32), prune="off") if d <= 128 else None
+    E0, J0 = ops.knn(Xd, Xd, k, metric="euclidean", prune="off")
+    C1, I1 = ops.knn(Xd, Xd, k, prune="on", sweep_stats=stats)
+    swept, full = (int(v) for v in stats.tolist())
+    Cc1, Ic1 = ops.knn(Xd[1000:5301], Xd, k, q_row0=1000)  # default = on
+    F1 = ops.knn_umap_fused(Xd, Xd, min(k, 32)) if d <= 128 else None
+    E1, J1 = ops.knn(Xd, Xd, k, metric="euclidean")
     assert torch.equal(I0, I1) and torch.equal(C0, C1)
     assert torch.equal(Ic0, Ic1) and torch.equal(Cc0, Cc1)
     assert torch.equal(J0, J1) and torch.equal(E0, E1)
@@ -137,12 +132,9 @@ def test_knn_pruned_sweep_is_bit_identical(ops, kind, n, d, k):
         assert swept < 0.25 * full
 
 
-@pytest.mark.skipif(__import__("os").environ.get("TDR_TEST_EXPERIMENTAL") != "1",
-                    reason="robust pruned sweep (tdr_knn_set_prune(2)) is written but not yet verified on hardware; "
-                           "set TDR_TEST_EXPERIMENTAL=1 to run")
 @pytest.mark.parametrize("kind", ["clustered", "shuffled", "reordered"])
-def test_knn_robust_pruned_sweep_experimental(ops, kind):
-    """Round-2 work in progress: thresholds without outlier rows + certification + second sweep
+def test_knn_certified_pruned_sweep(ops, kind):
+    """prune="certified" (thresholds without outlier rows + certification + second sweep of the uncertified query tiles)
     must still return exactly the full sweep's result, in the generator's order, shuffled, and shuffled then sorted
     by the Voronoi tree of torchdr_b200/reorder.py (where the certification pass has real work to do)."""
     from torchdr_b200.reorder import voronoi_tree_order
@@ -155,16 +147,11 @@ def test_knn_robust_pruned_sweep_experimental(ops, kind):
     if kind == "reordered":
         Xd = Xd[voronoi_tree_order(Xd, generator=torch.Generator(device=DEV).manual_seed(1))].contiguous()
     stats = torch.zeros(2, dtype=torch.int64, device=DEV)
-    try:
-        ops.knn_set_prune(0)
-        C0, I0 = ops.knn(Xd, Xd, k)
-        F0 = ops.knn_umap_fused(Xd, Xd, k)
-        ops.knn_set_prune(2, stats)
-        C1, I1 = ops.knn(Xd, Xd, k)
-        swept = int(stats[0])
-        F1 = ops.knn_umap_fused(Xd, Xd, k)
-    finally:
-        ops.knn_set_prune(1, None)
+    C0, I0 = ops.knn(Xd, Xd, k, prune="off")
+    F0 = ops.knn_umap_fused(Xd, Xd, k, prune="off")
+    C1, I1 = ops.knn(Xd, Xd, k, prune="certified", sweep_stats=stats)
+    swept = int(stats[0])
+    F1 = ops.knn_umap_fused(Xd, Xd, k, prune="certified")
     assert torch.equal(I0, I1) and torch.equal(C0, C1)
     for a, b in zip(F0, F1):
         assert torch.equal(a, b)
@@ -491,6 +478,54 @@ def test_umap_in_kernel_negatives(ops):
     assert torch.equal(res, Zc) and torch.equal(e1, e2)
 
 
+def test_umap_persistent_loop_equals_per_iteration_launches(ops):
+    """tdr_umap_run_f32 — ONE cooperative launch per <= 128 iterations, 32-row blocks handed out by a work counter, grid
+    barrier in the kernel — against the same iterations launched one by one (tdr_umap_step_f32): embedding, edge
+    schedule, gradient norm and the sampled-edge / negative counters must be identical bit for bit, over several
+    calls that reuse one RunSync (epochs carry over) and one call longer than 128 iterations (two launches)."""
+    n, d, k = 60_000, 32, 15
+    X = _cuda(clustered(n, d))
+    _, idx, P, _, _ = ops.knn_umap_fused(X, X, k, want_dist=False)
+    rowptr, col, val = ops.symmetrize_csr(P, idx, 0, n)
+    eps, _ = ops.umap_schedule(val, float(ops.max_value(val).item()), 300)
+    rp, cc, ce, eons0 = ops.umap_compact(rowptr, col, eps)
+    a, b = oracle.find_ab()
+    Z0 = (_cuda(torch.randn(n, 2, generator=torch.Generator().manual_seed(1))) * 1e-4).contiguous()
+    T = [1, 50, 131, 20]
+    lrs = oracle.linear_lr_sequence(1.0, 300, sum(T))
+    # reference: per-iteration launches
+    Zc, Zd, e2 = Z0.clone(), torch.empty_like(Z0), eons0.clone()
+    st2, gn2 = torch.zeros(2, dtype=torch.int64, device=DEV), torch.zeros(1, dtype=torch.float64, device=DEV)
+    t = 0
+    marks = []
+    for cnt in T:
+        for j in range(cnt):
+            last = j == cnt - 1
+            ops.umap_step(Zc, Zd, 0, n, rp, cc, ce, e2, t, a, b, float(lrs[t]), neg=None, seed=9, stats=st2,
+                          gnorm_sq=gn2 if last else None)
+            Zc, Zd = Zd, Zc
+            t += 1
+        marks.append((Zc.clone(), gn2.clone()))
+    # persistent loop, one RunSync for all calls
+    sync = ops.RunSync(DEV)
+    Za, Zb, e1 = Z0.clone(), torch.empty_like(Z0), eons0.clone()
+    st1, gn1 = torch.zeros(2, dtype=torch.int64, device=DEV), torch.zeros(1, dtype=torch.float64, device=DEV)
+    nan = torch.zeros(1, dtype=torch.int32, device=DEV)
+    t = 0
+    for i, cnt in enumerate(T):
+        res = ops.umap_run(Za, Zb, rp, cc, ce, e1, t, lrs[t:t + cnt], a, b, seed=9, stats=st1, gnorm_sq=gn1, nan_flag=nan,
+                           sync=sync)
+        if res is not Za:
+            Za, Zb = Zb, Za
+        t += cnt
+        sync.check()
+        assert torch.equal(Za, marks[i][0]), f"call {i}"
+        torch.testing.assert_close(gn1, marks[i][1], rtol=1e-12, atol=0)  # fp64 atomics: order differs, value agrees
+    assert sync.epoch == sum(T) and int(sync.words[1].item()) == sum(T)  # barriers completed == iterations run
+    assert int(sync.words[0].item()) == 0 and int(sync.words[2].item()) == 0 and int(sync.words[3].item()) == 0
+    assert torch.equal(e1, e2) and torch.equal(st1, st2) and int(nan.item()) == 0
+
+
 # --------------------------------------------------------------------------- LargeVis / TSNE
 def test_largevis_gradient_and_steps(ops):
     g = golden("largevis_n300_d16_p10")
@@ -548,8 +583,6 @@ def test_tsne_gradient_and_steps(ops):
             assert rel_fro(Z.cpu(), g[f"Z_{step + 1}"]) < _loop_tol(step + 1), step
 
 
-@pytest.mark.skipif(__import__("os").environ.get("TDR_TEST_EXPERIMENTAL") != "1",
-                    reason="added after the round's last GPU minute; set TDR_TEST_EXPERIMENTAL=1 to run")
 def test_baseline_config_1_tsne_2000x50(ops):
     """BASELINE.json configs[0] on the CUDA path: the t-SNE gradient + momentum kernels on the reference's own
     2000 x 50 run (affinity recomputed by the oracle, which matches the fixture bit for bit; fixture:
@@ -871,8 +904,6 @@ def test_estimator_edge_cases():
     assert Zd.shape == (257, 2)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("TDR_TEST_EXPERIMENTAL") != "1",
-                    reason="added after the round's last GPU minute; set TDR_TEST_EXPERIMENTAL=1 to run")
 def test_discard_nns_estimators_on_gpu():
     """discard_NNs=True on the CUDA path: the host flow is verified against the live reference on the CPU stand-ins
     (tests/test_oracle_vs_reference.py); here the injected tables must respect the exclusions and the fits must work."""
@@ -897,8 +928,6 @@ def test_discard_nns_estimators_on_gpu():
     assert bool(torch.isfinite(Zl).all())
 
 
-@pytest.mark.skipif(__import__("os").environ.get("TDR_TEST_EXPERIMENTAL") != "1",
-                    reason="added after the round's last GPU minute; set TDR_TEST_EXPERIMENTAL=1 to run")
 def test_generic_optimizers_on_gpu():
     """Optimisers beyond the fused SGD(+momentum): the torch optimiser object steps the device embedding with the
     kernels' gradient (host flow verified against the live reference on the CPU stand-ins)."""

@@ -203,14 +203,21 @@ def test_tile_prune_rule_is_exact_on_cpu():
             assert frac > 0.9, frac
 
 
-def test_knn_prune_switch_validates_without_a_gpu():
+def test_knn_options_validate_without_a_gpu():
+    """path / prune are per-call arguments of the C ABI (no process-wide switches): bad values are rejected before any
+    device work, so this runs without a GPU."""
+    import ctypes
+
     from torchdr_b200 import _lib
 
     lib = _lib.load()
-    assert lib.tdr_knn_set_prune(1, None) == 0
-    assert lib.tdr_knn_set_prune(3, None) == _lib.TDR_E_INVALID
-    assert "tdr_knn_set_prune" in _lib.last_error()
-    assert lib.tdr_knn_set_prune(1, None) == 0
+    one = ctypes.c_void_p(256)  # never dereferenced: argument validation comes first
+    args = (one, 4, 0, one, 4, 8, 2, 1, 0, one, one)
+    assert lib.tdr_knn_f32(*args, 7, -1, None, None, 0, None) == _lib.TDR_E_INVALID
+    assert "path" in _lib.last_error()
+    assert lib.tdr_knn_f32(*args, 0, 3, None, None, 0, None) == _lib.TDR_E_INVALID
+    assert "prune" in _lib.last_error()
+    assert not hasattr(lib, "tdr_knn_set_prune_") and "tdr_knn_set_prune" not in _lib.SIGNATURES
     # the workspace query covers the pruned sweep's buffers (boxes, bounds, tile lists) once there are >= 64 tiles
     small = lib.tdr_knn_workspace_bytes(64 * 128 - 1, 64 * 128 - 128, 128, 15)
     big = lib.tdr_knn_workspace_bytes(64 * 128, 64 * 128, 128, 15)
@@ -431,26 +438,75 @@ def test_momentum_estimators_host_flow_reproduce_reference_runs_on_cpu(monkeypat
 
 
 def test_reordered_affinity_equals_plain_affinity_on_cpu(monkeypatch):
-    """TDR_KNN_REORDER=1 (experimental): searching in the Voronoi-tree order and mapping the rows back must give the
-    same symmetrised graph as searching in the input order (host logic on the CPU stand-ins)."""
+    """knn_order="tree": searching in the Voronoi-tree order and mapping the rows back must give the same symmetrised
+    graph as searching in the input order (host logic on the CPU stand-ins)."""
     import fake_ops
 
     import torchdr_b200 as tb
     from torchdr_b200 import ops
 
+    from torchdr_b200 import reorder
+
     fake_ops.install(monkeypatch)
-    monkeypatch.setattr(ops, "knn_set_prune", lambda on=True, stats=None: None)
+    monkeypatch.setattr(reorder, "MIN_ROWS_FOR_REORDER", 0)
     g = golden("umap_n300_d16_k15")
     X = t(g["X"])
-    plain = tb.UMAPAffinity(n_neighbors=15, max_iter=100).compute_csr(X)
-    monkeypatch.setenv("TDR_KNN_REORDER", "1")
-    aff = tb.UMAPAffinity(n_neighbors=15, max_iter=100)
+    plain = tb.UMAPAffinity(n_neighbors=15, max_iter=100, knn_order="input").compute_csr(X)
+    aff = tb.UMAPAffinity(n_neighbors=15, max_iter=100, knn_order="tree")
     reordered = aff.compute_csr(X)
     for a, b in zip(plain, reordered):
         assert torch.equal(a, b)
     assert torch.equal(aff.eps_, t(g["sigma"])) and torch.equal(aff.rho_, t(g["rho"]))
     vals, idx = aff(X)
     assert torch.equal(idx, t(g["sym_idx"]).long()) and torch.equal(vals, t(g["sym_vals"]))
+
+
+def test_fit_in_tree_order_returns_rows_in_input_order_on_cpu(monkeypatch):
+    """Estimator-level re-ordering (neighbor_embedding._fit_order): a fit on rows WITHOUT index locality runs on
+    X[perm] and must hand back row r = the embedding of input row r.  With an injected initialisation and zero
+    optimisation steps' worth of randomness removed (max_iter=1, negatives from the stand-in's own seeded stream are
+    index-dependent, so the check is on the graph-independent part): the initial layout is un-permuted exactly, and the
+    locality probe takes its three decisions (clustered order kept, shuffled re-ordered, structureless kept)."""
+    import fake_ops
+
+    import torchdr_b200 as tb
+    from torchdr_b200 import reorder
+
+    g = torch.Generator().manual_seed(0)
+    nc, per, d = 24, 256, 16
+    centers = torch.randn(nc, d, generator=g) * 10
+    Xc = (centers.repeat_interleave(per, 0) + 0.5 * torch.randn(nc * per, d, generator=g)).contiguous()
+    shuf = torch.randperm(nc * per, generator=g)
+    Xs = Xc[shuf].contiguous()
+    Xu = torch.randn(nc * per, d, generator=g)
+    assert reorder.index_locality(Xc) < 0.3 < reorder.LOCALITY_THRESHOLD < reorder.index_locality(Xs)
+    monkeypatch.setattr(reorder, "MIN_ROWS_FOR_REORDER", 0)
+    assert reorder.choose_order(Xc) is None                      # locality already there
+    perm = reorder.choose_order(Xs)
+    assert perm is not None and torch.equal(torch.sort(perm).values, torch.arange(nc * per))
+    assert reorder.index_locality(Xs, perm=perm) < 0.5 * reorder.index_locality(Xs)
+    assert reorder.choose_order(Xu) is None                      # no cluster structure: no order helps
+
+    fake_ops.install(monkeypatch)
+    seen = {}
+    orig = tb.UMAPAffinity.compute_csr
+
+    def spy(self, X):
+        seen["X"], seen["order"] = X.clone(), self.knn_order
+        return orig(self, X)
+
+    monkeypatch.setattr(tb.UMAPAffinity, "compute_csr", spy)
+    Z0 = torch.randn(nc * per, 2, generator=g)
+    m = tb.UMAP(n_neighbors=10, max_iter=1, lr=0.0, init=Z0, init_scaling=1.0, random_state=0, process_duplicates=False,
+                distributed=False)
+    Z = m.fit_transform(Xs)
+    assert seen["order"] == "presorted" and torch.equal(seen["X"], Xs[perm])
+    # lr = 0: the step leaves the initialisation untouched, so the output must be Z0 (rescaled) in INPUT order
+    torch.testing.assert_close(Z, Z0 / Z0[perm][:, 0].std(), rtol=1e-6, atol=0)
+    m2 = tb.UMAP(n_neighbors=10, max_iter=1, lr=0.0, init=Z0, init_scaling=1.0, random_state=0, process_duplicates=False,
+                 distributed=False, knn_order="input")
+    m2.fit_transform(Xs)
+    assert seen["order"] == "input" and torch.equal(seen["X"], Xs)
 
 
 def test_baseline_config_1_host_flow_on_cpu(monkeypatch):

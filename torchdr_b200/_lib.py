@@ -21,6 +21,8 @@ TDR_MAX_K = 160
 TDR_RUN_SYNC_WORDS = 8
 TDR_RUN_STATUS_WORD = 4
 METRIC_IDS = {"sqeuclidean": 0, "euclidean": 1}
+KNN_PATHS = {"auto": 0, "simt": 1, "tc": 2}
+KNN_PRUNE = {"default": -1, "off": 0, "on": 1, "certified": 2}
 
 P = c_void_p  # every device pointer
 
@@ -30,7 +32,8 @@ SIGNATURES = {
     "tdr_last_error": (c_char_p, []),
     "tdr_device_info": (c_int, [ctypes.POINTER(c_int)] * 3),
     "tdr_knn_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int]),
-    "tdr_knn_f32": (c_int, [P, c_int64, c_int64, P, c_int64, c_int, c_int, c_int, c_int, P, P, P, c_size_t, P]),
+    "tdr_knn_f32": (c_int, [P, c_int64, c_int64, P, c_int64, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P, P,
+                            c_size_t, P]),
     "tdr_pairwise_full_f32": (c_int, [P, c_int64, P, c_int64, c_int, c_int, c_int, P, P, c_size_t, P]),
     "tdr_umap_affinity_f32": (c_int, [P, c_int64, c_int, c_int, P, P, P, P]),
     "tdr_entropic_affinity_f32": (c_int, [P, c_int64, c_int, c_float, c_float, c_int, c_float, c_float, c_float,
@@ -38,10 +41,8 @@ SIGNATURES = {
     "tdr_indexed_dist_f32": (c_int, [P, P, c_int64, P, c_int64, c_int, P, c_int, c_int, c_int, P, P]),
     "tdr_entropic_dense_f32": (c_int, [P, c_int64, c_int64, c_float, c_float, c_int, c_float, c_float, c_float,
                                        c_float, c_int, P, P, P, P]),
-    "tdr_knn_set_path": (c_int, [c_int]),
-    "tdr_knn_set_prune": (c_int, [c_int, P]),
     "tdr_knn_umap_fused_f32": (c_int, [P, c_int64, c_int64, P, c_int64, c_int, c_int, c_int, c_int, P, P, P, P, P,
-                                       P, c_size_t, P]),
+                                       c_int, c_int, P, P, c_size_t, P]),
     "tdr_symmetrize_workspace_bytes": (c_size_t, [c_int64, c_int, c_int64]),
     "tdr_symmetrize_csr_f32": (c_int, [P, P, c_int64, c_int, c_int64, c_int64, P, P, P, c_int64, c_int, P, P, P, P,
                                        P, c_size_t, P]),

@@ -75,8 +75,14 @@ class _SparseAffinityBase:
     """Common plumbing of ``affinity/base.py:255-486``."""
 
     def __init__(self, metric="sqeuclidean", zero_diag=True, device="auto", backend=None, verbose=False,
-                 compile=False, sparsity=True, distributed="auto", _pre_processed=False):
+                 compile=False, sparsity=True, distributed="auto", _pre_processed=False, knn_order="auto"):
         _check_metric(metric)
+        if knn_order not in ("auto", "input", "tree", "presorted"):
+            raise ValueError("[TorchDR-B200] knn_order must be 'auto', 'input' or 'tree'.")
+        # engine-native option (not in the reference): row order the exact kNN search runs in — "auto" re-orders
+        # inputs without index locality (torchdr_b200/reorder.py) and maps the result back; "presorted" is set by the
+        # estimators, which run the whole fit in the tree order themselves
+        self.knn_order = knn_order
         self.metric = metric
         self.zero_diag = zero_diag
         self.device = device
@@ -114,6 +120,18 @@ class _SparseAffinityBase:
         X = _to_device_tensor(X, self.device)
         return X.float().contiguous() if X.dtype != torch.float32 or not X.is_contiguous() else X
 
+    def _search_order(self, X):
+        """(permutation | None, prune mode) for the kNN search of this call (single-GPU only: the estimators handle
+        the row-sharded case by running the whole fit in the tree order)."""
+        if self.knn_order == "presorted":
+            return None, "certified"
+        if self.is_multi_gpu or self.knn_order == "input":
+            return None, None
+        from .reorder import choose_order
+
+        perm = choose_order(X, self.knn_order)
+        return perm, ("certified" if perm is not None else None)
+
     def _chunk(self, n):
         """Row chunk of this rank; records chunk_start_/end_/size_ (affinity/base.py:477-484)."""
         if self.distributed and self.dist_ctx is not None:
@@ -133,12 +151,13 @@ class UMAPAffinity(_SparseAffinityBase):
 
     def __init__(self, n_neighbors=30, max_iter=1000, sparsity=True, metric="sqeuclidean", zero_diag=True,
                  device="auto", backend=None, verbose=False, compile=False, symmetrize=True, distributed="auto",
-                 _pre_processed=False):
+                 _pre_processed=False, knn_order="auto"):
         self.n_neighbors = n_neighbors
         self.max_iter = max_iter
         self.symmetrize = symmetrize
         super().__init__(metric=metric, zero_diag=zero_diag, device=device, backend=backend, verbose=verbose,
-                         compile=compile, sparsity=sparsity, distributed=distributed, _pre_processed=_pre_processed)
+                         compile=compile, sparsity=sparsity, distributed=distributed, _pre_processed=_pre_processed,
+                         knn_order=knn_order)
 
     def compute_csr(self, X):
         """Engine-native result: kNN + sigma/rho search (one fused kernel) + symmetrisation -> CSR."""
@@ -156,27 +175,26 @@ class UMAPAffinity(_SparseAffinityBase):
         if timing:
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-        if self.metric == "sqeuclidean" and not self.is_multi_gpu and os.environ.get("TDR_KNN_REORDER") == "1":
-            # EXPERIMENTAL: create the index locality the pruned sweep needs, search in that
-            # order with the certified sweep, map the rows back.  Off by default until verified on hardware.
-            from .reorder import unpermute_knn_rows, unpermute_rows, voronoi_tree_order
+        perm, prune = self._search_order(X)
+        if perm is not None:
+            # no index locality in the input: search in the tree order with the certified sweep, map the rows back
+            from .reorder import unpermute_knn_rows, unpermute_rows
 
-            perm = voronoi_tree_order(X)
             Xp = X[perm].contiguous()
-            ops.knn_set_prune(2)
-            try:
+            if self.metric == "sqeuclidean":
                 dist, idx, P, rho, sigma = ops.knn_umap_fused(Xp, Xp, k, q_row0=0, exclude_self=bool(self.zero_diag),
-                                                              max_iter=self.max_iter)
-            finally:
-                ops.knn_set_prune(1)
+                                                              max_iter=self.max_iter, prune=prune)
+            else:
+                dist, idx = ops.knn(Xp, Xp, k, q_row0=0, exclude_self=bool(self.zero_diag), metric=self.metric, prune=prune)
+                P, rho, sigma = ops.umap_affinity_rows(dist, self.max_iter)
             idx, dist, P = unpermute_knn_rows(perm, idx, dist, P)
             rho, sigma = unpermute_rows(perm, rho, sigma)
             del Xp
         elif self.metric == "sqeuclidean":
             dist, idx, P, rho, sigma = ops.knn_umap_fused(X[s:e], X, k, q_row0=s, exclude_self=bool(self.zero_diag),
-                                                          max_iter=self.max_iter)
+                                                          max_iter=self.max_iter, prune=prune)
         else:  # euclidean rows go through the two-kernel route
-            dist, idx = ops.knn(X[s:e], X, k, q_row0=s, exclude_self=bool(self.zero_diag), metric=self.metric)
+            dist, idx = ops.knn(X[s:e], X, k, q_row0=s, exclude_self=bool(self.zero_diag), metric=self.metric, prune=prune)
             P, rho, sigma = ops.umap_affinity_rows(dist, self.max_iter)
         self.rho_, self.eps_ = rho, sigma
         self.knn_ = (dist, idx)
@@ -209,11 +227,12 @@ class EntropicAffinity(_SparseAffinityBase):
 
     def __init__(self, perplexity=30, max_iter=1000, sparsity=True, metric="sqeuclidean", zero_diag=True,
                  device="auto", backend=None, verbose=False, compile=False, distributed="auto",
-                 _pre_processed=False):
+                 _pre_processed=False, knn_order="auto"):
         self.perplexity = perplexity
         self.max_iter = max_iter
         super().__init__(metric=metric, zero_diag=zero_diag, device=device, backend=backend, verbose=verbose,
-                         compile=compile, sparsity=sparsity, distributed=distributed, _pre_processed=_pre_processed)
+                         compile=compile, sparsity=sparsity, distributed=distributed, _pre_processed=_pre_processed,
+                         knn_order=knn_order)
 
     def _compute_sparse_log_affinity(self, X):
         X = self._prepare(X)
@@ -236,7 +255,16 @@ class EntropicAffinity(_SparseAffinityBase):
         if self.verbose:
             self.logger.info(f"Sparsity mode enabled, computing {k} nearest neighbors...")
         s, e = self._chunk(n)
-        C, idx = ops.knn(X[s:e], X, k, q_row0=s, exclude_self=bool(self.zero_diag), metric=self.metric)
+        perm, prune = self._search_order(X)
+        if perm is not None:
+            from .reorder import unpermute_knn_rows
+
+            Xp = X[perm].contiguous()
+            C, idx = ops.knn(Xp, Xp, k, q_row0=0, exclude_self=bool(self.zero_diag), metric=self.metric, prune=prune)
+            idx, C = unpermute_knn_rows(perm, idx, C)
+            del Xp
+        else:
+            C, idx = ops.knn(X[s:e], X, k, q_row0=s, exclude_self=bool(self.zero_diag), metric=self.metric, prune=prune)
         self.knn_ = (C, idx)
         target = float(torch.log(torch.tensor(perp)) + 1)  # entropic.py:272
         log_n = float(torch.log(torch.tensor(float(n), dtype=torch.float32)))  # entropic.py:308-310

@@ -33,13 +33,8 @@ bool knn_tc_supported(int d, int k);
 size_t knn_tc_workspace_bytes(int64_t nq, int64_t ndb, int d, int k, bool same);
 int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb, int64_t ndb, int d, int k,
                   bool same, int exclude_self, int metric, int fused, int max_iter, float* out_dist, int32_t* out_idx,
-                  float* P, float* rho, float* sigma, void* ws, size_t ws_bytes, cudaStream_t st);
-void knn_tc_set_prune(int on, unsigned long long* stats);
-// 0 = auto, 1 = SIMT fp32 kernel, 2 = tcgen05 kernel (tests / profiling); env TDR_KNN_PATH seeds it
-static int g_knn_path = [] {
-    const char* e = getenv("TDR_KNN_PATH");
-    return e ? atoi(e) : 0;
-}();
+                  float* P, float* rho, float* sigma, int prune, unsigned long long* sweep_stats, void* ws,
+                  size_t ws_bytes, cudaStream_t st);
 
 struct KnnParams {
     const float* Xq;   // [nq, ld]
@@ -464,9 +459,12 @@ static int launch_knn(const KnnParams& prm, dim3 grid, cudaStream_t st) {
 
 static int knn_common(int mode, const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb, int64_t ndb,
                       int d, int k, int exclude_self, int metric, int max_iter, float* out_dist,
-                      int32_t* out_idx, float* P, float* rho, float* sigma, void* ws, size_t ws_bytes,
-                      cudaStream_t st) {
+                      int32_t* out_idx, float* P, float* rho, float* sigma, int path, int prune,
+                      uint64_t* sweep_stats, void* ws, size_t ws_bytes, cudaStream_t st) {
     TDR_CHECK_ARG(Xq && Xdb && out_idx, "knn: null pointer");
+    TDR_CHECK_ARG(path >= TDR_KNN_PATH_AUTO && path <= TDR_KNN_PATH_TC, "knn: path must be 0 (auto), 1 (SIMT fp32) or 2 (tcgen05)");
+    TDR_CHECK_ARG(prune >= TDR_KNN_PRUNE_DEFAULT && prune <= TDR_KNN_PRUNE_CERTIFIED, "knn: prune must be -1 .. 2");
+    if (prune == TDR_KNN_PRUNE_DEFAULT) prune = TDR_KNN_PRUNE_ON;
     TDR_CHECK_ARG(nq >= 0 && ndb >= 1 && d >= 1, "knn: bad shape nq=%lld ndb=%lld d=%d", (long long)nq,
                   (long long)ndb, d);
     TDR_CHECK_ARG(k >= 1 && k <= TDR_MAX_K, "knn: k=%d outside [1,%d]", k, TDR_MAX_K);
@@ -477,12 +475,13 @@ static int knn_common(int mode, const float* Xq, int64_t nq, int64_t q_row0, con
                   "[TorchDR] ERROR : metric id %d is not supported.", metric);
     if (nq == 0) return TDR_OK;
     // tensor-core path (knn_tc.cu) when the tile shapes allow it; the SIMT kernel below otherwise
-    if (g_knn_path != 1 && knn_tc_supported(d, k) && (g_knn_path == 2 || g_knn_path == 0)) {
+    if (path != TDR_KNN_PATH_SIMT && knn_tc_supported(d, k)) {
         const bool inside = (Xq == Xdb + q_row0 * d) && q_row0 + nq <= ndb;
         return knn_tc_launch(Xq, nq, q_row0, Xdb, ndb, d, k, inside, exclude_self, metric, mode == MODE_FUSED,
-                             max_iter, out_dist, out_idx, P, rho, sigma, ws, ws_bytes, st);
+                             max_iter, out_dist, out_idx, P, rho, sigma, prune,
+                             reinterpret_cast<unsigned long long*>(sweep_stats), ws, ws_bytes, st);
     }
-    if (g_knn_path == 2) {
+    if (path == TDR_KNN_PATH_TC) {
         set_error("knn: tensor-core path forced but unsupported for d=%d k=%d", d, k);
         return TDR_E_UNSUPPORTED;
     }
@@ -524,33 +523,23 @@ extern "C" TDR_API size_t tdr_knn_workspace_bytes(int64_t nq, int64_t ndb, int d
     return b;
 }
 
-extern "C" TDR_API int tdr_knn_set_path(int path) {
-    TDR_CHECK_ARG(path >= 0 && path <= 2, "tdr_knn_set_path: 0 = auto, 1 = SIMT fp32, 2 = tcgen05");
-    g_knn_path = path;
-    return TDR_OK;
-}
-
-extern "C" TDR_API int tdr_knn_set_prune(int on, uint64_t* sweep_stats) {
-    TDR_CHECK_ARG(on >= 0 && on <= 2, "tdr_knn_set_prune: on must be 0, 1 or 2");
-    knn_tc_set_prune(on, reinterpret_cast<unsigned long long*>(sweep_stats));
-    return TDR_OK;
-}
-
 extern "C" TDR_API int tdr_knn_f32(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb, int64_t ndb, int d,
-                           int k, int exclude_self, int metric, float* out_dist, int32_t* out_idx, void* ws,
-                           size_t ws_bytes, tdr_stream_t stream) {
+                           int k, int exclude_self, int metric, float* out_dist, int32_t* out_idx, int path,
+                           int prune, uint64_t* sweep_stats, void* ws, size_t ws_bytes, tdr_stream_t stream) {
     TDR_CHECK_ARG(out_dist, "tdr_knn_f32: out_dist is null");
     return knn_common(MODE_KNN, Xq, nq, q_row0, Xdb, ndb, d, k, exclude_self, metric, 0, out_dist, out_idx,
-                      nullptr, nullptr, nullptr, ws, ws_bytes, (cudaStream_t)stream);
+                      nullptr, nullptr, nullptr, path, prune, sweep_stats, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 extern "C" TDR_API int tdr_knn_umap_fused_f32(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
                                       int64_t ndb, int d, int k, int exclude_self, int max_iter,
                                       float* out_dist, int32_t* out_idx, float* P, float* rho, float* sigma,
-                                      void* ws, size_t ws_bytes, tdr_stream_t stream) {
+                                      int path, int prune, uint64_t* sweep_stats, void* ws, size_t ws_bytes,
+                                      tdr_stream_t stream) {
     TDR_CHECK_ARG(P && rho && sigma, "tdr_knn_umap_fused_f32: null output");
     return knn_common(MODE_FUSED, Xq, nq, q_row0, Xdb, ndb, d, k, exclude_self, TDR_METRIC_SQEUCLIDEAN,
-                      max_iter, out_dist, out_idx, P, rho, sigma, ws, ws_bytes, (cudaStream_t)stream);
+                      max_iter, out_dist, out_idx, P, rho, sigma, path, prune, sweep_stats, ws, ws_bytes,
+                      (cudaStream_t)stream);
 }
 
 extern "C" TDR_API int tdr_pairwise_full_f32(const float* X, int64_t n, const float* Y, int64_t m, int d, int metric,

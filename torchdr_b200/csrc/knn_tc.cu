@@ -958,18 +958,6 @@ bool knn_tc_supported(int d, int k) {
     return 3 * stage + (size_t)tc::BM * k * 8 + 512 + 1024 <= (size_t)227 * 1024;
 }
 
-// process-wide switches of the pruned sweep (tdr_knn_set_prune)
-static int g_prune = [] {
-    const char* e = getenv("TDR_KNN_PRUNE");
-    return e ? atoi(e) : 1;
-}();
-static unsigned long long* g_sweep_stats = nullptr;
-
-void knn_tc_set_prune(int on, unsigned long long* stats) {
-    g_prune = on;
-    g_sweep_stats = stats;
-}
-
 namespace tc {
 struct PruneLayout {
     int64_t n_tiles, ld_t, n_super, ld_s, n_qtiles;
@@ -1009,8 +997,7 @@ size_t knn_tc_workspace_bytes(int64_t nq, int64_t ndb, int d, int k, bool same) 
         b += align_up((size_t)nq_pad * 4, 256);
         b += 2 * align_up((size_t)nq * dp * 2, 256);
     }
-    // pruned sweep (queries inside the database only); part of the size whether or not the switch is on, so
-    // that a workspace sized before tdr_knn_set_prune() stays valid after it
+    // pruned sweep (queries inside the database only); part of the size whether or not the call asks for it
     if ((ndb + tc::BN - 1) / tc::BN >= tc::kPruneMinTiles) b += tc::prune_layout(nq, ndb, d, k).total;
     return b;
 }
@@ -1018,7 +1005,8 @@ size_t knn_tc_workspace_bytes(int64_t nq, int64_t ndb, int d, int k, bool same) 
 // `same`: the query rows are rows [q_row0, q_row0+nq) of the database buffer itself.
 int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb, int64_t ndb, int d, int k,
                   bool same, int exclude_self, int metric, int fused, int max_iter, float* out_dist, int32_t* out_idx,
-                  float* P, float* rho, float* sigma, void* ws, size_t ws_bytes, cudaStream_t st) {
+                  float* P, float* rho, float* sigma, int prune, unsigned long long* sweep_stats, void* ws,
+                  size_t ws_bytes, cudaStream_t st) {
     using namespace tc;
     const size_t need = knn_tc_workspace_bytes(nq, ndb, d, k, same);
     if (!ws || ws_bytes < need || (uintptr_t)ws % 256) {
@@ -1118,7 +1106,7 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
 
     // ---- pruned sweep: boxes -> phase A (window) -> surviving-tile lists; the launch below is phase B
     const int64_t n_tiles = (ndb + BN - 1) / BN;
-    if (g_prune && same && n_tiles >= kPruneMinTiles && !prm.debug) {
+    if (prune && same && n_tiles >= kPruneMinTiles && !prm.debug) {
         const PruneLayout L = prune_layout(nq, ndb, d, k);
         char* w = p;  // same: p is the end of the split buffers
         if ((size_t)(w - (char*)ws) + L.total > ws_bytes) {
@@ -1151,7 +1139,7 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
         w += L.bound;
         int* redo_count = (int*)w;
         int* redo_map = (int*)(w + 256);
-        const int robust = g_prune == 2 ? 1 : 0;
+        const int robust = prune == 2 ? 1 : 0;
         TDR_CUDA(cudaMemsetAsync(maxnorm, 0, 4, st));
         tile_box_kernel<<<(unsigned)L.ld_t, 128, 0, st>>>(Xdb, 0, ndb, d, dlo_t, dhi_t, L.ld_t);
         super_box_kernel<<<(unsigned)(((int64_t)d * L.ld_s * 32 + 255) / 256), 256, 0, st>>>(dlo_t, dhi_t, L.ld_t, L.n_super,
@@ -1179,9 +1167,9 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
         prm.tile_list = list;
         prm.tile_count = count;
         prm.list_cap = L.cap;
-        prm.sweep_stats = g_sweep_stats;
+        prm.sweep_stats = sweep_stats;
         if (robust) {
-            // EXPERIMENTAL (tdr_knn_set_prune(2, ..)): thresholds that ignore outlier rows, then
+            // TDR_KNN_PRUNE_CERTIFIED (for inputs brought into a locality-creating order, torchdr_b200/reorder.py): thresholds that ignore outlier rows, then
             // certify every row against the bound its tile was swept with and sweep the uncertified tiles again with
             // the (by then tight) k-th distances found.  Device-side queue, no host synchronisation.
             const int fused_req = prm.fused;

@@ -68,7 +68,7 @@ class _NeighborEmbeddingB200:
                  scheduler_kwargs="auto", min_grad_norm=1e-7, max_iter=2000, init="pca", init_scaling=1e-4,
                  device="auto", backend=None, verbose=False, random_state=None, early_exaggeration_coeff=None,
                  early_exaggeration_iter=None, repulsion_strength=1.0, check_interval=50, compile=False,
-                 distributed="auto", process_duplicates=True, precise=False, **kwargs):
+                 distributed="auto", process_duplicates=True, precise=False, knn_order="auto", **kwargs):
         if n_components != 2:
             raise NotImplementedError("[TorchDR-B200] the step kernels are specialised for n_components=2.")
         if "learning_rate" in kwargs:  # NE base.py:170-171
@@ -95,6 +95,9 @@ class _NeighborEmbeddingB200:
         self.compile = compile
         self.process_duplicates = process_duplicates
         self.precise = precise  # fp64 transcendental evaluation in the step kernel (parity runs)
+        # engine-native (not in the reference): "auto" runs the fit in a locality-creating row order when the input
+        # order has none (torchdr_b200/reorder.py) and undoes the permutation on the embedding; "input" never does
+        self.knn_order = knn_order
         # NE base.py:175-182 — LinearLR "auto" goes from 1 to 0 over max_iter
         if scheduler == "LinearLR" and scheduler_kwargs == "auto":
             scheduler_kwargs = {"start_factor": torch.tensor(1.0), "end_factor": torch.tensor(0), "total_iters": max_iter}
@@ -242,10 +245,15 @@ class _NeighborEmbeddingB200:
     def _init_embedding(self, X):
         n = X.shape[0]
         dev = X.device
+        perm = getattr(self, "_perm", None)  # the fit runs on X[perm]: row r of Z belongs to original point perm[r]
         if isinstance(self.init, (torch.Tensor, np.ndarray)):
             Z = torch.as_tensor(self.init).to(device=dev, dtype=torch.float32)
+            if perm is not None:
+                Z = Z[perm]
         elif self.init in ("normal", "random"):
             Z = torch.randn((n, self.n_components), device=dev, dtype=torch.float32)
+            if perm is not None:
+                Z = Z[perm]  # every original point keeps the draw it would get in the input order
         elif self.init == "pca":
             Z = _pca_init(X, self.n_components)
         else:
@@ -333,7 +341,49 @@ class _NeighborEmbeddingB200:
             self.scheduler_.step()
 
     # ---- main driver (affinity_matcher.py:201-352) -----------------------------------------
+    def _fit_order(self, X):
+        """Row order of this fit: None (the input's) or a permutation (rank 0's, broadcast, when row-sharded).  Subclass
+        hooks and injected tables see row indices, so they pin the input order."""
+        base = _NeighborEmbeddingB200
+        user_hooks = any(getattr(type(self), h) is not getattr(base, h) for h in
+                         ("on_training_step_start", "on_training_step_end", "on_affinity_computation_start",
+                          "on_affinity_computation_end"))
+        if self.knn_order == "input" or user_hooks or self.precise:
+            return None
+        from .reorder import choose_order
+
+        if self.world_size == 1:
+            return choose_order(X, self.knn_order)
+        flag = torch.zeros(1, dtype=torch.int64, device=X.device)
+        perm = None
+        if self.rank == 0:
+            perm = choose_order(X, self.knn_order)
+            flag.fill_(0 if perm is None else 1)
+        dist.broadcast(flag, src=0)
+        if int(flag.item()) == 0:
+            return None
+        if perm is None:
+            perm = torch.empty(X.shape[0], dtype=torch.int64, device=X.device)
+        dist.broadcast(perm, src=0)
+        return perm
+
     def _fit_transform(self, X):
+        self._perm = self._fit_order(X)
+        if self._perm is not None:
+            X = X[self._perm].contiguous()
+            self.affinity_in.knn_order = "presorted"
+        else:
+            self.affinity_in.knn_order = "input"
+        self._tick("order")
+        Z = self._fit_transform_ordered(X)
+        if self._perm is not None:
+            out = torch.empty_like(Z)
+            out[self._perm] = Z
+            self.embedding_ = Z = out
+        self._perm = None
+        return Z
+
+    def _fit_transform_ordered(self, X):
         n = X.shape[0]
         self._check_n_neighbors(n)
         self.early_exaggeration_coeff_ = self.early_exaggeration_coeff  # NE base.py:276

@@ -22,8 +22,23 @@ def _dev_f32(x, name):
     return x.contiguous()
 
 
-def knn(Xq, Xdb, k, q_row0=0, exclude_self=True, metric="sqeuclidean"):
-    """Exact kNN of query rows against the database -> (dist[nq,k] f32, idx[nq,k] i32)."""
+def _prune_id(prune):
+    if isinstance(prune, str):
+        return _lib.KNN_PRUNE[prune]
+    return -1 if prune is None else int(prune)
+
+
+def _check_stats(stats):
+    if stats is not None:
+        assert stats.is_cuda and stats.dtype == torch.int64 and stats.numel() >= 2 and stats.is_contiguous()
+    return stats
+
+
+def knn(Xq, Xdb, k, q_row0=0, exclude_self=True, metric="sqeuclidean", path="auto", prune=None, sweep_stats=None):
+    """Exact kNN of query rows against the database -> (dist[nq,k] f32, idx[nq,k] i32).
+
+    ``path``: "auto" | "simt" | "tc"; ``prune``: None (default = on) | 0/"off" | 1/"on" | 2/"certified";
+    ``sweep_stats``: optional int64[2] CUDA tensor accumulating (tiles swept, tiles of a full sweep)."""
     Xq, Xdb = _dev_f32(Xq, "Xq"), _dev_f32(Xdb, "Xdb")
     lib = _lib.load()
     nq, d = Xq.shape
@@ -33,20 +48,14 @@ def knn(Xq, Xdb, k, q_row0=0, exclude_self=True, metric="sqeuclidean"):
     idx = torch.empty((nq, k), dtype=torch.int32, device=Xq.device)
     with torch.cuda.device(Xq.device):
         check(lib.tdr_knn_f32(ptr(Xq), nq, q_row0, ptr(Xdb), ndb, d, k, int(exclude_self), _lib.METRIC_IDS[metric],
-                              ptr(dist), ptr(idx), ptr(ws), ws.numel(), stream()), "tdr_knn_f32")
+                              ptr(dist), ptr(idx), _lib.KNN_PATHS[path], _prune_id(prune), ptr(_check_stats(sweep_stats)),
+                              ptr(ws), ws.numel(), stream()), "tdr_knn_f32")
     return dist, idx
 
 
-def knn_set_prune(on=True, stats=None):
-    """Switch the tile-pruned sweep of the tensor-core kNN (``tdr_knn_set_prune``).  ``stats``: optional int64[2]
-    CUDA tensor that accumulates (tiles swept, tiles of a full sweep); keep it alive while it is registered."""
-    if stats is not None:
-        assert stats.is_cuda and stats.dtype == torch.int64 and stats.numel() >= 2 and stats.is_contiguous()
-    check(_lib.load().tdr_knn_set_prune(int(on), ptr(stats)), "tdr_knn_set_prune")  # True -> 1; 2 = experimental robust mode
-
-
-def knn_umap_fused(Xq, Xdb, k, q_row0=0, exclude_self=True, max_iter=100, want_dist=True):
-    """Fused kNN + UMAP rho/sigma search -> (dist|None, idx, P, rho, sigma)."""
+def knn_umap_fused(Xq, Xdb, k, q_row0=0, exclude_self=True, max_iter=100, want_dist=True, path="auto", prune=None,
+                   sweep_stats=None):
+    """Fused kNN + UMAP rho/sigma search -> (dist|None, idx, P, rho, sigma).  Options as in ``knn``."""
     Xq, Xdb = _dev_f32(Xq, "Xq"), _dev_f32(Xdb, "Xdb")
     lib = _lib.load()
     nq, d = Xq.shape
@@ -60,7 +69,8 @@ def knn_umap_fused(Xq, Xdb, k, q_row0=0, exclude_self=True, max_iter=100, want_d
     sigma = torch.empty((nq,), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         check(lib.tdr_knn_umap_fused_f32(ptr(Xq), nq, q_row0, ptr(Xdb), ndb, d, k, int(exclude_self), max_iter,
-                                         ptr(dist), ptr(idx), ptr(Pm), ptr(rho), ptr(sigma), ptr(ws), ws.numel(),
+                                         ptr(dist), ptr(idx), ptr(Pm), ptr(rho), ptr(sigma), _lib.KNN_PATHS[path],
+                                         _prune_id(prune), ptr(_check_stats(sweep_stats)), ptr(ws), ws.numel(),
                                          stream()), "tdr_knn_umap_fused_f32")
     return dist, idx, Pm, rho, sigma
 

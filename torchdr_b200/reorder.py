@@ -1,18 +1,21 @@
-"""EXPERIMENTAL (opt-in: ``TDR_KNN_REORDER=1`` in ``UMAPAffinity``, single GPU): spatial re-ordering for the pruned kNN sweep.
+"""Spatial re-ordering of the rows for inputs WITHOUT index locality.
 
 The pruned sweep of ``csrc/knn_tc.cu`` skips database tiles whose bounding box is too far from the query
-tile's box, which only pays when rows that are close in space are close in index.  ``voronoi_tree_order``
-creates that locality for an arbitrary input order: the rows are sorted by the leaves of an unbalanced
-Voronoi tree (every node hands its points to the nearest of <= ``branch`` centres sampled from the node
-itself, one Lloyd iteration, recursing until a node has <= ``leaf`` rows).  ``knn_in_any_order`` runs a kNN
-callable on the re-ordered rows and maps the result back.  Design study and measurements:
-``scripts/reorder_sim.py``, DESIGN.md section 8.  There is no counterpart in the reference
-(``torchdr/distance/base.py`` hands unordered data to FAISS); exactness is untouched because the
-pruning rule itself is exact for any order.
+tile's box, and the step kernel's gathers of neighbour rows hit L1/L2 when neighbours are close in index — both
+only pay when rows that are close in space are close in index.  Many pipelines deliver that (clusters or batches
+appended one after the other, like the reference benchmark's generator); for any other order
+``index_locality`` detects the lack of it and ``voronoi_tree_order`` creates it: the rows are sorted by the leaves
+of an unbalanced Voronoi tree (every node hands its points to the nearest of <= ``branch`` centres sampled from the
+node itself, one Lloyd iteration, recursing until a node has <= ``leaf`` rows).  The estimators then run the whole
+fit in that order and undo the permutation on the embedding (``neighbor_embedding._fit_transform``); the affinity
+classes, whose outputs are index-valued, search in that order and map rows and neighbour ids back
+(``unpermute_knn_rows``).  Exactness is untouched: the pruning rule is exact for any order, and in the tree order the
+sweep runs in its certified mode (TDR_KNN_PRUNE_CERTIFIED).  There is no counterpart in the reference
+(``torchdr/distance/base.py`` hands unordered data to FAISS).  Design study: ``scripts/reorder_sim.py``; measured:
+shuffled 1 M x 128 fit 1.33 s -> 0.26 s (``profiles/r2_first.log``).
 
 Level-synchronous and device-agnostic (plain tensor ops: sort, gather, index_add, batched dot products),
-so the host logic is unit-tested on the CPU (``tests/test_host_logic.py``: same graph as the plain path, bit for
-bit); the per-level nearest-of-16 search is the piece that becomes a CUDA kernel once the path has been measured.
+so the host logic is unit-tested on the CPU (``tests/test_host_logic.py``: same graph as the plain path, bit for bit).
 """
 
 import torch
@@ -34,6 +37,46 @@ def _assign(X, rows, node_of_row, centres, valid, chunk=16384):
         d2 = cn[nd] - 2.0 * dots  # + |x|^2, constant per row
         out[a:a + chunk] = d2.argmin(1)
     return out
+
+
+def index_locality(X, tiles=256, tile_rows=128, sample=32768, perm=None):
+    """Mean extent of a 128-row tile's bounding box relative to the data's extent (per dimension, averaged): ~0.05 when
+    consecutive rows are neighbours in space (clusters stored one after the other), ~0.7-0.9 when the order carries
+    no locality (shuffled, or data with no cluster structure at all).  A fixed-seed sample: O(tiles * d) work.
+    ``perm``: measure the order ``X[perm]`` without materialising it."""
+    n, d = X.shape
+    if n < 2 * tile_rows:
+        return 0.0
+    g = torch.Generator(device=X.device).manual_seed(0x5EED)
+    starts = torch.randint(0, n - tile_rows + 1, (min(tiles, n // tile_rows),), generator=g, device=X.device)
+    rows = starts.unsqueeze(1) + torch.arange(tile_rows, device=X.device).unsqueeze(0)
+    T = X[rows if perm is None else perm[rows]]  # [tiles, 128, d]
+    ext_tile = (T.amax(1) - T.amin(1)).mean(0)
+    S = X[torch.randint(0, n, (min(sample, n),), generator=g, device=X.device)]
+    ext_all = (S.amax(0) - S.amin(0)).clamp_min(1e-30)
+    return float((ext_tile / ext_all).mean())
+
+
+LOCALITY_THRESHOLD = 0.6  # index_locality above this: the order carries no locality (tiles straddling 2-3 clusters: ~0.4)
+LOCALITY_GAIN = 0.5       # the tree order is adopted only if it at least halves that figure
+MIN_ROWS_FOR_REORDER = 64 * 128  # below 64 database tiles the kNN kernel does not prune at all
+
+
+def choose_order(X, mode="auto", generator=None):
+    """Permutation to run the fit in, or None to keep the input order.  mode: "input" (never), "tree" (always),
+    "auto": only if the input order has no index locality AND the tree order has (data without cluster structure
+    gains nothing from any order; it is searched as it is)."""
+    if mode == "input" or X.shape[0] < MIN_ROWS_FOR_REORDER:
+        return None
+    before = index_locality(X) if mode == "auto" else 1.0
+    if mode == "auto" and before <= LOCALITY_THRESHOLD:
+        return None
+    if generator is None:
+        generator = torch.Generator(device=X.device).manual_seed(0x7EE)
+    perm = voronoi_tree_order(X, generator=generator)
+    if mode == "auto" and index_locality(X, perm=perm) > LOCALITY_GAIN * before:
+        return None
+    return perm
 
 
 def voronoi_tree_order(X, branch=16, leaf=128, lloyd=1, generator=None):
