@@ -284,11 +284,11 @@ TDR_API int tdr_largevis_grad_f32(const float* Z, int64_t n_total, int64_t row0,
  *   phase 0: zero ws; U_i = sum_j w_ij^2 (z_i - z_j) and the partial normaliser S (a device
  *            double at ws[0]) for local rows; attraction scattered into grad (caller-zeroed).
  *   (host: all-reduce S when distributed)
- *   phase 1: grad[local rows] += -4 U_i / S.
+ *   phase 1: grad[local rows] += -4 repulsion U_i / S   (repulsion = repulsion_strength, NE base.py:237-241).
  * ws: tdr_tsne_workspace_bytes(n_local), 16-byte aligned. */
 TDR_API size_t tdr_tsne_workspace_bytes(int64_t n_local);
 TDR_API int tdr_tsne_grad_f32(const float* Z, int64_t n_total, int64_t row0, int64_t n_local,
-                      const float* P, const int32_t* idx, int k, float lam, int phase,
+                      const float* P, const int32_t* idx, int k, float lam, float repulsion, int phase,
                       float* grad, void* ws, size_t ws_bytes, tdr_stream_t stream);
 
 /* InfoTSNE gradient (infotsne.py:179-197 differentiated): t-SNE attraction on the kNN rows plus the

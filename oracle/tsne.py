@@ -11,14 +11,14 @@ included, of -log(1 + C) with C in the expanded form of
 import torch
 
 
-def tsne_loss(Z, P, idx, rows, lam):
+def tsne_loss(Z, P, idx, rows, lam, repulsion=1.0):
     Zq = Z[rows]
     D = torch.sum((Zq.unsqueeze(1) - Z[idx.long()]) ** 2, dim=-1)
     att = -(P * (-(1 + D).log())).sum()  # tsne.py:162-170
     nz = (Z**2).sum(-1)
     C = nz.unsqueeze(-1) + nz.unsqueeze(-2) - 2 * (Z @ Z.transpose(-1, -2))
     rep = (-(1 + C).log()).logsumexp((0, 1))  # tsne.py:172-180
-    return lam * att + rep
+    return lam * att + repulsion * rep  # NE base.py:223-242: early_exag * attractive + repulsion_strength * repulsive
 
 
 def tsne_run(Z0, P, idx, n_steps, exag=12.0, exag_iter=250, lr=None, return_grads=False):

@@ -151,13 +151,13 @@ def tsne_workspace(n_local, device):
     return torch.zeros(8, dtype=torch.uint8)
 
 
-def tsne_grad(Z, row0, n_local, Pm, idx, lam, phase, grad, ws):
+def tsne_grad(Z, row0, n_local, Pm, idx, lam, phase, grad, ws, repulsion=1.0):
     if phase == 0:
         return
     from oracle.tsne import tsne_loss
 
     Zp = Z.detach().clone().requires_grad_(True)
-    tsne_loss(Zp, Pm, idx, torch.arange(n_local), lam).backward()
+    tsne_loss(Zp, Pm, idx, torch.arange(n_local), lam, repulsion).backward()
     grad += Zp.grad
 
 

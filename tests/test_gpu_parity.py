@@ -569,6 +569,15 @@ def test_tsne_gradient_and_steps(ops):
 
     gradient(12.0)
     assert rel_fro(grad.cpu(), g["G_1"]) < 1e-5
+    # repulsion_strength != 1 (NE base.py:223-242) against the oracle's autograd gradient of the same loss
+    from oracle.tsne import tsne_loss
+
+    Zp = Z.detach().cpu().clone().requires_grad_(True)
+    tsne_loss(Zp, t(g["P"]), t(g["I"]), torch.arange(300), 12.0, repulsion=2.5).backward()
+    grad.zero_()
+    ops.tsne_grad(Z, 0, 300, P, I, 12.0, 0, grad, ws, repulsion=2.5)
+    ops.tsne_grad(Z, 0, 300, P, I, 12.0, 1, grad, ws, repulsion=2.5)
+    assert rel_fro(grad.cpu(), Zp.grad) < 1e-5
     mom = torch.zeros_like(Z)
     lam, first = 12.0, True
     for step in range(12):

@@ -509,6 +509,41 @@ def test_fit_in_tree_order_returns_rows_in_input_order_on_cpu(monkeypatch):
     assert seen["order"] == "input" and torch.equal(seen["X"], Xs)
 
 
+def test_estimators_are_sklearn_estimators_and_torch_modules():
+    """base.py:27 ``DRModule(BaseEstimator, nn.Module, ABC)``: get_params / set_params / clone round trips and the module
+    tree (the input affinity is a sub-module), for every estimator of the path.  UMAP goes beyond the reference here:
+    torchdr.UMAP stores a / b only as _a / _b, so its get_params() raises AttributeError."""
+    import torch.nn as nn
+    from sklearn.base import BaseEstimator, clone
+
+    import torchdr_b200 as tb
+
+    for cls, kw in ((tb.UMAP, dict(n_neighbors=12, min_dist=0.2)), (tb.TSNE, dict(perplexity=20)),
+                    (tb.LargeVis, dict(perplexity=25, n_negatives=7)), (tb.InfoTSNE, dict(perplexity=10)),
+                    (tb.SNE, dict(perplexity=10))):
+        m = cls(max_iter=17, random_state=3, distributed=False, **kw)
+        assert isinstance(m, BaseEstimator) and isinstance(m, nn.Module)
+        p = m.get_params()
+        assert p["max_iter"] == 17 and p["random_state"] == 3
+        for key, val in kw.items():
+            assert p[key] == val
+        c = clone(m)
+        assert type(c) is cls and c is not m and c.get_params().keys() == p.keys()
+        for key in p:
+            a, b = p[key], c.get_params()[key]
+            assert (a is b) or (a == b) or (isinstance(a, dict) and a.keys() == b.keys()), key
+        m.set_params(max_iter=5)
+        assert m.max_iter == 5
+        assert [name for name, _ in m.named_modules()] == ["", "affinity_in"]
+        assert isinstance(m.affinity_in, nn.Module)
+        assert cls.__name__ in repr(m)
+    with pytest.raises(ValueError):
+        tb.UMAP(distributed=False).set_params(no_such_parameter=1)
+    # dense optimisation is outside the path: refused with a clear message instead of an AttributeError deep inside
+    with pytest.raises(NotImplementedError, match="sparsity=False"):
+        tb.TSNE(sparsity=False, distributed=False)._compute_affinity(torch.zeros(8, 3))
+
+
 def test_baseline_config_1_host_flow_on_cpu(monkeypatch):
     """BASELINE.json configs[0] through the public estimator on the CPU stand-ins: TSNE(perplexity=30) on the
     reference's 2000 x 50 blobs run.  Tolerances as in tests/test_oracle_golden.py (the reference's own backward is not

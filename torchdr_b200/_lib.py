@@ -67,7 +67,8 @@ SIGNATURES = {
     "tdr_largevis_grad_f32": (c_int, [P, c_int64, c_int64, c_int64, P, P, c_int, P, c_int, c_uint64, c_int64,
                                       c_float, c_float, P, P]),
     "tdr_tsne_workspace_bytes": (c_size_t, [c_int64]),
-    "tdr_tsne_grad_f32": (c_int, [P, c_int64, c_int64, c_int64, P, P, c_int, c_float, c_int, P, P, c_size_t, P]),
+    "tdr_tsne_grad_f32": (c_int, [P, c_int64, c_int64, c_int64, P, P, c_int, c_float, c_float, c_int, P, P, c_size_t,
+                                  P]),
     "tdr_infotsne_grad_f32": (c_int, [P, c_int64, c_int64, c_int64, P, P, c_int, P, c_int, c_uint64, c_int64,
                                       c_float, c_float, P, P]),
     "tdr_sne_grad_f32": (c_int, [P, c_int64, c_int64, c_int64, P, P, c_int, c_float, c_float, c_int, P, P, P]),

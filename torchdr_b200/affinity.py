@@ -16,6 +16,7 @@ import os
 import time
 
 import torch
+import torch.nn as nn
 
 from . import _lib, ops
 from .distance import _check_metric, _to_device_tensor
@@ -71,11 +72,13 @@ def entropic_bound_scalars(n_rows, perplexity):
     return (float(tN * lr), float(tN - 1), float(lr), float(torch.log((tN - 1) * p1 / (1.0 - p1))))
 
 
-class _SparseAffinityBase:
-    """Common plumbing of ``affinity/base.py:255-486``."""
+class _SparseAffinityBase(nn.Module):
+    """Common plumbing of ``affinity/base.py:30-486`` (``Affinity(nn.Module, ABC)``; fitted quantities are
+    non-persistent state dropped by ``clear_memory``)."""
 
     def __init__(self, metric="sqeuclidean", zero_diag=True, device="auto", backend=None, verbose=False,
                  compile=False, sparsity=True, distributed="auto", _pre_processed=False, knn_order="auto"):
+        nn.Module.__init__(self)
         _check_metric(metric)
         if knn_order not in ("auto", "input", "tree", "presorted"):
             raise ValueError("[TorchDR-B200] knn_order must be 'auto', 'input' or 'tree'.")

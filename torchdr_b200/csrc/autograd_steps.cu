@@ -299,10 +299,10 @@ sne_repulse_kernel(const float2* __restrict__ Z, int64_t n_total, int64_t row0, 
 
 __global__ void __launch_bounds__(256)
 tsne_finish_kernel(const float* __restrict__ U, const double* __restrict__ S, int64_t row0, int64_t n_local,
-                   float* __restrict__ grad) {
+                   float repulsion, float* __restrict__ grad) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 2 * n_local) return;
-    const float scale = (float)(-4.0 / *S);
+    const float scale = (float)(-4.0 * (double)repulsion / *S);  // NE base.py:237-241: repulsion_strength * repulsive
     atomicAdd(grad + 2 * row0 + i, scale * U[i]);
 }
 
@@ -351,8 +351,8 @@ extern "C" TDR_API int tdr_largevis_grad_f32(const float* Z, int64_t n_total, in
 extern "C" TDR_API size_t tdr_tsne_workspace_bytes(int64_t n_local) { return 256 + (size_t)n_local * 8; }
 
 extern "C" TDR_API int tdr_tsne_grad_f32(const float* Z, int64_t n_total, int64_t row0, int64_t n_local, const float* P,
-                                 const int32_t* idx, int k, float lam, int phase, float* grad, void* ws,
-                                 size_t ws_bytes, tdr_stream_t stream) {
+                                 const int32_t* idx, int k, float lam, float repulsion, int phase, float* grad,
+                                 void* ws, size_t ws_bytes, tdr_stream_t stream) {
     TDR_CHECK_ARG(Z && grad && ws, "tdr_tsne_grad_f32: null pointer");
     TDR_CHECK_ARG(n_total >= 2 && row0 >= 0 && n_local >= 0 && row0 + n_local <= n_total, "tdr_tsne_grad_f32: bad shape");
     TDR_CHECK_ARG(ws_bytes >= tdr_tsne_workspace_bytes(n_local) && (uintptr_t)ws % 16 == 0,
@@ -379,7 +379,7 @@ extern "C" TDR_API int tdr_tsne_grad_f32(const float* Z, int64_t n_total, int64_
     } else {
         // S now holds the global normaliser (all-reduced by the host when distributed)
         if (n_local > 0)
-            tsne_finish_kernel<<<(unsigned)((2 * n_local + 255) / 256), 256, 0, st>>>(U, S, row0, n_local, grad);
+            tsne_finish_kernel<<<(unsigned)((2 * n_local + 255) / 256), 256, 0, st>>>(U, S, row0, n_local, repulsion, grad);
     }
     TDR_LAUNCH_CHECK();
     return TDR_OK;

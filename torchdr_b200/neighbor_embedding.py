@@ -17,6 +17,8 @@ import warnings
 import numpy as np
 import torch
 import torch.distributed as dist
+import torch.nn as nn
+from sklearn.base import BaseEstimator
 
 from . import _lib, ops
 from .affinity import EntropicAffinity, UMAPAffinity
@@ -59,8 +61,11 @@ def _may_have_duplicate_rows(X, chunk=131072):
     return bool((hs[1:] == hs[:-1]).any())
 
 
-class _NeighborEmbeddingB200:
-    """Driver shared by the three methods (affinity_matcher.py + neighbor_embedding/base.py)."""
+class _NeighborEmbeddingB200(BaseEstimator, nn.Module):
+    """Driver shared by the estimators (base.py:27-79 ``DRModule(BaseEstimator, nn.Module, ABC)``, affinity_matcher.py,
+    neighbor_embedding/base.py).  Like the reference's classes these are sklearn estimators (``get_params`` /
+    ``set_params`` / ``clone`` read the constructor signature) and torch modules (the input affinity is a sub-module;
+    ``affinity_in_``, ``NN_indices_``, ``neg_indices_`` ... are non-persistent buffers dropped by ``clear_memory``)."""
 
     _use_closed_form_gradients = False
 
@@ -69,6 +74,7 @@ class _NeighborEmbeddingB200:
                  device="auto", backend=None, verbose=False, random_state=None, early_exaggeration_coeff=None,
                  early_exaggeration_iter=None, repulsion_strength=1.0, check_interval=50, compile=False,
                  distributed="auto", process_duplicates=True, precise=False, knn_order="auto", **kwargs):
+        nn.Module.__init__(self)
         if n_components != 2:
             raise NotImplementedError("[TorchDR-B200] the step kernels are specialised for n_components=2.")
         if "learning_rate" in kwargs:  # NE base.py:170-171
@@ -228,7 +234,7 @@ class _NeighborEmbeddingB200:
         n_possible = self.n_samples_in_ - excl.shape[1]
         if self.n_negatives > n_possible and self.verbose:
             raise ValueError(f"[TorchDR] ERROR : requested {self.n_negatives} negatives but only {n_possible} available.")
-        self.negative_exclusion_indices_ = excl
+        self._set_buffer("negative_exclusion_indices_", excl)  # NE base.py:605
 
     def on_training_step_end(self):
         pass
@@ -399,7 +405,7 @@ class _NeighborEmbeddingB200:
             self.logger.info(f"----- Computing the input affinity matrix with {self.affinity_in.__class__.__name__} -----")
         self._compute_affinity(X)
         self._tick("affinity+graph")
-        self.chunk_indices_ = torch.arange(self.chunk_start_, self.chunk_end_, device=X.device)  # NE base.py:406-408
+        self._set_buffer("chunk_indices_", torch.arange(self.chunk_start_, self.chunk_end_, device=X.device))  # NE base.py:406-408
         if getattr(self, "discard_NNs", False):
             self._build_negative_exclusions(self._neighbour_rows())
         self.on_affinity_computation_end()
@@ -428,6 +434,13 @@ class _NeighborEmbeddingB200:
         self.clear_memory()
         return self.embedding_
 
+    def _kernel_seed(self):
+        """Key of the in-kernel negative stream: the estimator's seed, else torch's current seed (unseeded runs differ
+        from process to process like the reference's torch.randint draws, NE base.py:629)."""
+        if self.random_state is not None:
+            return int(self._actual_seed)
+        return int(torch.initial_seed() % (2**63))
+
     def _check_nan(self, step):
         """check_NaNs of affinity_matcher.py:315-319.  Row-sharded runs agree on the flag first (MAX over ranks): a
         rank that alone saw a NaN must not leave its peers waiting in the next iteration's exchange."""
@@ -446,7 +459,20 @@ class _NeighborEmbeddingB200:
             return True
         return False
 
+    def _set_buffer(self, name, tensor):
+        """register_buffer(..., persistent=False) as in affinity_matcher.py:269-286 / NE base.py:605,649 (re-entrant)."""
+        if name in self._buffers:
+            self._buffers[name] = tensor
+        else:
+            if name in self.__dict__:
+                del self.__dict__[name]
+            self.register_buffer(name, tensor, persistent=False)
+
     def clear_memory(self):
+        """affinity_matcher.py:661-677: drop every non-persistent buffer (and the loop's scratch state)."""
+        for name in list(self._non_persistent_buffers_set):
+            if hasattr(self, name):
+                delattr(self, name)
         for name in ("_gnorm", "_nan", "optimizer_", "scheduler_", "params_", "_dummy", "neg_indices_", "_graph",
                      "affinity_in_", "NN_indices_", "chunk_indices_", "_mom", "_grad", "negative_exclusion_indices_"):
             if hasattr(self, name):
@@ -531,6 +557,7 @@ class UMAP(_NeighborEmbeddingB200):
         self.negative_sample_rate = negative_sample_rate
         self.sparsity = True
         self._eps = 1e-3
+        self.a, self.b = a, b  # as passed: sklearn's get_params / clone read them (the reference raises here)
         if a is None or b is None:
             a, b = find_ab_params(spread, min_dist)
         self._a, self._b = a, b
@@ -574,7 +601,7 @@ class UMAP(_NeighborEmbeddingB200):
         rowptr, col, eps, eons = self._graph
         s, e = self.chunk_start_, self.chunk_end_
         Za = self.embedding_
-        seed = int(self._actual_seed) if self.random_state is not None else int(torch.initial_seed() % (2**63))
+        seed = self._kernel_seed()
         rep = float(self.repulsion_strength)
         if not self._native_opt or self._hyper()[1] != 0.0:
             # the step kernel fuses plain SGD (umap.py:139, the default); anything else takes the gradient from the
@@ -734,9 +761,15 @@ class _EntropicInputMixin:
         return self.NN_indices_
 
     def _compute_affinity(self, X):
+        if not self.sparsity:
+            # the reference's dense mode (affinity_matcher.py:280-286: an N x N affinity_in_, no NN_indices_) is outside
+            # the accelerated path: the gradient kernels walk kNN rows.  EntropicAffinity(sparsity=False) itself — the
+            # dense affinity of BASELINE configs[2] — is available on its own.
+            raise NotImplementedError(f"[TorchDR-B200] {self.__class__.__name__}(sparsity=False): the dense N x N "
+                                      "optimisation is outside the accelerated path; use sparsity=True.")
         P, idx = self.affinity_in(X, log=False, return_indices=True)
-        self.affinity_in_ = P.contiguous()
-        self.NN_indices_ = idx.contiguous()
+        self._set_buffer("affinity_in_", P.contiguous())      # affinity_matcher.py:269-286
+        self._set_buffer("NN_indices_", idx.contiguous())
 
 
 class LargeVis(_EntropicInputMixin, _NeighborEmbeddingB200):
@@ -767,7 +800,7 @@ class LargeVis(_EntropicInputMixin, _NeighborEmbeddingB200):
 
     def _compute_gradient(self, Z, step):
         s, e = self.chunk_start_, self.chunk_end_
-        seed = int(self._actual_seed) if self.random_state is not None else 0
+        seed = self._kernel_seed()
         ops.largevis_grad(Z, s, e - s, self.affinity_in_, self.NN_indices_, self._grad, step,
                           neg=getattr(self, "neg_indices_", None), n_neg=self.n_negatives, seed=seed,
                           lam=float(self.early_exaggeration_coeff_), repulsion=float(self.repulsion_strength))
@@ -800,14 +833,14 @@ class TSNE(_EntropicInputMixin, _NeighborEmbeddingB200):
         s, e = self.chunk_start_, self.chunk_end_
         if not hasattr(self, "_tsne_ws"):
             self._tsne_ws = ops.tsne_workspace(e - s, Z.device)
-        lam = float(self.early_exaggeration_coeff_)
-        ops.tsne_grad(Z, s, e - s, self.affinity_in_, self.NN_indices_, lam, 0, self._grad, self._tsne_ws)
+        lam, rep = float(self.early_exaggeration_coeff_), float(self.repulsion_strength)
+        ops.tsne_grad(Z, s, e - s, self.affinity_in_, self.NN_indices_, lam, 0, self._grad, self._tsne_ws, repulsion=rep)
         if self.world_size > 1:
             # the reference has every rank compute the whole N x N term and divide by W (tsne.py:172-180);
             # here each rank owns a row range of the double sum and the scalar normaliser is all-reduced
             S = self._tsne_ws[:8].view(torch.float64)
             dist.all_reduce(S, op=dist.ReduceOp.SUM)
-        ops.tsne_grad(Z, s, e - s, self.affinity_in_, self.NN_indices_, lam, 1, self._grad, self._tsne_ws)
+        ops.tsne_grad(Z, s, e - s, self.affinity_in_, self.NN_indices_, lam, 1, self._grad, self._tsne_ws, repulsion=rep)
 
     def clear_memory(self):
         if hasattr(self, "_tsne_ws"):
@@ -843,7 +876,7 @@ class InfoTSNE(_EntropicInputMixin, _NeighborEmbeddingB200):
 
     def _compute_gradient(self, Z, step):
         s, e = self.chunk_start_, self.chunk_end_
-        seed = int(self._actual_seed) if self.random_state is not None else 0
+        seed = self._kernel_seed()
         ops.infotsne_grad(Z, s, e - s, self.affinity_in_, self.NN_indices_, self._grad, step,
                           neg=getattr(self, "neg_indices_", None), n_neg=self.n_negatives, seed=seed,
                           lam=float(self.early_exaggeration_coeff_), repulsion=float(self.repulsion_strength))

@@ -340,11 +340,12 @@ def tsne_workspace(n_local, device):
     return workspace(_lib.load().tdr_tsne_workspace_bytes(n_local), device)
 
 
-def tsne_grad(Z, row0, n_local, Pm, idx, lam, phase, grad, ws):
+def tsne_grad(Z, row0, n_local, Pm, idx, lam, phase, grad, ws, repulsion=1.0):
     k = Pm.shape[1] if Pm is not None else 0
     with torch.cuda.device(Z.device):
         check(_lib.load().tdr_tsne_grad_f32(ptr(Z), Z.shape[0], row0, n_local, ptr(Pm), ptr(idx), k, float(lam),
-                                            int(phase), ptr(grad), ptr(ws), ws.numel(), stream()), "tdr_tsne_grad_f32")
+                                            float(repulsion), int(phase), ptr(grad), ptr(ws), ws.numel(), stream()),
+              "tdr_tsne_grad_f32")
 
 
 def infotsne_grad(Z, row0, n_local, Pm, idx, grad, n_iter, neg=None, n_neg=300, seed=0, lam=1.0, repulsion=1.0):
