@@ -456,8 +456,9 @@ def gpu_arm(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"UMAP n_neighbors={K_NEIGHBORS} on {n}x{d} clustered synthetic "
-                                   + ("(BASELINE north-star size)" if n == 10_000_000 else
-                                      "(BASELINE configs[1])" if n == 1_000_000 else ""),
+                                   + ("(BASELINE north-star size)" if (n, d) == (10_000_000, 128) else
+                                      "(BASELINE configs[1])" if (n, d) == (1_000_000, 128) else
+                                      "(BASELINE configs[4])" if (n, d) == (50_000_000, 96) else ""),
                        "points": n, "dim": d, "row_order": args.order, "n_negatives": N_NEG, "schedule_max_iter": sched,
                        "negatives": "in-kernel Philox4x32-7", "parallelism": f"rows sharded x{world}", "exchange": exchange,
                        "l2": "per-iteration working set (CSR edge state %.0f MB + embedding %.0f MB) exceeds the 126 MB L2; "
@@ -516,14 +517,265 @@ def e2e_arm(args, dev, world):
                     "ranks) incl. H2D, exact kNN, sigma search, symmetrise, loop, D2H; h2d bytes are per rank"}
 
 
+# ----------------------------------------------------------------------------- BASELINE configs[3]: LargeVis
+LV_PERPLEXITY, LV_NEG = 30, 5
+
+
+def largevis_cpu(steps, warmup, n_total, d, sample_n=20000):
+    """oracle port of the LargeVis path (entropic affinity k = 90 + autograd loss + momentum SGD) on a bounded sample."""
+    import oracle
+    from oracle.largevis import largevis_loss
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    X = clustered(sample_n, d, "cpu")
+    k = 3 * LV_PERPLEXITY
+    t0 = time.perf_counter()
+    C, I = oracle.knn_chunked(X, k, block=4096)
+    logP, _, _ = oracle.entropic_affinity_rows(C, LV_PERPLEXITY, n_total=sample_n)
+    P = logP.exp()
+    t_aff = time.perf_counter() - t0
+    g = torch.Generator().manual_seed(0)
+    Z = torch.nn.Parameter(1e-4 * torch.randn(sample_n, 2, generator=g))
+    opt = torch.optim.SGD([Z], lr=max(sample_n / 4, 50), momentum=0.8)
+    rows = torch.arange(sample_n)
+
+    def one():
+        neg = oracle.adjust_negatives(torch.randint(0, sample_n - 1, (sample_n, LV_NEG), generator=g), rows)
+        opt.zero_grad(set_to_none=True)
+        largevis_loss(Z, P, I, neg, rows, sample_n).backward()
+        opt.step()
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    t_loop = time.perf_counter() - t0
+    its = steps / t_loop
+    return {"value": its * sample_n / n_total, "unit": "iters/s", "cores": torch.get_num_threads(), "kind": "port",
+            "value_measured": its, "sample_points": sample_n,
+            "sample": f"oracle LargeVis on {sample_n}x{d}: loop {its:.2f} it/s measured over {steps} iters (autograd, as the "
+                      f"reference), kNN k={k} + entropic affinity {t_aff:.1f}s; value extrapolated x{sample_n}/{n_total} (O(N) per iteration)"}
+
+
+def largevis_arm(args):
+    """LargeVis(perplexity=30, n_negatives=5) on args.points x args.dim, rows sharded over the ranks: kNN k = 90 +
+    entropic affinity once (untimed, reported), then per iteration: gradient kernel (fp32 atomics into an N x 2 buffer) ->
+    all-reduce (affinity_matcher.py:418-425) -> momentum SGD."""
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from torchdr_b200 import LargeVis, _lib, ops
+    from torchdr_b200.affinity import EntropicAffinity
+    from torchdr_b200.distributed import all_bounds
+
+    _lib.require_device(dev)
+    n, d, K, W = args.points, args.dim, args.steps, max(args.warmup, 3)
+    blocks = BLOCKS if K <= 200 else max(1, 2000 // K)
+    clk = ClockSampler(local_rank)
+    X = clustered(n, d, dev)
+    bounds = all_bounds(n, world)
+    s, e = bounds[rank]
+    aff = EntropicAffinity(perplexity=LV_PERPLEXITY, max_iter=100, knn_order="input")
+    _sync_all(world)
+    t0 = time.perf_counter()
+    P, idx = aff(X, log=False, return_indices=True)
+    torch.cuda.synchronize()
+    t_aff = time.perf_counter() - t0
+    k = P.shape[1]
+    g = torch.Generator(device=dev).manual_seed(0)
+    Z = torch.randn(n, 2, generator=g, device=dev)
+    Z = (1e-4 * Z / Z[:, 0].std()).contiguous()
+    grad, mom = torch.zeros_like(Z), torch.zeros_like(Z)
+    lr = max(n / 4, 50)
+    nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+    parts = {"grad": 0.0, "allreduce": 0.0, "sgd": 0.0}
+
+    def step(t, first, timed_parts=False):
+        grad.zero_()
+        if timed_parts:
+            ev[0].record()
+        ops.largevis_grad(Z, s, e - s, P, idx, grad, t, neg=None, n_neg=LV_NEG, seed=1234)
+        if timed_parts:
+            ev[1].record()
+        if world > 1:
+            dist.all_reduce(grad, op=dist.ReduceOp.SUM)
+        if timed_parts:
+            ev[2].record()
+        ops.sgd_momentum(Z, mom, grad, lr * min(1.0, (1 + 2 * min(t, 5) / 5) / 3), 0.8, first, nan_flag=nan_flag)
+        if timed_parts:
+            ev[3].record()
+            torch.cuda.synchronize()
+            parts["grad"] += ev[0].elapsed_time(ev[1])
+            parts["allreduce"] += ev[1].elapsed_time(ev[2])
+            parts["sgd"] += ev[2].elapsed_time(ev[3])
+
+    it = 0
+    for _ in range(W):
+        step(it, it == 0)
+        it += 1
+    block_ms = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with clk:
+        for _ in range(blocks):
+            _sync_all(world)
+            e0.record()
+            for _ in range(K):
+                step(it, False)
+                it += 1
+            e1.record()
+            _sync_all(world)
+            block_ms.append(e0.elapsed_time(e1))
+    for _ in range(5):  # per-stage split, outside the timed region
+        step(it, False, timed_parts=True)
+        it += 1
+    ms = torch.tensor(block_ms, device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    assert int(nan_flag.item()) == 0 and bool(torch.isfinite(Z).all())
+    block_list = [float(v) for v in ms.tolist()]
+    ms_per_step = float(np.median(block_list)) / K
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", FALLBACK_HBM_GBS))
+    alg = (e - s) * (16.0 + k * (4 + 4 + 8) + LV_NEG * 8 + (k + LV_NEG) * 8)  # SURVEY 8(d): ~2.3 KB / point / iteration
+    grad_ms = parts["grad"] / 5
+    out = None
+    if rank == 0:
+        out = {
+            "metric": f"LargeVis iters/sec ({n} x {d}, perplexity={LV_PERPLEXITY}, n_negatives={LV_NEG})",
+            "value": 1e3 / ms_per_step, "unit": "iters/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"LargeVis perplexity={LV_PERPLEXITY} n_negatives={LV_NEG} on {n}x{d} clustered synthetic "
+                                   "(BASELINE configs[3])", "points": n, "dim": d, "k": k, "parallelism": f"rows sharded x{world}",
+                       "exchange": "none" if world == 1 else "NCCL all-reduce of the N x 2 gradient (affinity_matcher.py:418-425)",
+                       "l2": "per-iteration working set (P + idx %.0f MB per rank) exceeds the L2; no flush" % ((e - s) * k * 8 / 1e6)},
+            "timing": {"blocks": blocks, "steps_per_block": K, "block_ms_max_over_ranks": block_list, "reported": "median block"},
+            "stage_ms_per_iteration": {k_: v / 5 for k_, v in parts.items()},
+            "affinity_seconds": t_aff,
+            "roofline": {"bound": "hbm", "kernel": "tdr::largevis_grad_kernel (fp32 atomics scatter)", "achieved": alg / (grad_ms * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": alg / (grad_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                         "algorithmic_bytes_per_launch": alg,
+                         "note": "per GPU, gradient kernel alone (events around it, outside the timed blocks); bytes per SURVEY 8(d): "
+                                 "16 + k (4 idx + 4 P + 8 z_j) + 5 x 8 read + (k + 5) x 8 scatter-add per local point"},
+            "gpu_launches": 3 * K * blocks, "clocks": clk.summary(),
+        }
+    e2e = None
+    if not args.no_e2e:
+        Xh = X.cpu().pin_memory().numpy()
+        del X, P, idx
+        m = LargeVis(perplexity=LV_PERPLEXITY, n_negatives=LV_NEG, max_iter=E2E_ITERS, init="normal", random_state=0,
+                     process_duplicates=False)
+        m.fit_transform(Xh[:max(20000, 2048 * world)])
+        _sync_all(world)
+        t0 = time.perf_counter()
+        Zh = m.fit_transform(Xh)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        assert Zh.shape == (n, 2) and np.isfinite(Zh).all()
+        e2e = {"value": E2E_ITERS / dt, "unit": "iters/s", "h2d_bytes_per_step": Xh.nbytes / world / E2E_ITERS,
+               "d2h_bytes_per_step": Zh.nbytes / E2E_ITERS, "seconds": dt, "iters": E2E_ITERS,
+               "note": "LargeVis(perplexity=30, max_iter=500, init='normal').fit_transform(numpy X), wall time max over ranks"}
+    if rank == 0:
+        if e2e:
+            out["e2e"] = e2e
+        if world == 1 and not args.no_cpu:
+            out["cpu_baseline"] = largevis_cpu(5, 1, n, d)
+    return out, world
+
+
+# ----------------------------------------------------------------------------- BASELINE configs[2]: dense entropic affinity
+def dense_entropic_arm(args):
+    """EntropicAffinity(perplexity=30, sparsity=False) on args.points x args.dim (100 k x 256): the full N x N distance
+    matrix (40 GB, resident in HBM) + the per-row eps search streaming each row once per bisection step."""
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    from torchdr_b200 import _lib, ops
+    from torchdr_b200.affinity import entropic_bound_scalars
+
+    _lib.require_device(dev)
+    n, d = args.points, args.dim
+    clk = ClockSampler(0)
+    X = clustered(n, d, dev)
+    perp = 30
+    target = float(torch.log(torch.tensor(perp)) + 1)
+    log_n = float(torch.log(torch.tensor(float(n), dtype=torch.float32)))
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    times = []
+    with clk:
+        for rep in range(max(2, min(args.steps, 3))):
+            torch.cuda.synchronize()
+            ev[0].record()
+            C = ops.pairwise_full(X, None, metric="sqeuclidean", exclude_diag=True)
+            ev[1].record()
+            logP, eps, log_norm = ops.entropic_dense_rows(C, target, log_n, entropic_bound_scalars(n, perp), 100, inplace=True)
+            ev[2].record()
+            torch.cuda.synchronize()
+            times.append((ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])))
+            if rep + 1 < max(2, min(args.steps, 3)):
+                del C, logP
+    t_dist, t_rows = min(t[0] for t in times), min(t[1] for t in times)
+    # sampled-row check of eps against the oracle restatement of entropic.py:272-310 on the same distance rows
+    parity = None
+    if not args.no_parity:
+        import oracle
+
+        C2 = ops.pairwise_full(X[:256].contiguous(), X, metric="sqeuclidean", exclude_diag=False)
+        C2[torch.arange(256), torch.arange(256)] += 1e12  # torch.py:111-116
+        _, eps_ref, _ = oracle.entropic_affinity_rows(C2.cpu(), perp, n_total=n)
+        rel = float(((eps[:256].cpu() - eps_ref).abs() / eps_ref.abs()).max())
+        parity = {"rows_checked": 256, "eps_max_rel_err_vs_oracle": rel, "tolerance": 2e-5}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", FALLBACK_HBM_GBS))
+    total_s = (t_dist + t_rows) * 1e-3
+    return {
+        "metric": f"dense entropic affinity ({n} x {d}, perplexity=30, sparsity=False): rows/s", "value": n / total_s,
+        "unit": "rows/s", "n_gpus": 1, "steps": len(times), "warmup": 1, "ms_per_step": (t_dist + t_rows),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"EntropicAffinity(perplexity=30, sparsity=False) on {n}x{d} clustered synthetic (BASELINE configs[2])",
+                   "points": n, "dim": d},
+        "stage_ms": {"pairwise_full (fp32 SIMT tile kernel, writes 4 N^2 bytes)": t_dist,
+                     "entropic_dense_rows (one CTA per row, row re-read from L2 per bisection step, log_P in place)": t_rows},
+        "distance_tflops_2nnd": 2.0 * n * n * d / (t_dist * 1e-3) / 1e12,
+        "roofline": {"bound": "hbm", "kernel": "tdr::entropic_dense_kernel", "achieved": 8.0 * n * n / (t_rows * 1e-3) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": 8.0 * n * n / (t_rows * 1e-3) / 1e9 / peak, "traffic": None,
+                     "note": "algorithmic bytes = one read of C + one write of log_P (8 N^2); the bisection passes re-read the "
+                             "row from L2 (400 KB per row), so the kernel is bound by exp / div issue, not by HBM"},
+        "parity": parity, "gpu_launches": 2 * len(times), "clocks": clk.summary(),
+    }, 1
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--points", type=int, default=10_000_000)
-    ap.add_argument("--dim", type=int, default=128)
+    ap.add_argument("--config", default="umap", choices=["umap", "c3", "c4", "c5"],
+                    help="umap: UMAP k=15 (default 10 M x 128, the north star; --points 1000000 = BASELINE configs[1]); "
+                         "c3: dense entropic affinity 100 k x 256; c4: LargeVis 10 M x 64; c5: UMAP 50 M x 96")
+    ap.add_argument("--points", type=int, default=None)
+    ap.add_argument("--dim", type=int, default=None)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
@@ -532,6 +784,9 @@ def main():
     ap.add_argument("--order", default="generator", choices=["generator", "shuffled"],
                     help="row order of the synthetic points: the reference generator's (clusters contiguous) or shuffled")
     args = ap.parse_args()
+    dflt = {"umap": (10_000_000, 128), "c3": (100_000, 256), "c4": (10_000_000, 64), "c5": (50_000_000, 96)}[args.config]
+    args.points = args.points or dflt[0]
+    args.dim = args.dim or dflt[1]
     rank = int(os.environ.get("RANK", "0"))
     # NCCL prints its version banner to STDOUT when NCCL_DEBUG=VERSION; the contract is ONE JSON line there
     if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
@@ -546,8 +801,9 @@ def main():
         os.write(real_stdout, (json.dumps(obj) + "\n").encode())
 
     workload = (f"UMAP n_neighbors={K_NEIGHBORS} on {args.points}x{args.dim} clustered synthetic "
-                + ("(BASELINE north-star size)" if args.points == 10_000_000 else
-                   "(BASELINE configs[1])" if args.points == 1_000_000 else ""))
+                + ("(BASELINE north-star size)" if (args.points, args.dim) == (10_000_000, 128) else
+                   "(BASELINE configs[1])" if (args.points, args.dim) == (1_000_000, 128) else
+                   "(BASELINE configs[4])" if (args.points, args.dim) == (50_000_000, 96) else ""))
     metric = f"UMAP iters/sec ({args.points} x {args.dim}, n_neighbors=15); affinity-kernel GB/s in `affinity_kernel`"
     if args.impl == "reference":
         if rank != 0:
@@ -573,6 +829,16 @@ def main():
         emit(line)
         return
 
+    if args.config in ("c3", "c4"):
+        out, world = dense_entropic_arm(args) if args.config == "c3" else largevis_arm(args)
+        if rank == 0:
+            emit(out)
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     out, (rank, world, dev) = gpu_arm(args)
     e2e = None
     if not args.no_e2e:

@@ -391,7 +391,7 @@ def test_umap_single_steps_match_oracle(ops):
     print(f"worst single-step rel error {worst:.3e}")
 
 
-@pytest.mark.parametrize("precise", [1, 0, 2], ids=["parity-kernel", "throughput-kernel", "powf-kernel"])
+@pytest.mark.parametrize("precise", [1, 0], ids=["parity-kernel", "throughput-kernel"])
 def test_umap_fixed_iteration_count_matches_reference(ops, precise):
     """Fixed iteration count from the reference's own Z0, injected negatives: T <= 3 within 1e-4 relative.
 

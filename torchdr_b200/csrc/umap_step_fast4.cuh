@@ -290,18 +290,18 @@ struct RunParams {
     float lrs[kMaxRunSteps];
 };
 
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* a) {
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* a) {
     uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a) : "memory");
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_sys(uint32_t* a, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* a) {
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* a) {
     uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a) : "memory");
     return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* a, uint32_t v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(a), "r"(v) : "memory");
 }
 __device__ __forceinline__ void st_release_gpu(uint32_t* a, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a), "r"(v) : "memory");
@@ -319,26 +319,33 @@ __device__ __forceinline__ unsigned long long global_ns() {
 
 // Barrier between two iterations, executed by thread 0 of every CTA (the CTA's other threads wait at __syncthreads).
 // `epoch` = number of barriers completed once this one is.  Returns false if the run was aborted.
+// Release side: the CTA barrier ordered every store of this CTA (own buffer, NVLink peers, epoch_of_next_sample) before
+// this point; one fence makes them visible at the scope the consumers read from (system scope when rows also went to
+// peers), then the arrival is counted.  Acquire side: the flag words are polled with RELAXED loads (a spinning
+// ld.acquire would issue a fence + L1 invalidation per poll from every CTA) and ONE fence after the wait orders the
+// next iteration's loads behind it and drops stale L1 lines of the embedding buffers.
 __device__ bool run_barrier(const UmapStepParams& p, const RunParams& rp, uint32_t epoch, uint32_t* work_used) {
     uint32_t* const arrive = rp.sync;
     uint32_t* const go = rp.sync + 1;
     uint32_t* const status = rp.sync + 4;
-    // every store of this CTA (own buffer, NVLink peers, epoch_of_next_sample) was ordered before this point by the
-    // CTA barrier; the fence makes them visible at the scope the consumers read from before the arrival is announced
-    if (p.n_peers != 0) __threadfence_system(); else __threadfence();
+    const bool multi = p.n_peers != 0;
+    if (multi) __threadfence_system(); else __threadfence();
     const uint32_t old = atom_add_acq_rel_gpu(arrive, 1u);
     const unsigned long long t0 = global_ns();
+    bool ok = true;
     if (old == gridDim.x - 1) {  // last CTA of this rank
         *arrive = 0u;
         *work_used = 0u;
-        bool ok = true;
-        if (p.n_peers != 0) {
+        if (multi) {
+            // release: ONE system-scope fence orders this rank's stores (the other CTAs' were observed through the
+            // arrival counter) before the flag stores, which can then be relaxed
             __threadfence_system();
-            for (int q = 0; q < p.n_peers; ++q) st_release_sys(rp.peer_flags[q] + rp.rank, epoch);
+            for (int q = 0; q < p.n_peers; ++q) st_relaxed_sys(rp.peer_flags[q] + rp.rank, epoch);
             for (int q = 0; q < p.n_peers && ok; ++q) {
                 const uint32_t* f = rp.my_flags + rp.peer_rank[q];
-                while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
-                    if (global_ns() - t0 > rp.timeout_ns) {
+                unsigned spins = 0;
+                while ((int32_t)(ld_relaxed_sys(f) - epoch) < 0) {
+                    if ((++spins & 1023u) == 0 && global_ns() - t0 > rp.timeout_ns) {
                         ok = false;
                         break;
                     }
@@ -348,20 +355,26 @@ __device__ bool run_barrier(const UmapStepParams& p, const RunParams& rp, uint32
         }
         if (!ok) *status = 1u;
         st_release_gpu(go, ok ? epoch : kAbort);
-        return ok;
-    }
-    for (;;) {
-        const uint32_t v = p.n_peers != 0 ? ld_acquire_sys(go) : ld_acquire_gpu(go);
-        if (v == kAbort) return false;
-        if ((int32_t)(v - epoch) >= 0) break;
-        if (global_ns() - t0 > 2 * rp.timeout_ns) {
-            *status = 2u;
-            st_release_gpu(go, kAbort);
-            return false;
+    } else {
+        unsigned spins = 0;
+        for (;;) {
+            const uint32_t v = ld_relaxed_gpu(go);
+            if (v == kAbort) {
+                ok = false;
+                break;
+            }
+            if ((int32_t)(v - epoch) >= 0) break;
+            __nanosleep(40);
+            if ((++spins & 1023u) == 0 && global_ns() - t0 > 2 * rp.timeout_ns) {
+                *status = 2u;
+                st_release_gpu(go, kAbort);
+                ok = false;
+                break;
+            }
         }
     }
-    if (p.n_peers != 0) __threadfence_system(); else __threadfence();
-    return true;
+    if (multi) __threadfence_system(); else __threadfence();
+    return ok;
 }
 
 __global__ void __launch_bounds__(kFastThreads, kOcc4)
