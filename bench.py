@@ -320,8 +320,10 @@ def gpu_arm(args):
     a, b = find_ab_params(1.0, 0.1)
     g = torch.Generator(device=dev).manual_seed(0)
     Z = torch.randn(n, 2, generator=g, device=dev)
-    Za = (1e-4 * Z / Z[:, 0].std()).contiguous()
-    Zb = Za.clone()
+    ZZ = torch.empty((2, n, 2), device=dev)  # the two buffers side by side (one L2 access-policy window covers both)
+    ZZ[0] = 1e-4 * Z / Z[:, 0].std()
+    ZZ[1] = ZZ[0]
+    Za, Zb = ZZ[0], ZZ[1]
     # learning rates of the reference schedule (LinearLR 1 -> 0 over MAX_ITER), host-side scalars
     lr_all = np.asarray([1.0 * (1.0 - t / sched) for t in range(total_iters)], dtype=np.float32)
     stats = torch.zeros(2, dtype=torch.int64, device=dev)

@@ -63,8 +63,8 @@ TDR_API size_t tdr_knn_workspace_bytes(int64_t nq, int64_t ndb, int d, int k);
 
 /* Per-call options of the two kNN entry points (no process-wide switches):
  * path   kernel selection: AUTO = tcgen05 tensor-core kernel (fp16 hi/lo split) whenever the tile shapes fit
- *        (d <= 128 and lists + tiles <= 227 KB of shared memory: k <= 33 at d = 128, k <= 96 at d <= 64), else
- *        the fp32 SIMT kernel; SIMT / TC force one (TC returns TDR_E_UNSUPPORTED if the shape does not fit).
+ *        (d <= 256, k <= 96 and query tile + lists + a two-stage ring <= 227 KB of shared memory: k <= 96 at
+ *        d <= 128, k <= 33 at d <= 256), else the fp32 SIMT kernel; SIMT / TC force one (TC returns TDR_E_UNSUPPORTED if the shape does not fit).
  * prune  tile-pruned sweep of the tensor-core kernel (queries that are rows of the database, >= 64 database
  *        tiles): database tiles whose bounding box is farther from the query tile's box than a bound on the
  *        tile's k-th neighbour distances are not swept.  Results are bit-identical to the full sweep.
@@ -87,10 +87,11 @@ TDR_API int tdr_knn_f32(const float* Xq, int64_t nq, int64_t q_row0,
                 int path, int prune, uint64_t* sweep_stats,
                 void* ws, size_t ws_bytes, tdr_stream_t stream);
 
-/* Full matrix C[n,m] (k=None path, distance/torch.py:81-116).  Y may equal X.
+/* Full matrix C[n,m] (k=None path, distance/torch.py:81-116).  Y may equal X.  path as above: AUTO = the
+ * tcgen05 kernel with a dense epilogue for d <= 256, else the fp32 SIMT tile kernel.
  * Workspace: tdr_knn_workspace_bytes(n, m, d, 1). */
 TDR_API int tdr_pairwise_full_f32(const float* X, int64_t n, const float* Y, int64_t m, int d,
-                          int metric, int exclude_diag, float* C /*[n,m]*/,
+                          int metric, int exclude_diag, float* C /*[n,m]*/, int path,
                           void* ws, size_t ws_bytes, tdr_stream_t stream);
 
 /* pairwise_distances_indexed, per-query key lists (distance/base.py:252-405, 2-D key_indices):
@@ -100,6 +101,14 @@ TDR_API int tdr_indexed_dist_f32(const float* X, const int64_t* query_idx, int64
                                  const float* Y, int64_t ny, int d,
                                  const void* key_idx, int key_is_int64, int k, int metric,
                                  float* out /*[nq,k]*/, tdr_stream_t stream);
+
+/* Row ordering for inputs without index locality (torchdr_b200/reorder.py; no counterpart in the reference, which
+ * hands unordered rows to FAISS): nearest-centre assignment of one level of the Voronoi tree.  Entry i is row rows[i]
+ * of X[., d], a member of tree node node[i]; centres is [n_nodes, B, d], cnorm [n_nodes, B] holds |c|^2 (+inf = not a
+ * centre); child_out[i] = argmin_c |c|^2 - 2 x.c, ties to the lower c.  d <= 512, B <= 64. */
+TDR_API int tdr_tree_assign_f32(const float* X, int d, const int64_t* rows, const int64_t* node, int64_t m,
+                                const float* centres, const float* cnorm, int B, int64_t* child_out,
+                                tdr_stream_t stream);
 
 /* ---- (ii) per-row bandwidth search --------------------------------------
  * UMAPAffinity rows: rho = row min, sigma by bracket+bisection

@@ -115,7 +115,7 @@ def knn(Xq, Xdb, k, q_row0=0, exclude_self=True, metric="sqeuclidean", path="aut
     return v, i.int()
 
 
-def pairwise_full(X, Y=None, metric="sqeuclidean", exclude_diag=False):
+def pairwise_full(X, Y=None, metric="sqeuclidean", exclude_diag=False, path="auto"):
     return oracle.pairwise_full(X, Y, metric, exclude_diag)
 
 

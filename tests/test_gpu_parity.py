@@ -46,6 +46,31 @@ def test_knn_matches_reference_golden(ops, name):
     assert bool((C[:, 1:] >= C[:, :-1]).all())
 
 
+@pytest.mark.parametrize("n,d,k", [(3000, 128, 90), (2500, 256, 15), (2500, 256, 33), (2000, 200, 20), (1500, 192, 96),
+                                   (700, 65, 96)])
+def test_knn_tensor_core_wide_shapes(ops, n, d, k):
+    """The tcgen05 kernel beyond round 1's tile shapes — the entropic k = 3 * perplexity = 90 on 128-dimensional input
+    (t-SNE / LargeVis) and d up to 256 — with the K-atom TMA ring: decided entries equal the fp64 ranking and the
+    fp32 SIMT kernel's, distances within the fp32 expanded-form error of the norms."""
+    X = blobs(n, d, 6, n + d + k)
+    Xd = _cuda(X)
+    C, I = ops.knn(Xd, Xd, k, path="tc")
+    Cs, Is = ops.knn(Xd, Xd, k, path="simt")
+    idx64, d64, entry_ok, set_ok = oracle.knn_ambiguity(X, k)
+    assert torch.equal(I.cpu().long()[entry_ok], idx64[entry_ok])
+    assert torch.equal(Is.cpu().long()[entry_ok], idx64[entry_ok])
+    same_set = (I.cpu().long().sort(1)[0] == idx64.sort(1)[0]).all(1)
+    assert bool(same_set[set_ok].all())
+    scale = float((X**2).sum(1).max()) * 2
+    assert float((C.cpu().double() - d64).abs().max()) < 2e-6 * scale
+    assert bool((C[:, 1:] >= C[:, :-1]).all())
+    if k <= 33:  # fused rows on the same shapes
+        _, I2, P, rho, sigma = ops.knn_umap_fused(Xd, Xd, k, path="tc")
+        P_ref, rho_ref, sig_ref = oracle.umap_affinity_rows(C.cpu(), k)
+        assert torch.equal(I2, I) and torch.equal(rho.cpu(), rho_ref)
+        torch.testing.assert_close(sigma.cpu(), sig_ref, rtol=1e-5, atol=0)
+
+
 def test_knn_euclidean_metric(ops):
     g = golden("knn_n300_d16_k15")
     X, k = t(g["X"]), 15
@@ -96,6 +121,8 @@ def test_knn_cross_and_chunk(ops):
 @pytest.mark.parametrize("kind,n,d,k", [("clustered", 60_000, 128, 15), ("clustered", 20_000, 50, 90),
                                         ("clustered", 30_000, 128, 32), ("clustered", 24_000, 64, 20),
                                         ("clustered", 9_000, 128, 1),
+                                        ("clustered", 16_000, 128, 90), ("clustered", 20_000, 256, 15),
+                                        ("clustered", 12_000, 200, 33),
                                         ("uniform", 12_000, 64, 15), ("shuffled", 16_000, 128, 15)])
 def test_knn_pruned_sweep_is_bit_identical(ops, kind, n, d, k):
     """The tile-pruned sweep (csrc/knn_tc.cu) must return exactly what the full sweep returns — distances,
@@ -203,6 +230,31 @@ def test_pairwise_full(ops):
         assert not bool(bad.any()), f"CPU oracle still deviates from the fp64 distances in {msg}"
     torch.testing.assert_close(Ce**2, Co, rtol=1e-5, atol=atol)
     assert bool((Ce >= 0).all())
+
+
+@pytest.mark.parametrize("n,m,d", [(700, 500, 256), (300, 300, 130), (257, 1000, 64), (1100, 1100, 200)])
+def test_pairwise_full_on_tensor_cores(ops, n, m, d):
+    """tdr_pairwise_full_f32 through the tcgen05 kernel's dense epilogue (d <= 256) against fp64 and the SIMT kernel:
+    both metrics, the 1e12 diagonal, cross and self shapes, m not a multiple of 4 (scalar store path) and of 128."""
+    X = blobs(n, d, 5, n + m + d)
+    same = n == m
+    Y = X if same else blobs(m, d, 5, 3 * n + d)
+    Xd, Yd = _cuda(X), (None if same else _cuda(Y))
+    truth = torch.cdist(X.double(), Y.double()) ** 2
+    atol = 2e-6 * float(X.pow(2).sum(1).max() + Y.pow(2).sum(1).max())
+    for metric in ("sqeuclidean", "euclidean"):
+        Ct = ops.pairwise_full(Xd, Yd, metric=metric, exclude_diag=same, path="tc").cpu()
+        Cs = ops.pairwise_full(Xd, Yd, metric=metric, exclude_diag=same, path="simt").cpu()
+        assert Ct.shape == (n, m)
+        off = ~torch.eye(n, dtype=torch.bool) if same else torch.ones(n, m, dtype=torch.bool)
+        sq_t = Ct**2 if metric == "euclidean" else Ct
+        sq_s = Cs**2 if metric == "euclidean" else Cs
+        assert float((sq_t.double() - truth)[off].abs().max()) < atol
+        assert float((sq_s.double() - truth)[off].abs().max()) < atol
+        if same:
+            assert bool((Ct.diag() >= 1e12 - 1e6).all()) and bool((Cs.diag() >= 1e12 - 1e6).all())
+        if metric == "euclidean":
+            assert bool((Ct >= 0).all())
 
 
 def test_knn_large_properties(ops):

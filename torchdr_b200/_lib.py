@@ -34,7 +34,8 @@ SIGNATURES = {
     "tdr_knn_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int]),
     "tdr_knn_f32": (c_int, [P, c_int64, c_int64, P, c_int64, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P, P,
                             c_size_t, P]),
-    "tdr_pairwise_full_f32": (c_int, [P, c_int64, P, c_int64, c_int, c_int, c_int, P, P, c_size_t, P]),
+    "tdr_pairwise_full_f32": (c_int, [P, c_int64, P, c_int64, c_int, c_int, c_int, P, c_int, P, c_size_t, P]),
+    "tdr_tree_assign_f32": (c_int, [P, c_int, P, P, c_int64, P, P, c_int, P, P]),
     "tdr_umap_affinity_f32": (c_int, [P, c_int64, c_int, c_int, P, P, P, P]),
     "tdr_entropic_affinity_f32": (c_int, [P, c_int64, c_int, c_float, c_float, c_int, c_float, c_float, c_float,
                                           c_float, c_int, P, P, P, P]),

@@ -30,6 +30,9 @@ enum { MODE_KNN = 0, MODE_FUSED = 1, MODE_FULL = 2 };
 
 // knn_tc.cu
 bool knn_tc_supported(int d, int k);
+bool knn_tc_full_supported(int d);
+int knn_tc_full_launch(const float* X, int64_t n, const float* Y, int64_t m, int d, bool same, int metric,
+                       int exclude_diag, float* C, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t knn_tc_workspace_bytes(int64_t nq, int64_t ndb, int d, int k, bool same);
 int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb, int64_t ndb, int d, int k,
                   bool same, int exclude_self, int metric, int fused, int max_iter, float* out_dist, int32_t* out_idx,
@@ -543,15 +546,22 @@ extern "C" TDR_API int tdr_knn_umap_fused_f32(const float* Xq, int64_t nq, int64
 }
 
 extern "C" TDR_API int tdr_pairwise_full_f32(const float* X, int64_t n, const float* Y, int64_t m, int d, int metric,
-                                     int exclude_diag, float* C, void* ws, size_t ws_bytes,
+                                     int exclude_diag, float* C, int path, void* ws, size_t ws_bytes,
                                      tdr_stream_t stream) {
     TDR_CHECK_ARG(X && Y && C, "tdr_pairwise_full_f32: null pointer");
+    TDR_CHECK_ARG(path >= TDR_KNN_PATH_AUTO && path <= TDR_KNN_PATH_TC, "tdr_pairwise_full_f32: path must be 0, 1 or 2");
     TDR_CHECK_ARG(n >= 1 && m >= 1 && d >= 1, "tdr_pairwise_full_f32: bad shape");
     TDR_CHECK_ARG(m < 0x7fffffffLL, "tdr_pairwise_full_f32: m must fit int32");
     TDR_CHECK_ARG(metric == TDR_METRIC_SQEUCLIDEAN || metric == TDR_METRIC_EUCLIDEAN,
                   "[TorchDR] ERROR : metric id %d is not supported.", metric);
     cudaStream_t st = (cudaStream_t)stream;
     const bool same = (X == Y && n == m);
+    if (path != TDR_KNN_PATH_SIMT && knn_tc_full_supported(d))
+        return knn_tc_full_launch(X, n, Y, m, d, same, metric, exclude_diag, C, ws, ws_bytes, st);
+    if (path == TDR_KNN_PATH_TC) {
+        set_error("tdr_pairwise_full_f32: tensor-core path forced but unsupported for d=%d", d);
+        return TDR_E_UNSUPPORTED;
+    }
     Prepared pr;
     int rc = prepare(X, n, Y, m, d, same, ws, ws_bytes, st, &pr);
     if (rc != TDR_OK) return rc;

@@ -8,9 +8,12 @@
 // is 2^-22 relative — below the fp32 rounding of the reference's own sgemm.  fp16 MMAs run at
 // the full 16-bit tensor rate, i.e. 3 passes cost what 1.5 TF32 passes would.
 //
-// One CTA (256 threads, 1 per SM) owns 128 query rows: their hi/lo tiles stay resident in
+// One CTA (256 or 384 threads, 1 per SM) owns 128 query rows: their hi/lo tiles stay resident in
 // shared memory (TMA, 128B swizzle) for the whole sweep over the database, which streams through
-// a ring of TMA stages in 128-row tiles.  Warp 0 = TMA producer, warp 1 = MMA issuer (one
+// a ring of TMA stages.  A stage is one K-ATOM of a 128-row database tile ([128 x 64] hi + lo = 32 KB), not a
+// whole tile: the ring then fits next to the resident queries and the top-k lists for every shape up to
+// d = 256 / k = 33 and d = 128 / k = 96 (the entropic k = 3 * perplexity of t-SNE / LargeVis), and the
+// MMAs of an atom start as soon as that atom has landed.  Warp 0 = TMA producer, warp 1 = MMA issuer (one
 // thread), warp 2 = TMEM allocator, warps 4-7 = epilogue: thread t owns TMEM lane t = query row
 // t, reads its 128 accumulator columns with tcgen05.ld, forms the distance and compares it with
 // its row's running k-th best held in a register; the rare survivor is insertion-sorted into the
@@ -33,7 +36,11 @@ namespace tc {
 constexpr int BM = 128, BN = 128, KATOM = 64;  // 64 fp16 = one 128-byte swizzle row
 constexpr int NT = 256;
 constexpr int TILE_BYTES = BM * KATOM * 2;  // 16 KB: one [128 x 64] fp16 box
-constexpr int MAX_ATOMS = 2;                // d <= 128
+constexpr int MAX_ATOMS = 4;                // d <= 256
+constexpr int STAGE_BYTES = 2 * TILE_BYTES; // one ring stage: hi + lo of one atom of a database tile
+constexpr int MAX_STAGES = 8;
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+constexpr size_t SMEM_MISC = 512 + 1024;    // barriers + TMEM slot, 1024-byte alignment slack
 constexpr int MAX_K = 96;                   // top-k lists in shared memory next to the operand tiles
 constexpr int kMaxEpl = MAX_K / 32;
 
@@ -242,6 +249,10 @@ struct Params {
     float* P;
     float* rho;
     float* sigma;
+    // dense mode (tdr_pairwise_full_f32 on the tensor cores): every distance of the sweep is written to
+    // c_full[row * ndb + col] instead of being filtered; no lists
+    float* c_full;
+    int full_exclude_diag;  // add 1e12 where the global query row equals the column (torch.py:111-116)
     // re-sweep of selected query tiles (robust mode, knn_tc_kernel<true> only): CTA b works on query tile
     // qtile_map[b]; CTAs >= *qtile_count exit.  Kept at the end so that the default kernel's argument layout is
     // the one that was verified on hardware.
@@ -259,13 +270,14 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int atoms = prm.atoms, stages = prm.stages, k = prm.k, kpad = prm.kpad;
-    const int a_bytes = atoms * 2 * TILE_BYTES;  // hi + lo
+    const int a_bytes = atoms * STAGE_BYTES;  // hi + lo
     unsigned char* a_tiles = smem;                    // [atoms][hi, lo][16 KB]
-    unsigned char* b_tiles = smem + a_bytes;          // [stages][atoms][hi, lo][16 KB]
-    const int nl = 1 + prm.dual;  // list sets
-    float* ld_s = reinterpret_cast<float*>(b_tiles + (size_t)stages * a_bytes);  // [nl][128][kpad]
-    int* li_s = reinterpret_cast<int*>(ld_s + nl * BM * kpad);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(li_s + nl * BM * kpad);
+    unsigned char* b_tiles = smem + a_bytes;          // [stages][hi, lo][16 KB]: one atom of a database tile per stage
+    const int nl = 1 + prm.dual;  // list sets (epilogue warpgroups)
+    const int n_lists = prm.c_full ? 0 : nl;
+    float* ld_s = reinterpret_cast<float*>(b_tiles + (size_t)stages * STAGE_BYTES);  // [n_lists][128][kpad]
+    int* li_s = reinterpret_cast<int*>(ld_s + n_lists * BM * kpad);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(li_s + n_lists * BM * kpad);
     // barrier slots: 0 a_full | 1..S full | 1+S..2S empty | 2S+1, 2S+2 tmem_full | 2S+3, 2S+4 tmem_empty
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 5);
 
@@ -320,7 +332,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    for (int i = tid; i < nl * BM * kpad; i += (int)blockDim.x) {
+    for (int i = tid; i < n_lists * BM * kpad; i += (int)blockDim.x) {
         ld_s[i] = INFINITY;
         li_s[i] = 0x7fffffff;
     }
@@ -339,20 +351,21 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                 tma_load_2d(smem_u32(a_tiles + (a * 2 + 1) * TILE_BYTES), &map_q_lo, BAR(0), a * KATOM,
                             (int)(prm.q_tile_row0 + q0));
             }
+            int64_t c = 0;  // ring slot counter: one slot per (tile, atom)
             for (int64_t t = 0; t < n_sweep; ++t) {
-                const int s = (int)(t % stages);
-                const uint32_t ph = (uint32_t)((t / stages) & 1);
                 const int row_db = (int)(tile_of(t) * BN);
-                mbar_wait(BAR(B_EMPTY + s), ph ^ 1u);
-                if ((prm.debug & 4) && t >= stages) {
-                    mbar_arrive(BAR(B_FULL + s));
-                    continue;
-                }
-                mbar_expect_tx(BAR(B_FULL + s), (uint32_t)a_bytes);
-                unsigned char* dst = b_tiles + (size_t)s * a_bytes;
-                for (int a = 0; a < atoms; ++a) {
-                    tma_load_2d(smem_u32(dst + (a * 2 + 0) * TILE_BYTES), &map_db_hi, BAR(B_FULL + s), a * KATOM, row_db);
-                    tma_load_2d(smem_u32(dst + (a * 2 + 1) * TILE_BYTES), &map_db_lo, BAR(B_FULL + s), a * KATOM, row_db);
+                for (int a = 0; a < atoms; ++a, ++c) {
+                    const int s = (int)(c % stages);
+                    const uint32_t ph = (uint32_t)((c / stages) & 1);
+                    mbar_wait(BAR(B_EMPTY + s), ph ^ 1u);
+                    if ((prm.debug & 4) && c >= stages) {
+                        mbar_arrive(BAR(B_FULL + s));
+                        continue;
+                    }
+                    mbar_expect_tx(BAR(B_FULL + s), (uint32_t)STAGE_BYTES);
+                    unsigned char* dst = b_tiles + (size_t)s * STAGE_BYTES;
+                    tma_load_2d(smem_u32(dst), &map_db_hi, BAR(B_FULL + s), a * KATOM, row_db);
+                    tma_load_2d(smem_u32(dst + TILE_BYTES), &map_db_lo, BAR(B_FULL + s), a * KATOM, row_db);
                 }
             }
         }
@@ -360,36 +373,38 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
             mbar_wait(BAR(0), 0);
+            int64_t c = 0;
             for (int64_t t = 0; t < n_sweep; ++t) {
-                const int s = (int)(t % stages);
-                const uint32_t ph = (uint32_t)((t / stages) & 1);
                 const int as = (int)(t & 1);
                 const uint32_t aph = (uint32_t)((t >> 1) & 1);
                 mbar_wait(BAR(T_EMPTY + as), aph ^ 1u);
-                mbar_wait(BAR(B_FULL + s), ph);
-                tc_fence_after();
                 const uint32_t d_big = tmem_base + (uint32_t)(as * 256);
                 const uint32_t d_small = d_big + 128u;
-                const unsigned char* bt = b_tiles + (size_t)s * a_bytes;
-                for (int a = 0; a < ((prm.debug & 2) ? 0 : atoms); ++a) {
-                    const uint64_t a_hi = make_smem_desc(smem_u32(a_tiles + (a * 2 + 0) * TILE_BYTES));
-                    const uint64_t a_lo = make_smem_desc(smem_u32(a_tiles + (a * 2 + 1) * TILE_BYTES));
-                    const uint64_t b_hi = make_smem_desc(smem_u32(bt + (a * 2 + 0) * TILE_BYTES));
-                    const uint64_t b_lo = make_smem_desc(smem_u32(bt + (a * 2 + 1) * TILE_BYTES));
+                for (int a = 0; a < atoms; ++a, ++c) {
+                    const int s = (int)(c % stages);
+                    const uint32_t ph = (uint32_t)((c / stages) & 1);
+                    mbar_wait(BAR(B_FULL + s), ph);
+                    tc_fence_after();
+                    if (!(prm.debug & 2)) {
+                        const unsigned char* bt = b_tiles + (size_t)s * STAGE_BYTES;
+                        const uint64_t a_hi = make_smem_desc(smem_u32(a_tiles + (a * 2 + 0) * TILE_BYTES));
+                        const uint64_t a_lo = make_smem_desc(smem_u32(a_tiles + (a * 2 + 1) * TILE_BYTES));
+                        const uint64_t b_hi = make_smem_desc(smem_u32(bt));
 #pragma unroll
-                    for (int kk = 0; kk < KATOM / 16; ++kk) {
-                        const uint64_t adv = (uint64_t)(kk * 2);  // 16 fp16 = 32 B -> +2 in the >>4 address field
-                        const uint32_t acc = (a | kk) ? 1u : 0u;
-                        // The kernel is bound by shared-memory operand bandwidth (A + B are both read from smem for
-                        // every MMA).  hi.hi and hi.lo share the A operand: the database hi and lo tiles of an atom
-                        // are adjacent in smem (16 KB + 16 KB = 256 K-major rows), so ONE N = 256 MMA produces
-                        // [hi.hi | hi.lo] into TMEM columns [0,128) | [128,256) with a single read of A_hi.
-                        tc_mma_f16(d_big, a_hi + adv, b_hi + adv, kInstrDescN256, acc);
-                        tc_mma_f16(d_small, a_lo + adv, b_hi + adv, kInstrDesc, 1u);
+                        for (int kk = 0; kk < KATOM / 16; ++kk) {
+                            const uint64_t adv = (uint64_t)(kk * 2);  // 16 fp16 = 32 B -> +2 in the >>4 address field
+                            const uint32_t acc = (a | kk) ? 1u : 0u;
+                            // The kernel is bound by shared-memory operand bandwidth (A + B are both read from smem for
+                            // every MMA).  hi.hi and hi.lo share the A operand: the database hi and lo tiles of an atom
+                            // are adjacent in smem (16 KB + 16 KB = 256 K-major rows), so ONE N = 256 MMA produces
+                            // [hi.hi | hi.lo] into TMEM columns [0,128) | [128,256) with a single read of A_hi.
+                            tc_mma_f16(d_big, a_hi + adv, b_hi + adv, kInstrDescN256, acc);
+                            tc_mma_f16(d_small, a_lo + adv, b_hi + adv, kInstrDesc, 1u);
+                        }
                     }
+                    tc_commit(BAR(B_EMPTY + s));  // ring slot reusable once these MMAs retire
                 }
-                tc_commit(BAR(B_EMPTY + s));   // smem stage reusable once these MMAs retire
-                tc_commit(BAR(T_FULL + as));   // accumulators ready for the epilogue
+                tc_commit(BAR(T_FULL + as));  // accumulators ready for the epilogue
             }
         }
     } else if (warp >= 4) {
@@ -465,7 +480,58 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
 
         const int c_beg = prm.dual ? 64 * wg : 0;   // first column of this warpgroup's share
         const int n_ch = prm.dual ? 2 : 4;          // 32-column chunks in the share
-        if (prm.kth_out && unsorted) {
+        if (prm.c_full) {
+            // ---- dense mode: the whole tile of distances goes to global memory (row-major C[nq, ndb]); a thread
+            // owns one row and writes 32 consecutive columns (128 B) per chunk
+            const bool vec_ok = (prm.ndb & 3) == 0;
+            const int64_t grow = prm.q_row0 + gq;  // global id of the query row (diagonal rule)
+            for (int64_t t = 0; t < n_sweep; ++t) {
+                const int as = (int)(t & 1);
+                const uint32_t aph = (uint32_t)((t >> 1) & 1);
+                mbar_wait(BAR(T_FULL + as), aph);
+                tc_fence_after();
+                const int col0 = (int)(tile_of(t) * BN) + c_beg;
+                const uint32_t tb = tmem_base + lane_addr + (uint32_t)(as * 256 + c_beg);
+#pragma unroll 1
+                for (int c = 0; c < n_ch; ++c) {
+                    uint32_t big[32], small[32];
+                    tc_ld32(tb + 32 * c, big);
+                    tc_ld32(tb + 128 + 32 * c, small);
+                    tc_ld_wait(big, small);
+                    const int col_base = col0 + 32 * c;
+                    float dv[32];
+#pragma unroll
+                    for (int j4 = 0; j4 < 32; j4 += 4) {
+                        const float4 nb = __ldg(reinterpret_cast<const float4*>(prm.dbn + col_base + j4));
+                        const float nbv[4] = {nb.x, nb.y, nb.z, nb.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = j4 + u;
+                            // torch.py:89-91: (|x|^2 + |y|^2) - 2 x.y
+                            float dd = fmaf(__fadd_rn(__uint_as_float(big[j]), __uint_as_float(small[j])), neg2s,
+                                            __fadd_rn(qn, nbv[u]));
+                            if (prm.metric == TDR_METRIC_EUCLIDEAN) dd = sqrtf(fmaxf(dd, 0.0f));  // torch.py:92-95
+                            if (prm.full_exclude_diag && (int64_t)(col_base + j) == grow) dd = __fadd_rn(dd, 1e12f);  // :111-116
+                            dv[j] = dd;
+                        }
+                    }
+                    if (gq < prm.nq) {
+                        float* out = prm.c_full + gq * prm.ndb + col_base;
+                        if (vec_ok && (int64_t)col_base + 32 <= prm.ndb) {
+#pragma unroll
+                            for (int j4 = 0; j4 < 32; j4 += 4)
+                                *reinterpret_cast<float4*>(out + j4) = make_float4(dv[j4], dv[j4 + 1], dv[j4 + 2], dv[j4 + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if ((int64_t)col_base + j < prm.ndb) out[j] = dv[j];
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(BAR(T_EMPTY + as));
+            }
+        } else if (prm.kth_out && unsorted) {
             // ---- phase A of the pruned sweep, k <= 32: no lists.  gm[j] = smallest distance among the columns this
             // thread sees at chunk position j; the row's 32 (x 2 warpgroups) minima belong to disjoint column sets,
             // so their k-th smallest bounds the k-th neighbour distance (k columns at most that far) — and it is
@@ -562,7 +628,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
 
     // ---- write back; fused: rho/sigma search on the finished rows (one warp per row) ----
     const int n_warps = (int)blockDim.x >> 5;
-    for (int row = warp; row < BM; row += n_warps) {
+    for (int row = warp; row < (prm.c_full ? 0 : BM); row += n_warps) {
         const int64_t gr = q0 + row;
         if (gr >= prm.nq) continue;
         float* ldr = ld_s + row * kpad;
@@ -717,22 +783,22 @@ __global__ void __launch_bounds__(128) tile_box_kernel(const float* __restrict__
                                                        int d, float* __restrict__ lo, float* __restrict__ hi,
                                                        int64_t ld_t) {
     const int64_t b = blockIdx.x;
-    const int j = threadIdx.x;
-    if (j >= d) return;
     const int64_t r_beg = row0 + b * BM;
     const int64_t r_end = min(r_beg + BM, row_limit);
-    float mn = INFINITY, mx = -INFINITY;
-    for (int64_t r = r_beg; r < r_end; ++r) {
-        const float v = __ldg(X + r * d + j);
-        mn = fminf(mn, v);
-        mx = fmaxf(mx, v);
-    }
-    if (ld_t) {
-        lo[(int64_t)j * ld_t + b] = mn;
-        hi[(int64_t)j * ld_t + b] = mx;
-    } else {
-        lo[b * d + j] = mn;
-        hi[b * d + j] = mx;
+    for (int j = threadIdx.x; j < d; j += (int)blockDim.x) {
+        float mn = INFINITY, mx = -INFINITY;
+        for (int64_t r = r_beg; r < r_end; ++r) {
+            const float v = __ldg(X + r * d + j);
+            mn = fminf(mn, v);
+            mx = fmaxf(mx, v);
+        }
+        if (ld_t) {
+            lo[(int64_t)j * ld_t + b] = mn;
+            hi[(int64_t)j * ld_t + b] = mx;
+        } else {
+            lo[b * d + j] = mn;
+            hi[b * d + j] = mx;
+        }
     }
 }
 
@@ -951,12 +1017,26 @@ static int make_map(CUtensorMap* m, const __half* base, int64_t rows, int dp) {
 
 }  // namespace tc
 
-bool knn_tc_supported(int d, int k) {
-    if (d > tc::MAX_ATOMS * tc::KATOM || k > tc::MAX_K) return false;
-    // shared memory: resident query tile + at least two TMA stages + one set of lists + barriers/alignment
-    const size_t stage = (size_t)((d + tc::KATOM - 1) / tc::KATOM) * 2 * tc::TILE_BYTES;
-    return 3 * stage + (size_t)tc::BM * k * 8 + 512 + 1024 <= (size_t)227 * 1024;
+// Shared-memory plan: resident query tile (atoms x 32 KB) + ring of >= 2 atom stages (32 KB each) + list sets + misc.
+static bool tc_smem_plan(int d, int k, bool dense, int* dual_out, int* stages_out, size_t* smem_out) {
+    using namespace tc;
+    if (d > MAX_ATOMS * KATOM || (!dense && k > MAX_K)) return false;
+    const size_t q_bytes = (size_t)((d + KATOM - 1) / KATOM) * STAGE_BYTES;
+    const size_t one_list = dense ? 0 : (size_t)BM * k * 8;
+    auto fits = [&](int nl, int st) { return q_bytes + (size_t)st * STAGE_BYTES + nl * one_list + SMEM_MISC <= SMEM_LIMIT; };
+    if (!fits(1, 2)) return false;
+    // two epilogue warpgroups (each with its own list set) when that still leaves a ring of >= 3 stages
+    const int dual = (dense || fits(2, 3)) ? 1 : 0;
+    int stages = (int)((SMEM_LIMIT - q_bytes - (1 + dual) * one_list - SMEM_MISC) / STAGE_BYTES);
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (dual_out) *dual_out = dual;
+    if (stages_out) *stages_out = stages;
+    if (smem_out) *smem_out = q_bytes + (size_t)stages * STAGE_BYTES + (1 + dual) * one_list + SMEM_MISC;
+    return true;
 }
+
+bool knn_tc_supported(int d, int k) { return tc_smem_plan(d, k, false, nullptr, nullptr, nullptr); }
+bool knn_tc_full_supported(int d) { return tc_smem_plan(d, 1, true, nullptr, nullptr, nullptr); }
 
 namespace tc {
 struct PruneLayout {
@@ -1081,23 +1161,21 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
     prm.P = P;
     prm.rho = rho;
     prm.sigma = sigma;
-    const size_t stage_bytes = (size_t)atoms * 2 * TILE_BYTES;
-    // two epilogue warpgroups when a second set of lists still leaves room for two TMA stages
     {
         const char* us = getenv("TDR_TC_UNSORTED");
         prm.unsorted = (k <= 32 && !(us && atoi(us) == 0)) ? 1 : 0;
     }
-    prm.dual = ((size_t)3 * stage_bytes + (size_t)2 * BM * k * 8 + 512 + 1024 <= (size_t)227 * 1024) ? 1 : 0;
-    if (prm.debug & 32) prm.dual = 0;
-    const size_t fixed = stage_bytes + (size_t)(1 + prm.dual) * BM * k * 8 + 512 + 1024;
-    int stages = (int)((227 * 1024 - fixed) / stage_bytes);
-    if (stages > 6) stages = 6;
-    if (stages < 2) {
-        set_error("knn (tensor-core path): shared memory budget exceeded");
+    int stages = 0;
+    size_t smem = 0;
+    if (!tc_smem_plan(d, k, false, &prm.dual, &stages, &smem)) {
+        set_error("knn (tensor-core path): shared memory budget exceeded for d=%d k=%d", d, k);
         return TDR_E_UNSUPPORTED;
     }
+    if ((prm.debug & 32) && prm.dual) {  // ablation: one epilogue warpgroup
+        prm.dual = 0;
+        smem -= (size_t)BM * k * 8;
+    }
     prm.stages = stages;
-    const size_t smem = fixed + (size_t)stages * stage_bytes;
     // per call: the attribute belongs to the current device's context (a process may drive several GPUs)
     TDR_CUDA(cudaFuncSetAttribute(knn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     TDR_CUDA(cudaFuncSetAttribute(knn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1204,6 +1282,76 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
         }
     }
     knn_tc_kernel<false><<<grid, threads, smem, st>>>(mq_hi, mq_lo, mdb_hi, mdb_lo, prm);
+    TDR_LAUNCH_CHECK();
+    return TDR_OK;
+}
+
+// Dense distance matrix C[n, m] on the tensor cores (tdr_pairwise_full_f32 for d <= 256): same mainloop, the epilogue
+// writes every distance instead of filtering.  Workspace = knn_tc_workspace_bytes(n, m, d, 1, same).
+int knn_tc_full_launch(const float* X, int64_t n, const float* Y, int64_t m, int d, bool same, int metric,
+                       int exclude_diag, float* C, void* ws, size_t ws_bytes, cudaStream_t st) {
+    using namespace tc;
+    const size_t need = knn_tc_workspace_bytes(n, m, d, 1, same);
+    if (!ws || ws_bytes < need || (uintptr_t)ws % 256) {
+        set_error("pairwise (tensor-core path) workspace: need %zu bytes (256-aligned), got %zu", need, ws_bytes);
+        return TDR_E_WORKSPACE;
+    }
+    const int dp = (int)align_up((size_t)d, KATOM);
+    const int64_t m_pad = (int64_t)align_up((size_t)m, 128);
+    const int64_t n_pad = (int64_t)align_up((size_t)n, 128);
+    char* p = (char*)ws;
+    int* absmax = (int*)p;
+    p += 256;
+    float* dbn = (float*)p;
+    p += align_up((size_t)m_pad * 4, 256);
+    __half* db_hi = (__half*)p;
+    p += align_up((size_t)m * dp * 2, 256);
+    __half* db_lo = (__half*)p;
+    p += align_up((size_t)m * dp * 2, 256);
+    float* qn = dbn;
+    __half *q_hi = db_hi, *q_lo = db_lo;
+    if (!same) {
+        qn = (float*)p;
+        p += align_up((size_t)n_pad * 4, 256);
+        q_hi = (__half*)p;
+        p += align_up((size_t)n * dp * 2, 256);
+        q_lo = (__half*)p;
+    }
+    TDR_CUDA(cudaMemsetAsync(absmax, 0, 4, st));
+    absmax_kernel<<<(unsigned)std::min<int64_t>((int64_t)kNumSMs * 16, (m * d + 255) / 256), 256, 0, st>>>(Y, m * d, absmax);
+    if (!same)
+        absmax_kernel<<<(unsigned)std::min<int64_t>((int64_t)kNumSMs * 16, (n * d + 255) / 256), 256, 0, st>>>(X, n * d, absmax);
+    split_kernel<<<(unsigned)((m * dp + 255) / 256), 256, 0, st>>>(Y, m, d, dp, absmax, db_hi, db_lo);
+    sqnorm_pad_kernel<<<(unsigned)((m_pad + 7) / 8), 256, 0, st>>>(Y, m, m_pad, d, dbn);
+    if (!same) {
+        split_kernel<<<(unsigned)((n * dp + 255) / 256), 256, 0, st>>>(X, n, d, dp, absmax, q_hi, q_lo);
+        sqnorm_pad_kernel<<<(unsigned)((n_pad + 7) / 8), 256, 0, st>>>(X, n, n_pad, d, qn);
+    }
+    TDR_LAUNCH_CHECK();
+    CUtensorMap mq_hi, mq_lo, mdb_hi, mdb_lo;
+    int rc;
+    if ((rc = make_map(&mq_hi, q_hi, same ? m : n, dp)) || (rc = make_map(&mq_lo, q_lo, same ? m : n, dp)) ||
+        (rc = make_map(&mdb_hi, db_hi, m, dp)) || (rc = make_map(&mdb_lo, db_lo, m, dp)))
+        return rc;
+    Params prm{};
+    prm.nq = n;
+    prm.ndb = m;
+    prm.qn = qn;
+    prm.dbn = dbn;
+    prm.absmax_bits = absmax;
+    prm.k = 1;
+    prm.kpad = 1;
+    prm.atoms = dp / KATOM;
+    prm.metric = metric;
+    prm.c_full = C;
+    prm.full_exclude_diag = (exclude_diag && same) ? 1 : 0;
+    size_t smem = 0;
+    if (!tc_smem_plan(d, 1, true, &prm.dual, &prm.stages, &smem)) {
+        set_error("pairwise (tensor-core path): d=%d exceeds %d", d, MAX_ATOMS * KATOM);
+        return TDR_E_UNSUPPORTED;
+    }
+    TDR_CUDA(cudaFuncSetAttribute(knn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    knn_tc_kernel<false><<<(unsigned)((n + BM - 1) / BM), prm.dual ? 384 : 256, smem, st>>>(mq_hi, mq_lo, mdb_hi, mdb_lo, prm);
     TDR_LAUNCH_CHECK();
     return TDR_OK;
 }

@@ -629,7 +629,9 @@ class UMAP(_NeighborEmbeddingB200):
                 self.logger.warning(f"symmetric memory unavailable ({exc}); falling back to NCCL all-gather")
                 peer = None
         if peer is None:
-            Zb = Za.clone()
+            pair = torch.empty((2,) + tuple(Za.shape), dtype=Za.dtype, device=Za.device)  # the two buffers side by side
+            pair[0], pair[1] = Za, Za
+            Za, Zb = pair[0], pair[1]
         sync = peer.sync if peer is not None else ops.RunSync(Za.device)
         # Learning rates come from the reference's own optimizer / scheduler objects (~25 us of host time per step).
         # In the batched branches they are produced one batch AHEAD, after the current batch has been launched and

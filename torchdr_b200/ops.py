@@ -75,7 +75,7 @@ def knn_umap_fused(Xq, Xdb, k, q_row0=0, exclude_self=True, max_iter=100, want_d
     return dist, idx, Pm, rho, sigma
 
 
-def pairwise_full(X, Y=None, metric="sqeuclidean", exclude_diag=False):
+def pairwise_full(X, Y=None, metric="sqeuclidean", exclude_diag=False, path="auto"):
     X = _dev_f32(X, "X")
     Y = X if Y is None or Y is X else _dev_f32(Y, "Y")
     lib = _lib.load()
@@ -85,8 +85,22 @@ def pairwise_full(X, Y=None, metric="sqeuclidean", exclude_diag=False):
     C = torch.empty((n, m), dtype=torch.float32, device=X.device)
     with torch.cuda.device(X.device):
         check(lib.tdr_pairwise_full_f32(ptr(X), n, ptr(Y), m, d, _lib.METRIC_IDS[metric], int(exclude_diag), ptr(C),
-                                        ptr(ws), ws.numel(), stream()), "tdr_pairwise_full_f32")
+                                        _lib.KNN_PATHS[path], ptr(ws), ws.numel(), stream()), "tdr_pairwise_full_f32")
     return C
+
+
+def tree_assign(X, rows, node_of_row, centres, cnorm):
+    """Nearest centre of every listed row within its own tree node (reorder.py) -> int64 [m]."""
+    X = _dev_f32(X, "X")
+    rows, node_of_row = rows.contiguous(), node_of_row.contiguous()
+    centres, cnorm = centres.contiguous(), cnorm.contiguous()
+    assert rows.dtype == torch.int64 and node_of_row.dtype == torch.int64 and centres.dtype == torch.float32
+    m = rows.numel()
+    out = torch.empty(m, dtype=torch.int64, device=X.device)
+    with torch.cuda.device(X.device):
+        check(_lib.load().tdr_tree_assign_f32(ptr(X), X.shape[1], ptr(rows), ptr(node_of_row), m, ptr(centres), ptr(cnorm),
+                                              centres.shape[1], ptr(out), stream()), "tdr_tree_assign_f32")
+    return out
 
 
 def umap_affinity_rows(C, max_iter=100):

@@ -14,8 +14,9 @@ sweep runs in its certified mode (TDR_KNN_PRUNE_CERTIFIED).  There is no counter
 (``torchdr/distance/base.py`` hands unordered data to FAISS).  Design study: ``scripts/reorder_sim.py``; measured:
 shuffled 1 M x 128 fit 1.33 s -> 0.26 s (``profiles/r2_first.log``).
 
-Level-synchronous and device-agnostic (plain tensor ops: sort, gather, index_add, batched dot products),
-so the host logic is unit-tested on the CPU (``tests/test_host_logic.py``: same graph as the plain path, bit for bit).
+Level-synchronous; the per-level nearest-of-16 search is a CUDA kernel (``csrc/reorder.cu``) on the device and plain
+tensor ops on the CPU, where the host logic is unit-tested (``tests/test_host_logic.py``: same graph as the plain path,
+bit for bit); sorts / segment bookkeeping are torch library calls (one-off plumbing around the fit).
 """
 
 import torch
@@ -26,9 +27,13 @@ _MAX_DEPTH = 15
 
 def _assign(X, rows, node_of_row, centres, valid, chunk=16384):
     """Nearest valid centre of every row's own node.  centres: [n_nodes, B, d], valid: [n_nodes, B]."""
-    out = torch.empty(rows.numel(), dtype=torch.long, device=X.device)
     cn = (centres * centres).sum(-1)  # [n_nodes, B]
     cn = torch.where(valid, cn, torch.full_like(cn, float("inf")))
+    if X.is_cuda and X.shape[1] <= 512:
+        from . import ops
+
+        return ops.tree_assign(X, rows, node_of_row, centres, cn)  # csrc/reorder.cu: one warp per row
+    out = torch.empty(rows.numel(), dtype=torch.long, device=X.device)
     for a in range(0, rows.numel(), chunk):
         r = rows[a:a + chunk]
         nd = node_of_row[a:a + chunk]
@@ -102,13 +107,15 @@ def voronoi_tree_order(X, branch=16, leaf=128, lloyd=1, generator=None):
         node_of_row = remap[node_of_row]
         sizes = sizes[big]
         n_nodes = sizes.numel()
-        # rows grouped by node (stable), to sample member rows as centres
+        # rows grouped by node (stable): member rows are sampled as centres, and the assignment kernel finds a node's
+        # centres in cache while it walks the node's rows
         order = torch.argsort(node_of_row, stable=True)
+        open_rows, node_of_row = open_rows[order], node_of_row[order]
         starts = torch.cumsum(sizes, 0) - sizes
         n_centres = torch.clamp(sizes // leaf, min=2, max=branch)  # [n_nodes]
         u = torch.rand((n_nodes, branch), generator=generator, device=dev)
         pick = starts.unsqueeze(1) + torch.clamp((u * sizes.unsqueeze(1)).long(), max=(sizes - 1).unsqueeze(1))
-        centres = X[open_rows[order[pick]]]  # [n_nodes, branch, d]
+        centres = X[open_rows[pick]]  # [n_nodes, branch, d]
         valid = torch.arange(branch, device=dev).unsqueeze(0) < n_centres.unsqueeze(1)
         child = _assign(X, open_rows, node_of_row, centres, valid)
         for _ in range(lloyd):
