@@ -756,13 +756,19 @@ def dense_entropic_arm(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"EntropicAffinity(perplexity=30, sparsity=False) on {n}x{d} clustered synthetic (BASELINE configs[2])",
                    "points": n, "dim": d},
-        "stage_ms": {"pairwise_full (fp32 SIMT tile kernel, writes 4 N^2 bytes)": t_dist,
-                     "entropic_dense_rows (one CTA per row, row re-read from L2 per bisection step, log_P in place)": t_rows},
+        "stage_ms": {"pairwise_full (tcgen05 kNN mainloop with the dense epilogue: -2XY^T on the tensor cores, writes 4 N^2 bytes)": t_dist,
+                     "entropic_dense_rows (one CTA per row: half the row parked in shared memory, the rest re-read from L2 "
+                     "per bisection step, log_P in place)": t_rows},
         "distance_tflops_2nnd": 2.0 * n * n * d / (t_dist * 1e-3) / 1e12,
+        "distance_tensor_tflops_3pass": 6.0 * n * n * d / (t_dist * 1e-3) / 1e12,
+        "distance_tensor_frac_of_measured_bf16_peak": (6.0 * n * n * d / (t_dist * 1e-3) / 1e12 / float(peaks["bf16_tflops"]))
+        if "bf16_tflops" in peaks else None,
+        "distance_write_gbs": 4.0 * n * n / (t_dist * 1e-3) / 1e9,
         "roofline": {"bound": "hbm", "kernel": "tdr::entropic_dense_kernel", "achieved": 8.0 * n * n / (t_rows * 1e-3) / 1e9,
                      "peak": peak, "unit": "GB/s", "frac": 8.0 * n * n / (t_rows * 1e-3) / 1e9 / peak, "traffic": None,
-                     "note": "algorithmic bytes = one read of C + one write of log_P (8 N^2); the bisection passes re-read the "
-                             "row from L2 (400 KB per row), so the kernel is bound by exp / div issue, not by HBM"},
+                     "note": "algorithmic bytes = one read of C + one write of log_P (8 N^2); the ~35 bisection passes per row run "
+                             "from shared memory (first 200 KB of the row) and L2 (the rest), one MUFU.EX2 per element and pass: "
+                             "bound by the SFU / L2 rate, not by HBM"},
         "parity": parity, "gpu_launches": 2 * len(times), "clocks": clk.summary(),
     }, 1
 

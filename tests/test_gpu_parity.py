@@ -46,7 +46,7 @@ def test_knn_matches_reference_golden(ops, name):
     assert bool((C[:, 1:] >= C[:, :-1]).all())
 
 
-@pytest.mark.parametrize("n,d,k", [(3000, 128, 90), (2500, 256, 15), (2500, 256, 33), (2000, 200, 20), (1500, 192, 96),
+@pytest.mark.parametrize("n,d,k", [(3000, 128, 90), (2500, 256, 15), (2500, 256, 33), (2000, 200, 20), (1500, 128, 96), (1200, 192, 60),
                                    (700, 65, 96)])
 def test_knn_tensor_core_wide_shapes(ops, n, d, k):
     """The tcgen05 kernel beyond round 1's tile shapes — the entropic k = 3 * perplexity = 90 on 128-dimensional input

@@ -82,12 +82,18 @@ static int launch_entropic(const float* C, int64_t n, int k, int max_iter, const
 }
 
 // ---- dense rows (EntropicAffinity(sparsity=False), BASELINE config 3) -----------------------------
-// One CTA per row of the dense N x M distance matrix; the row (400 KB at M = 100 k) does not fit on
-// chip, so every bisection step is one streaming pass over it (HBM-bound: 4 M bytes per step per
-// row).  Entropy in one pass:  with  m = max_j l_j = -C_min/eps,  S = sum e^{l_j - m},
+// One CTA (1024 threads, 1 per SM) per row of the dense N x M distance matrix.  Every bisection step is one pass
+// over the row; the row (400 KB at M = 100 k) does not fit on chip, so its first m_smem entries (up to 200 KB) are
+// parked in shared memory during the first pass and only the rest is re-read from L2 in the later ones — HBM sees
+// the row once.  Entropy in one pass:  with  m = max_j l_j = -C_min/eps,  S = sum e^{l_j - m},
 // T = sum e^{l_j - m}(l_j - m):  H = log S - T/S + 1  (same quantity as entropic.py:274-277 /
 // utils/utils.py:167-168, reassociated so that logsumexp and entropy share a pass).
-constexpr int kDenseThreads = 512;
+// Per element the pass is FFMA + MUFU.EX2 + FADD + FFMA in the log2 domain (l_j - m = (c_j - c_min)(-1/eps)); the
+// reference's elementwise division and libm exp are NOT mirrored op by op here: with 1e10 elements x ~35 passes the
+// kernel is bound by the SFU / L2 rate, and the root it converges to is the same within the tolerance the tests state
+// (eps rtol 2e-5 against the reference's own output).
+constexpr int kDenseThreads = 1024;
+constexpr int kDenseSmemFloats = 50 * 1024;  // 200 KB
 
 __device__ __forceinline__ float block_sum(float v, float* red) {
     v = warp_sum(v);
@@ -107,71 +113,106 @@ __device__ __forceinline__ float block_min(float v, float* red) {
     for (int w = 0; w < kDenseThreads / 32; ++w) t = fminf(t, red[w]);
     return t;
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
-__global__ void __launch_bounds__(kDenseThreads)
-entropic_dense_kernel(const float* C, int64_t n_rows, int64_t m, int max_iter, EntropicConsts K,
-                      float* logP /* may alias C */, float* __restrict__ eps_out, float* __restrict__ log_norm) {
+__global__ void __launch_bounds__(kDenseThreads, 1)
+entropic_dense_kernel(const float* C, int64_t n_rows, int64_t m, int64_t m_smem /* multiple of 4, <= m */, int max_iter,
+                      EntropicConsts K, float* logP /* may alias C */, float* __restrict__ eps_out,
+                      float* __restrict__ log_norm) {
+    extern __shared__ __align__(16) float row_s[];
     __shared__ float red[kDenseThreads / 32];
-    const int64_t row = blockIdx.x;
-    const float* c = C + row * m;
-    // pass 0: smallest, second smallest (with multiplicity) and largest entry (entropic.py:93-98)
-    float mn = INFINITY, mn2 = INFINITY, mx = -INFINITY;
-    for (int64_t j = threadIdx.x; j < m; j += kDenseThreads) {
-        const float v = c[j];
-        if (v < mn) {
-            mn2 = mn;
-            mn = v;
-        } else if (v < mn2) {
-            mn2 = v;
-        }
-        mx = fmaxf(mx, v);
-    }
-    const float d1 = block_min(mn, red);
-    // second smallest overall: every thread contributes its own second smallest, or its smallest if that
-    // is not the (unique) holder of d1; count holders of d1 to honour multiplicity
-    const float cnt = block_sum(mn == d1 ? 1.0f : 0.0f, red);
-    const float cand = (mn == d1 && cnt < 1.5f) ? mn2 : (mn == d1 ? fminf(mn2, d1) : mn);
-    const float d2 = block_min(cnt > 1.5f ? d1 : cand, red);
-    const float dN = -block_min(-mx, red);
-
-    auto gap = [&](float eps) {
-        const float mm = __fdiv_rn(-d1, eps);
-        float s = 0.0f, t = 0.0f;
+    constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+    const bool vec = (m & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
+    for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        const float* c = C + row * m;
+        __syncthreads();  // the previous row's readers of row_s are done
+        // pass 0: smallest, second smallest (with multiplicity) and largest entry (entropic.py:93-98); park the prefix
+        float mn = INFINITY, mn2 = INFINITY, mx = -INFINITY;
         for (int64_t j = threadIdx.x; j < m; j += kDenseThreads) {
-            const float x = __fsub_rn(__fdiv_rn(-c[j], eps), mm);
-            const float e = expf(x);
-            s += e;
-            t = fmaf(e, x, t);
+            const float v = c[j];
+            if (j < m_smem) row_s[j] = v;
+            if (v < mn) {
+                mn2 = mn;
+                mn = v;
+            } else if (v < mn2) {
+                mn2 = v;
+            }
+            mx = fmaxf(mx, v);
         }
-        s = block_sum(s, red);
-        t = block_sum(t, red);
-        return __fsub_rn(__fadd_rn(__fsub_rn(logf(s), __fdiv_rn(t, s)), 1.0f), K.target);
-    };
-    float b = 1.0f, e = 1.0f;
-    if (K.use_bounds) {  // entropic.py:99-115
-        const float span = __fsub_rn(dN, d1), step = __fsub_rn(d2, d1);
-        const float t1 = __fdiv_rn(K.b_num, __fmul_rn(K.b_den, span));
-        const float t2 = sqrtf(__fdiv_rn(K.b_lr, __fsub_rn(__fmul_rn(dN, dN), __fmul_rn(d1, d1))));
-        float beta_lo = fmaxf(t1, t2);
-        if (t1 != t1 || t2 != t2) beta_lo = NAN;
-        b = __fadd_rn(__fdiv_rn(1.0f, __fdiv_rn(K.b_logp1, step)), 1e-6f);
-        e = __fdiv_rn(1.0f, beta_lo);
-    }
-    const float eps = bracket_bisect(gap, b, e, max_iter);
-    // final normalisation (entropic.py:299-310)
-    const float mm = __fdiv_rn(-d1, eps);
-    float s = 0.0f;
-    for (int64_t j = threadIdx.x; j < m; j += kDenseThreads) s += expf(__fsub_rn(__fdiv_rn(-c[j], eps), mm));
-    s = block_sum(s, red);
-    const float z = __fadd_rn(logf(s), mm);
-    if (logP) {
-        float* out = logP + row * m;
-        for (int64_t j = threadIdx.x; j < m; j += kDenseThreads)
-            out[j] = __fsub_rn(__fsub_rn(__fdiv_rn(-c[j], eps), z), K.log_n_total);
-    }
-    if (threadIdx.x == 0) {
-        eps_out[row] = eps;
-        log_norm[row] = z;
+        const float d1 = block_min(mn, red);
+        // second smallest overall: every thread contributes its own second smallest, or its smallest if that
+        // is not the (unique) holder of d1; count holders of d1 to honour multiplicity
+        const float cnt = block_sum(mn == d1 ? 1.0f : 0.0f, red);
+        const float cand = (mn == d1 && cnt < 1.5f) ? mn2 : (mn == d1 ? fminf(mn2, d1) : mn);
+        const float d2 = block_min(cnt > 1.5f ? d1 : cand, red);
+        const float dN = -block_min(-mx, red);
+
+        // one pass: S = sum 2^x, T2 = sum 2^x x with x = (c - d1) * a, a = -log2(e)/eps  (x <= 0, log2 domain)
+        auto sums = [&](float a, float& S, float& T2) {
+            const float off = -d1 * a;
+            float s0 = 0.0f, s1 = 0.0f, t0 = 0.0f, t1 = 0.0f;
+            auto acc4 = [&](const float4 v) {
+                const float x0 = fmaf(v.x, a, off), x1 = fmaf(v.y, a, off), x2 = fmaf(v.z, a, off), x3 = fmaf(v.w, a, off);
+                const float e0 = ex2_approx(x0), e1 = ex2_approx(x1), e2 = ex2_approx(x2), e3 = ex2_approx(x3);
+                s0 += e0;
+                s1 += e1;
+                s0 += e2;
+                s1 += e3;
+                t0 = fmaf(e0, x0, t0);
+                t1 = fmaf(e1, x1, t1);
+                t0 = fmaf(e2, x2, t0);
+                t1 = fmaf(e3, x3, t1);
+            };
+            for (int64_t j = (int64_t)threadIdx.x * 4; j < m_smem; j += kDenseThreads * 4)
+                acc4(*reinterpret_cast<const float4*>(row_s + j));
+            if (vec) {
+                for (int64_t j = m_smem + (int64_t)threadIdx.x * 4; j < m; j += kDenseThreads * 4)
+                    acc4(__ldcg(reinterpret_cast<const float4*>(c + j)));
+            } else {
+                for (int64_t j = m_smem + threadIdx.x; j < m; j += kDenseThreads) {
+                    const float x = fmaf(c[j], a, off), e = ex2_approx(x);
+                    s0 += e;
+                    t0 = fmaf(e, x, t0);
+                }
+            }
+            S = block_sum(s0 + s1, red);
+            T2 = block_sum(t0 + t1, red);
+        };
+        auto gap = [&](float eps) {
+            float S, T2;
+            sums(-kLog2e / eps, S, T2);
+            return __fsub_rn(__fadd_rn(__fsub_rn(logf(S), kLn2 * T2 / S), 1.0f), K.target);
+        };
+        float b = 1.0f, e = 1.0f;
+        if (K.use_bounds) {  // entropic.py:99-115
+            const float span = __fsub_rn(dN, d1), step = __fsub_rn(d2, d1);
+            const float t1 = __fdiv_rn(K.b_num, __fmul_rn(K.b_den, span));
+            const float t2 = sqrtf(__fdiv_rn(K.b_lr, __fsub_rn(__fmul_rn(dN, dN), __fmul_rn(d1, d1))));
+            float beta_lo = fmaxf(t1, t2);
+            if (t1 != t1 || t2 != t2) beta_lo = NAN;
+            b = __fadd_rn(__fdiv_rn(1.0f, __fdiv_rn(K.b_logp1, step)), 1e-6f);
+            e = __fdiv_rn(1.0f, beta_lo);
+        }
+        const float eps = bracket_bisect(gap, b, e, max_iter);
+        // final normalisation (entropic.py:299-310): z = logsumexp(-c/eps) = log S + (-d1/eps)
+        float S, T2;
+        sums(-kLog2e / eps, S, T2);
+        const float inv = -1.0f / eps;
+        const float z = __fadd_rn(logf(S), d1 * inv);
+        if (logP) {
+            float* out = logP + row * m;
+            const float sub = z + K.log_n_total;
+            for (int64_t j = threadIdx.x; j < m_smem; j += kDenseThreads) out[j] = fmaf(row_s[j], inv, -sub);
+            for (int64_t j = m_smem + threadIdx.x; j < m; j += kDenseThreads) out[j] = fmaf(c[j], inv, -sub);
+        }
+        if (threadIdx.x == 0) {
+            eps_out[row] = eps;
+            log_norm[row] = z;
+        }
     }
 }
 
@@ -187,8 +228,13 @@ extern "C" TDR_API int tdr_entropic_dense_f32(const float* C, int64_t n_rows, in
     TDR_CHECK_ARG(n_rows >= 0 && m >= 2 && n_rows < 0x7fffffffLL, "tdr_entropic_dense_f32: bad shape");
     if (n_rows == 0) return TDR_OK;
     EntropicConsts K{target_entropy, log_n_total, use_bounds, b_num, b_den, b_lr, b_logp1};
-    entropic_dense_kernel<<<(unsigned)n_rows, kDenseThreads, 0, (cudaStream_t)stream>>>(C, n_rows, m, max_iter, K, logP,
-                                                                                      eps, log_norm);
+    int64_t m_smem = m < kDenseSmemFloats ? m : kDenseSmemFloats;
+    m_smem &= ~(int64_t)3;
+    const size_t smem = (size_t)m_smem * 4;
+    TDR_CUDA(cudaFuncSetAttribute(entropic_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmemFloats * 4));
+    const int64_t grid = n_rows < (int64_t)kNumSMs * 64 ? n_rows : (int64_t)kNumSMs * 64;  // row-strided beyond that
+    entropic_dense_kernel<<<(unsigned)grid, kDenseThreads, smem, (cudaStream_t)stream>>>(C, n_rows, m, m_smem, max_iter, K,
+                                                                                       logP, eps, log_norm);
     TDR_LAUNCH_CHECK();
     return TDR_OK;
 }

@@ -240,43 +240,12 @@ static int launch_persistent(UmapStepParams& p, RunParams& rp, int n_steps, cons
     int64_t grid = (int64_t)sms * occ;
     const int64_t ctas_needed = (p.n_local + kWarps4 * 32 - 1) / (kWarps4 * 32);
     if (grid > ctas_needed) grid = ctas_needed < 1 ? 1 : ctas_needed;
-    // L2 residency of the embedding (experiment, TDR_L2_PERSIST_MB): at 10 M points the two 80 MB buffers compete with
-    // ~3 GB of edge streams per iteration for the 126 MB L2; an access-policy window marks the buffers persisting
-    // (hit ratio = set-aside / window) and everything else streaming
-    cudaLaunchAttribute attrs[2];
-    unsigned n_attrs = 0;
-    attrs[n_attrs].id = cudaLaunchAttributeCooperative;
-    attrs[n_attrs].val.cooperative = 1;
-    ++n_attrs;
-    static const int persist_mb = [] {
-        const char* e = getenv("TDR_L2_PERSIST_MB");
-        return e ? atoi(e) : 0;
-    }();
-    if (persist_mb > 0) {
-        int max_persist = 0, max_window = 0;
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
-        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-        size_t want = (size_t)persist_mb << 20;
-        if (want > (size_t)max_persist) want = (size_t)max_persist;
-        const char* lo = (const char*)(rp.Z[0] < rp.Z[1] ? rp.Z[0] : rp.Z[1]);
-        const char* hi = (const char*)(rp.Z[0] < rp.Z[1] ? rp.Z[1] : rp.Z[0]) + (size_t)p.n_total * 8;
-        size_t span = (size_t)(hi - lo);
-        if (span > (size_t)max_window) span = (size_t)max_window;
-        static bool once = false;
-        if (!once) {
-            once = true;
-            fprintf(stderr, "[tdr] L2 persist: max set-aside %d MB, max window %d MB, using %zu MB over a %zu MB window\n",
-                    max_persist >> 20, max_window >> 20, want >> 20, span >> 20);
-        }
-        TDR_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
-        attrs[n_attrs].id = cudaLaunchAttributeAccessPolicyWindow;
-        attrs[n_attrs].val.accessPolicyWindow.base_ptr = (void*)lo;
-        attrs[n_attrs].val.accessPolicyWindow.num_bytes = span;
-        attrs[n_attrs].val.accessPolicyWindow.hitRatio = span ? (float)((double)want / (double)span > 1.0 ? 1.0 : (double)want / (double)span) : 0.0f;
-        attrs[n_attrs].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attrs[n_attrs].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        ++n_attrs;
-    }
+    // (An L2 access-policy window marking the two embedding buffers persisting and the edge streams streaming was
+    // measured at 10 M points: 48 MB set-aside +0.3 %, 79 MB -7 % — profiles/r2_step_variants.md; not used.)
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeCooperative;
+    attrs[0].val.cooperative = 1;
+    const unsigned n_attrs = 1;
     const int64_t n_iter0 = p.n_iter;
     for (int done = 0; done < n_steps; done += kMaxRunSteps) {
         const int chunk = n_steps - done < kMaxRunSteps ? n_steps - done : kMaxRunSteps;
