@@ -592,33 +592,80 @@ def largevis_arm(args):
     torch.cuda.synchronize()
     t_aff = time.perf_counter() - t0
     k = P.shape[1]
+    # union graph S = P + P^T of the local rows (one edge exchange when sharded), as LargeVis._compute_affinity builds it
+    t0 = time.perf_counter()
+    ext = None
+    if world > 1:
+        from torchdr_b200.distributed import exchange_edges
+
+        counts, er, ec, ev_ = ops.symmetrize_export(P, idx, s, n, world, rank)
+        ext = exchange_edges(counts, er, ec, ev_)
+    rowptr, col, val = ops.symmetrize_csr(P, idx, s, n, ext=ext, mode="sum")
+    torch.cuda.synchronize()
+    t_graph = time.perf_counter() - t0
+    nnz_union = int(col.numel())
     g = torch.Generator(device=dev).manual_seed(0)
     Z = torch.randn(n, 2, generator=g, device=dev)
     Z = (1e-4 * Z / Z[:, 0].std()).contiguous()
-    grad, mom = torch.zeros_like(Z), torch.zeros_like(Z)
     lr = max(n / 4, 50)
     nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
     parts = {"grad": 0.0, "allreduce": 0.0, "sgd": 0.0}
+    # row-local form (default): gather gradient + momentum SGD + NVLink row exchange, no all-reduce
+    peer, exchange = None, "none"
+    if world > 1:
+        try:
+            from torchdr_b200.distributed import PeerEmbedding
+
+            peer = PeerEmbedding.get(Z)
+            exchange = "p2p-fused (rows stored into every peer by the update kernel + symmetric-memory barrier)"
+        except Exception as exc:
+            if rank == 0:
+                print(f"[bench] symmetric memory unavailable: {exc}", file=sys.stderr)
+            exchange = "nccl all-gather of the updated rows"
+    if peer is not None:
+        bufs = [peer.bufs[0], peer.bufs[1]]
+    else:
+        pair = torch.empty((2, n, 2), device=dev)
+        pair[0], pair[1] = Z, Z
+        bufs = [pair[0], pair[1]]
+    state = {"cur": 0}
+    mom_l = torch.zeros((e - s, 2), device=dev)
+    scratch = torch.empty((e - s, 2), device=dev)
+    from torchdr_b200.distributed import all_gather_rows
+
+    def lr_at(t):
+        return lr * min(1.0, (1 + 2 * min(t, 5) / 5) / 3)  # LinearLR with torch defaults (largevis.py:118)
 
     def step(t, first, timed_parts=False):
+        cur = state["cur"]
+        ops.largevis_step(bufs[cur], bufs[1 - cur], s, e - s, rowptr, col, val, scratch, mom_l, t, lr_at(t), 0.8, first,
+                          n_neg=LV_NEG, seed=1234, nan_flag=nan_flag,
+                          peer_ptrs=peer.peer_ptrs(1 - cur) if peer is not None else ())
+        if peer is not None:
+            peer.barrier(1 - cur)
+        elif world > 1:
+            all_gather_rows(bufs[1 - cur], bounds, rank)
+        state["cur"] = 1 - cur
+
+    # the reference's formulation, for comparison (outside the timed blocks): scatter kernel -> all-reduce -> SGD on all rows
+    grad, mom = torch.zeros_like(Z), torch.zeros_like(Z)
+    Zs = Z.clone()
+
+    def scatter_step(t, first, timed_parts=True):
         grad.zero_()
-        if timed_parts:
-            ev[0].record()
-        ops.largevis_grad(Z, s, e - s, P, idx, grad, t, neg=None, n_neg=LV_NEG, seed=1234)
-        if timed_parts:
-            ev[1].record()
+        ev[0].record()
+        ops.largevis_grad(Zs, s, e - s, P, idx, grad, t, neg=None, n_neg=LV_NEG, seed=1234)
+        ev[1].record()
         if world > 1:
             dist.all_reduce(grad, op=dist.ReduceOp.SUM)
-        if timed_parts:
-            ev[2].record()
-        ops.sgd_momentum(Z, mom, grad, lr * min(1.0, (1 + 2 * min(t, 5) / 5) / 3), 0.8, first, nan_flag=nan_flag)
-        if timed_parts:
-            ev[3].record()
-            torch.cuda.synchronize()
-            parts["grad"] += ev[0].elapsed_time(ev[1])
-            parts["allreduce"] += ev[1].elapsed_time(ev[2])
-            parts["sgd"] += ev[2].elapsed_time(ev[3])
+        ev[2].record()
+        ops.sgd_momentum(Zs, mom, grad, lr_at(t), 0.8, first, nan_flag=nan_flag)
+        ev[3].record()
+        torch.cuda.synchronize()
+        parts["grad"] += ev[0].elapsed_time(ev[1])
+        parts["allreduce"] += ev[1].elapsed_time(ev[2])
+        parts["sgd"] += ev[2].elapsed_time(ev[3])
 
     it = 0
     for _ in range(W):
@@ -636,9 +683,9 @@ def largevis_arm(args):
             e1.record()
             _sync_all(world)
             block_ms.append(e0.elapsed_time(e1))
-    for _ in range(5):  # per-stage split, outside the timed region
-        step(it, False, timed_parts=True)
-        it += 1
+    Z = bufs[state["cur"]]
+    for j in range(5):  # the scatter + all-reduce formulation, per stage, outside the timed region
+        scatter_step(j, j == 0)
     ms = torch.tensor(block_ms, device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -651,8 +698,9 @@ def largevis_arm(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", FALLBACK_HBM_GBS))
-    alg = (e - s) * (16.0 + k * (4 + 4 + 8) + LV_NEG * 8 + (k + LV_NEG) * 8)  # ~2.3 KB / point / iteration
-    grad_ms = parts["grad"] / 5
+    # row-local form: z read + write, momentum read + write, union-graph entries (col + val + z_j), own negatives, pushes
+    alg = (e - s) * (16.0 + 16.0 + 8.0 + LV_NEG * 8.0 + LV_NEG * (8.0 + 8.0 + 8.0)) + nnz_union * (4 + 4 + 8.0)
+    scatter_ms = sum(parts.values()) / 5
     out = None
     if rank == 0:
         out = {
@@ -662,22 +710,26 @@ def largevis_arm(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"LargeVis perplexity={LV_PERPLEXITY} n_negatives={LV_NEG} on {n}x{d} clustered synthetic "
                                    "(BASELINE configs[3])", "points": n, "dim": d, "k": k, "parallelism": f"rows sharded x{world}",
-                       "exchange": "none" if world == 1 else "NCCL all-reduce of the N x 2 gradient (affinity_matcher.py:418-425)",
-                       "l2": "per-iteration working set (P + idx %.0f MB per rank) exceeds the L2; no flush" % ((e - s) * k * 8 / 1e6)},
+                       "exchange": exchange, "formulation": "row-local (tdr_largevis_step_f32): gather over S = P + P^T, negatives' push "
+                       "re-generated by the owner of the sampled row, fused momentum SGD; no N x 2 all-reduce",
+                       "union_graph_nnz": nnz_union,
+                       "l2": "per-iteration working set (union graph %.0f MB per rank) exceeds the L2; no flush" % (nnz_union * 8 / 1e6)},
             "timing": {"blocks": blocks, "steps_per_block": K, "block_ms_max_over_ranks": block_list, "reported": "median block"},
-            "stage_ms_per_iteration": {k_: v / 5 for k_, v in parts.items()},
-            "affinity_seconds": t_aff,
-            "roofline": {"bound": "hbm", "kernel": "tdr::largevis_grad_kernel (fp32 atomics scatter)", "achieved": alg / (grad_ms * 1e-3) / 1e9,
-                         "peak": peak, "unit": "GB/s", "frac": alg / (grad_ms * 1e-3) / 1e9 / peak, "traffic": None,
-                         "algorithmic_bytes_per_launch": alg,
-                         "note": "per GPU, gradient kernel alone (events around it, outside the timed blocks); bytes per SURVEY 8(d): "
-                                 "16 + k (4 idx + 4 P + 8 z_j) + 5 x 8 read + (k + 5) x 8 scatter-add per local point"},
+            "reference_formulation_ms_per_iteration": dict({k_: v / 5 for k_, v in parts.items()}, total=scatter_ms,
+                                                           note="scatter kernel (fp32 atomics) -> NCCL all-reduce of N x 2 -> SGD on all "
+                                                                "rows, affinity_matcher.py:418-425; same engine, measured after the timed blocks"),
+            "affinity_seconds": t_aff, "union_graph_seconds": t_graph,
+            "roofline": {"bound": "hbm", "kernel": "tdr::largevis_pull_update_kernel (+ largevis_push_kernel)",
+                         "achieved": alg / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (ms_per_step * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes_per_launch": alg,
+                         "note": "per GPU and iteration (both kernels + exchange): 32 B z/momentum read+write + 8 B push per local row, 16 B "
+                                 "(col, val, z_j) per union-graph entry, 8 B per own negative, 24 B per received push"},
             "gpu_launches": 3 * K * blocks, "clocks": clk.summary(),
         }
     e2e = None
     if not args.no_e2e:
         Xh = X.cpu().pin_memory().numpy()
-        del X, P, idx
+        del X, P, idx, rowptr, col, val, grad, mom, Zs
         m = LargeVis(perplexity=LV_PERPLEXITY, n_negatives=LV_NEG, max_iter=E2E_ITERS, init="normal", random_state=0,
                      process_duplicates=False)
         m.fit_transform(Xh[:max(20000, 2048 * world)])

@@ -159,12 +159,16 @@ TDR_API int tdr_knn_umap_fused_f32(const float* Xq, int64_t nq, int64_t q_row0,
  * ext_* (may be NULL, n_ext=0) are transposed edges received from other ranks
  * (distributed_symmetrize_sparse, sparse.py:209-342): ext_row is the GLOBAL row
  * (owned locally), ext_col the global column, ext_val = P[col,row].
- * Capacity of col/val must be >= 2*n_local*k + n_ext.  *nnz_out is a device int64. */
+ * Capacity of col/val must be >= 2*n_local*k + n_ext.  *nnz_out is a device int64.
+ * mode: TDR_SYM_SUM_MINUS_PROD (UMAP, sparse.py:163-164) or TDR_SYM_SUM = P + P^T (sparse.py:159-160; the union graph
+ * the row-local LargeVis step pulls from). */
+#define TDR_SYM_SUM_MINUS_PROD 0
+#define TDR_SYM_SUM 1
 TDR_API size_t tdr_symmetrize_workspace_bytes(int64_t n_local, int k, int64_t n_ext);
 TDR_API int tdr_symmetrize_csr_f32(const float* P /*[n_local,k]*/, const int32_t* idx /*[n_local,k]*/,
                            int64_t n_local, int k, int64_t row0, int64_t n_total,
                            const int64_t* ext_row, const int32_t* ext_col, const float* ext_val,
-                           int64_t n_ext, int transpose_local,
+                           int64_t n_ext, int transpose_local, int mode,
                            int64_t* rowptr /*[n_local+1]*/, int32_t* col, float* val,
                            int64_t* nnz_out, void* ws, size_t ws_bytes, tdr_stream_t stream);
 
@@ -286,6 +290,24 @@ TDR_API int tdr_largevis_grad_f32(const float* Z, int64_t n_total, int64_t row0,
                           const int64_t* neg /*[n_local,n_neg] or NULL*/, int n_neg,
                           uint64_t seed, int64_t n_iter, float lam, float repulsion,
                           float* grad /*[n_total,2]*/, tdr_stream_t stream);
+
+/* One LargeVis iteration for local rows [row0, row0+n_local) in ROW-LOCAL form — gradient, momentum SGD and row
+ * exchange without the N x 2 all-reduce of affinity_matcher.py:418-425 (in-kernel negatives only):
+ *   rowptr/col/val = CSR of S = P + P^T for the local rows (tdr_symmetrize_csr_f32, mode TDR_SYM_SUM): the attraction
+ *   of row i, 2 lam S_ij Q_ij (z_i - z_j), then collects its own edges and the edges pointing at it in one gather sum;
+ *   the push of a negative pair (i', j) onto j is computed by the owner of j, which re-generates the counter-based
+ *   negative stream of all N rows and keeps the pairs that hit its rows (fp32 atomics into grad_scratch[n_local,2]);
+ *   then buf = mu*buf + g (first: buf = g), z -= lr*buf on the local rows (torch.optim.SGD, NE base.py:331-343),
+ *   written to Z_out (Jacobi: Z_in is read for all N rows) and to the Z_out of n_peers NVLink peers
+ *   (peer_out_ptrs: HOST array of device addresses, may be NULL when n_peers = 0).
+ * mom: [n_local,2] momentum buffer; gnorm_sq / nan_flag as in tdr_umap_step_f32. */
+TDR_API int tdr_largevis_step_f32(const float* Z_in, float* Z_out, int64_t n_total, int64_t row0, int64_t n_local,
+                                  const int64_t* rowptr, const int32_t* col, const float* val,
+                                  int n_neg, uint64_t seed, int64_t n_iter, float lam, float repulsion,
+                                  float* grad_scratch /*[n_local,2]*/, float* mom /*[n_local,2]*/,
+                                  float lr, float momentum, int first,
+                                  double* gnorm_sq, int* nan_flag,
+                                  const uint64_t* peer_out_ptrs, int n_peers, tdr_stream_t stream);
 
 /* t-SNE gradient (tsne.py:162-180 differentiated): sparse attraction on the kNN rows
  * plus the dense N x N repulsion of the logsumexp normaliser (expanded-form distances,

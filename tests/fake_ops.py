@@ -36,9 +36,9 @@ def knn_umap_fused(Xq, Xdb, k, q_row0=0, exclude_self=True, max_iter=100, want_d
     return C, I, P, rho, sigma
 
 
-def symmetrize_csr(Pm, idx, row0, n_total, ext=None, transpose_local=True):
+def symmetrize_csr(Pm, idx, row0, n_total, ext=None, transpose_local=True, mode="sum_minus_prod"):
     assert ext is None and row0 == 0
-    V, J = oracle.symmetrize_ell(Pm, idx)
+    V, J = oracle.symmetrize_ell(Pm, idx, mode=mode)
     return oracle.ell_to_csr(V, J)
 
 
@@ -147,6 +147,36 @@ def largevis_grad(Z, row0, n_local, Pm, idx, grad, n_iter, neg=None, n_neg=5, se
     grad += Zp.grad
 
 
+def largevis_step(Z_in, Z_out, row0, n_local, rowptr, col, val, grad_scratch, mom, n_iter, lr, momentum, first, n_neg=5,
+                  seed=0, lam=1.0, repulsion=1.0, gnorm_sq=None, nan_flag=None, peer_ptrs=()):
+    """tdr_largevis_step_f32 stand-in: gradient of the local rows from the UNION graph S = P + P^T (CSR) — attraction
+    2 lam S_ij Q_ij (z_i - z_j) — plus both halves of every negative pair of the stand-in's own stream (pull on the
+    sampling row, push on the sampled row), then torch.optim.SGD-with-momentum arithmetic on the local rows."""
+    n = Z_in.shape[0]
+    Z = Z_in.double()
+    G = torch.zeros(n, 2, dtype=torch.float64)
+    cnt = (rowptr[1:] - rowptr[:-1]).long()
+    rows = torch.repeat_interleave(torch.arange(n_local) + row0, cnt)
+    cj = col.long()
+    d = Z[rows] - Z[cj]
+    Q = 1.0 / (2.0 + (d * d).sum(1))
+    G.index_add_(0, rows, (2.0 * lam * val.double() * Q).unsqueeze(1) * d)
+    neg = _own_negatives(n, n_neg, seed, n_iter)  # all rows' negatives: pull for local i, push onto local j
+    i_all = torch.arange(n).repeat_interleave(n_neg)
+    j_all = neg.reshape(-1).long()
+    dn = Z[i_all] - Z[j_all]
+    Qn = 1.0 / (2.0 + (dn * dn).sum(1))
+    c = (-2.0 * repulsion / n * Qn * Qn / (1.0 - Qn)).unsqueeze(1) * dn
+    G.index_add_(0, i_all, c)
+    G.index_add_(0, j_all, -c)
+    g = G[row0:row0 + n_local].float()
+    buf = g.clone() if first else mom * momentum + g
+    mom.copy_(buf)
+    Z_out[row0:row0 + n_local] = Z_in[row0:row0 + n_local] - lr * buf
+    if gnorm_sq is not None:
+        gnorm_sq += float((g.double() ** 2).sum())
+
+
 def tsne_workspace(n_local, device):
     return torch.zeros(8, dtype=torch.uint8)
 
@@ -193,7 +223,7 @@ def install_entropic(monkeypatch):
 
     for name, fn in (("knn", knn), ("pairwise_full", pairwise_full), ("indexed_distances", indexed_distances),
                      ("entropic_affinity_rows", entropic_affinity_rows), ("largevis_grad", largevis_grad),
-                     ("tsne_workspace", tsne_workspace), ("tsne_grad", tsne_grad), ("infotsne_grad", infotsne_grad),
+                     ("largevis_step", largevis_step), ("tsne_workspace", tsne_workspace), ("tsne_grad", tsne_grad), ("infotsne_grad", infotsne_grad),
                      ("sne_grad", sne_grad), ("sgd_momentum", sgd_momentum)):
         monkeypatch.setattr(ops, name, fn)
 
@@ -232,7 +262,7 @@ def symmetrize_export(Pm, idx, row0, n_total, world, rank):
     return counts, j[away][order].contiguous(), i[away][order].int().contiguous(), v[away][order].contiguous()
 
 
-def symmetrize_csr_chunk(Pm, idx, row0, n_total, ext=None, transpose_local=True):
+def symmetrize_csr_chunk(Pm, idx, row0, n_total, ext=None, transpose_local=True, mode="sum_minus_prod"):
     """Q = P + P^T - P o P^T for the local rows; P^T entries come from local edges landing on local rows and from the
     received triples.  Same three separately rounded fp32 operations as utils/sparse.py:163-164."""
     n_local, k = Pm.shape

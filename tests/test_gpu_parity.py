@@ -596,6 +596,57 @@ def test_largevis_gradient_and_steps(ops):
             assert rel_fro(Z.cpu(), g[f"Z_{step + 1}"]) < 1e-4, step
 
 
+def test_largevis_row_local_step_equals_scatter_gradient(ops):
+    """tdr_largevis_step_f32 (gather form on S = P + P^T, push of the negatives by the owner of the sampled row,
+    fused momentum SGD) against tdr_largevis_grad_f32 (the autograd scatter, itself held against the reference's
+    gradient above) on the same in-kernel negative stream: the gradient (= the momentum buffer after a first step),
+    the update, a second step with momentum, and the same rows computed as three row chunks."""
+    g = golden("largevis_n300_d16_p10")
+    P, I = _cuda(t(g["P"])), _cuda(t(g["I"]))
+    n = 300
+    Z = _cuda(t(g["Z0"])).clone()
+    rowptr, col, val = ops.symmetrize_csr(P, I, 0, n, mode="sum")
+    # union graph: S = P + P^T exactly (dense check)
+    S = torch.zeros(n, n, device=DEV)
+    S[torch.arange(n, device=DEV).repeat_interleave(P.shape[1]), I.reshape(-1).long()] = P.reshape(-1)
+    S = S + S.T
+    cnt = (rowptr[1:] - rowptr[:-1]).long()
+    rows = torch.repeat_interleave(torch.arange(n, device=DEV), cnt)
+    torch.testing.assert_close(S[rows, col.long()], val, rtol=1e-7, atol=0)
+    assert int(cnt.sum()) == int((S != 0).sum())
+    lr, mu = 75.0, 0.8
+    Zc = Z.clone()
+    momf = torch.zeros(n, 2, device=DEV)
+    Za, Zb = Z.clone(), torch.empty_like(Z)
+    mom, scratch = torch.zeros(n, 2, device=DEV), torch.empty(n, 2, device=DEV)
+    gn = torch.zeros(1, dtype=torch.float64, device=DEV)
+    for step in range(3):
+        grad = torch.zeros(n, 2, device=DEV)
+        ops.largevis_grad(Zc, 0, n, P, I, grad, step, neg=None, n_neg=5, seed=7, lam=1.0, repulsion=1.3)
+        ops.sgd_momentum(Zc, momf, grad, lr, mu, step == 0)
+        gn.zero_()
+        ops.largevis_step(Za, Zb, 0, n, rowptr, col, val, scratch, mom, step, lr, mu, step == 0, n_neg=5, seed=7, lam=1.0,
+                          repulsion=1.3, gnorm_sq=gn)
+        Za, Zb = Zb, Za
+        if step == 0:
+            assert rel_fro(mom.cpu(), grad.cpu()) < 1e-5  # first step: momentum buffer == gradient
+            torch.testing.assert_close(float(gn.item()), float((grad.double() ** 2).sum()), rtol=1e-5, atol=0)
+        assert rel_fro(Za.cpu(), Zc.cpu()) < 1e-5, step
+    # three row chunks, each with its own slice of the union graph, reproduce the full step (Jacobi: same Z_in)
+    Zin = Za.clone()
+    full, mfull = torch.empty_like(Zin), mom.clone()
+    ops.largevis_step(Zin, full, 0, n, rowptr, col, val, scratch, mfull, 9, lr, mu, False, n_neg=5, seed=7)
+    parts = torch.zeros_like(Zin)
+    for r in range(3):
+        s, e = oracle.chunk_bounds(n, r, 3)
+        lo, hi = int(rowptr[s]), int(rowptr[e])
+        mpart = mom[s:e].clone()
+        ops.largevis_step(Zin, parts, s, e - s, (rowptr[s:e + 1] - rowptr[s]).contiguous(), col[lo:hi].contiguous(),
+                          val[lo:hi].contiguous(), torch.empty(e - s, 2, device=DEV), mpart, 9, lr, mu, False, n_neg=5, seed=7)
+        assert rel_fro(mpart.cpu(), mfull[s:e].cpu()) < 1e-6
+    assert rel_fro(parts.cpu(), full.cpu()) < 1e-6
+
+
 def _loop_tol(T):
     """Tolerance on Z after T steps of the early-exaggerated momentum loops (t-SNE, InfoTSNE; lr 50-75, lambda 12).
 

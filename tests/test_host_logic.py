@@ -544,6 +544,29 @@ def test_estimators_are_sklearn_estimators_and_torch_modules():
         tb.TSNE(sparsity=False, distributed=False)._compute_affinity(torch.zeros(8, 3))
 
 
+def test_largevis_row_local_form_equals_scatter_form_on_cpu(monkeypatch):
+    """The row-local LargeVis step (union graph S = P + P^T gathered per row + both halves of every negative pair,
+    momentum SGD on the local rows: tdr_largevis_step_f32) must be the same optimisation as the reference's
+    formulation (autograd scatter of largevis.py:181-201 + SGD on all rows).  Both run here on the CPU stand-ins with
+    the same negative stream; the stand-in of the scatter form differentiates the oracle's loss with autograd."""
+    import fake_ops
+    from helpers import rel_fro
+
+    import torchdr_b200 as tb
+
+    fake_ops.install(monkeypatch)
+    fake_ops.install_entropic(monkeypatch)
+    g = golden("largevis_n300_d16_p10")
+    X, Z0 = t(g["X"]), t(g["Z0"])
+    out = {}
+    for row_local in (True, False):
+        m = tb.LargeVis(perplexity=10, max_iter=12, init=Z0, init_scaling=float(Z0[:, 0].std()), random_state=0,
+                        process_duplicates=False, distributed=False, row_local=row_local, knn_order="input")
+        out[row_local] = m.fit_transform(X)
+        assert (m._row_local() is row_local)
+    assert rel_fro(out[True], out[False]) < 1e-5, rel_fro(out[True], out[False])
+
+
 def test_baseline_config_1_host_flow_on_cpu(monkeypatch):
     """BASELINE.json configs[0] through the public estimator on the CPU stand-ins: TSNE(perplexity=30) on the
     reference's 2000 x 50 blobs run.  Tolerances as in tests/test_oracle_golden.py (the reference's own backward is not

@@ -21,6 +21,7 @@ TDR_MAX_K = 160
 TDR_RUN_SYNC_WORDS = 8
 TDR_RUN_STATUS_WORD = 4
 METRIC_IDS = {"sqeuclidean": 0, "euclidean": 1}
+SYM_MODES = {"sum_minus_prod": 0, "sum": 1}
 KNN_PATHS = {"auto": 0, "simt": 1, "tc": 2}
 KNN_PRUNE = {"default": -1, "off": 0, "on": 1, "certified": 2}
 
@@ -45,8 +46,8 @@ SIGNATURES = {
     "tdr_knn_umap_fused_f32": (c_int, [P, c_int64, c_int64, P, c_int64, c_int, c_int, c_int, c_int, P, P, P, P, P,
                                        c_int, c_int, P, P, c_size_t, P]),
     "tdr_symmetrize_workspace_bytes": (c_size_t, [c_int64, c_int, c_int64]),
-    "tdr_symmetrize_csr_f32": (c_int, [P, P, c_int64, c_int, c_int64, c_int64, P, P, P, c_int64, c_int, P, P, P, P,
-                                       P, c_size_t, P]),
+    "tdr_symmetrize_csr_f32": (c_int, [P, P, c_int64, c_int, c_int64, c_int64, P, P, P, c_int64, c_int, c_int, P, P, P,
+                                       P, P, c_size_t, P]),
     "tdr_symmetrize_export_f32": (c_int, [P, P, c_int64, c_int, c_int64, c_int64, c_int, c_int, P, P, P, P, P]),
     "tdr_csr_to_ell_f32": (c_int, [P, P, P, c_int64, c_int64, c_float, P, P, P]),
     "tdr_max_f32": (c_int, [P, c_int64, P, P]),
@@ -67,6 +68,8 @@ SIGNATURES = {
                                      c_int, c_int, c_int, ctypes.c_uint32, c_double, P]),
     "tdr_largevis_grad_f32": (c_int, [P, c_int64, c_int64, c_int64, P, P, c_int, P, c_int, c_uint64, c_int64,
                                       c_float, c_float, P, P]),
+    "tdr_largevis_step_f32": (c_int, [P, P, c_int64, c_int64, c_int64, P, P, P, c_int, c_uint64, c_int64, c_float,
+                                      c_float, P, P, c_float, c_float, c_int, P, P, ctypes.POINTER(c_uint64), c_int, P]),
     "tdr_tsne_workspace_bytes": (c_size_t, [c_int64]),
     "tdr_tsne_grad_f32": (c_int, [P, c_int64, c_int64, c_int64, P, P, c_int, c_float, c_float, c_int, P, P, c_size_t,
                                   P]),

@@ -17,6 +17,8 @@
 //   attraction sum P_ij D_ij (dL/dD = lam P); repulsion = (1/N) sum_i log sum_j exp(-C_ij), C the expanded
 //   form on the embedding, diagonal included:  grad_i = -(2 rep/N) sum_j e_ij (1/S_i + 1/S_j)(z_i - z_j).
 // SGD       torch.optim.SGD with momentum (NE base.py:331-343).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace tdr {
@@ -74,6 +76,114 @@ largevis_grad_kernel(const float2* __restrict__ Z, int64_t n_total, int64_t row0
     gy = warp_sum(gy);
     if (lane == 0) {
         atomicAdd(reinterpret_cast<float2*>(grad) + gi, make_float2(gx, gy));
+    }
+}
+
+// ---- LargeVis, row-local form (tdr_largevis_step_f32) ------------------------------------------------------------
+// The scatter of the autograd graph is turned into gathers, so that a rank produces the COMPLETE gradient of its
+// own rows and the N x 2 all-reduce of affinity_matcher.py:418-425 disappears:
+//   * attraction: row i receives 2 lam P_ij Q_ij (z_i - z_j) from its own edge (i, j) and 2 lam P_ji Q_ji (z_i - z_j)
+//     from every edge (j, i) that points at it; Q is symmetric in (i, j), so with S = P + P^T (the union graph,
+//     tdr_symmetrize_csr_f32 mode SUM) both are one term  2 lam S_ij Q_ij (z_i - z_j)  of a row-local sum;
+//   * repulsion: row i pulls from its own negatives; the equal and opposite force on a negative j is the only true
+//     scatter left.  The negatives are a counter-based stream (Philox, counter = iteration / row / slot), so the
+//     owner of j does not need to be told: largevis_push_kernel re-generates the negatives of ALL rows — 2 Philox
+//     blocks per row — and keeps the pairs whose target is one of its own rows (local fp32 atomics, ~n_neg per row).
+// largevis_pull_update_kernel then adds the row-local sums, applies torch.optim.SGD with momentum to the rank's
+// rows (NE base.py:331-343) and writes them to Z_out — and to every NVLink peer's Z_out — Jacobi like the UMAP step.
+__global__ void __launch_bounds__(256)
+largevis_push_kernel(const float2* __restrict__ Z, int64_t n_total, int64_t row0, int64_t n_local, int n_neg,
+                     uint64_t seed, int64_t n_iter, float rep_over_n, float* __restrict__ grad_local) {
+    const Philox rng(seed);
+    for (int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < n_total; gi += (int64_t)gridDim.x * blockDim.x) {
+        float2 zi;
+        bool have = false;
+        for (int s0 = 0; s0 < n_neg; s0 += 4) {
+            const uint4 u = rng((uint32_t)n_iter, (uint32_t)(n_iter >> 32) ^ (uint32_t)(gi >> 32), (uint32_t)gi,
+                                (uint32_t)(s0 >> 2));
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (s0 + q >= n_neg) break;
+                int64_t j = (int64_t)(((uint64_t)w[q] * (uint64_t)(n_total - 1)) >> 32);
+                j += (j >= gi) ? 1 : 0;  // NE base.py:636
+                if (j < row0 || j >= row0 + n_local) continue;
+                if (!have) {
+                    zi = __ldg(Z + gi);
+                    have = true;
+                }
+                const float2 zj = __ldg(Z + j);
+                const float dx = __fsub_rn(zi.x, zj.x), dy = __fsub_rn(zi.y, zj.y);
+                const float D = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                const float q1 = __fdiv_rn(1.0f, __fadd_rn(1.0f, D));   // largevis.py:188
+                const float Q = __fdiv_rn(q1, __fadd_rn(q1, 1.0f));     // largevis.py:189
+                const float c = -2.0f * rep_over_n * __fdiv_rn(Q * Q, __fsub_rn(1.0f, Q));
+                atomicAdd(reinterpret_cast<float2*>(grad_local) + (j - row0), make_float2(-c * dx, -c * dy));
+            }
+        }
+    }
+}
+
+struct LvPeers {
+    float2* out[8];
+    int n;
+};
+
+__global__ void __launch_bounds__(kAgWarps * 32)
+largevis_pull_update_kernel(const float2* __restrict__ Zin, float2* __restrict__ Zout, int64_t n_total, int64_t row0,
+                            int64_t n_local, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                            const float* __restrict__ val, int n_neg, uint64_t seed, int64_t n_iter, float lam,
+                            float rep_over_n, const float2* __restrict__ push, float2* __restrict__ mom, float neg_lr,
+                            float mu, int first, double* __restrict__ gnorm_sq, int* __restrict__ nan_flag,
+                            const LvPeers peers) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * kAgWarps + (threadIdx.x >> 5);
+    if (r >= n_local) return;
+    const int64_t gi = row0 + r;
+    const float2 zi = __ldg(Zin + gi);
+    float gx = 0.0f, gy = 0.0f;
+    const int64_t e0 = __ldg(rowptr + r), e1 = __ldg(rowptr + r + 1);
+    for (int64_t e = e0 + lane; e < e1; e += 32) {
+        const float2 zj = __ldg(Zin + __ldg(col + e));
+        const float dx = __fsub_rn(zi.x, zj.x), dy = __fsub_rn(zi.y, zj.y);
+        const float D = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        const float q = __fdiv_rn(1.0f, __fadd_rn(1.0f, D));   // largevis.py:199
+        const float Q = __fdiv_rn(q, __fadd_rn(q, 1.0f));      // largevis.py:200
+        const float c = 2.0f * lam * __ldg(val + e) * Q;
+        gx = fmaf(c, dx, gx);
+        gy = fmaf(c, dy, gy);
+    }
+    const Philox rng(seed);
+    for (int s = lane; s < n_neg; s += 32) {
+        const int64_t j = draw_negative(rng, n_iter, gi, s, n_total);
+        const float2 zj = __ldg(Zin + j);
+        const float dx = __fsub_rn(zi.x, zj.x), dy = __fsub_rn(zi.y, zj.y);
+        const float D = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        const float q = __fdiv_rn(1.0f, __fadd_rn(1.0f, D));   // largevis.py:188
+        const float Q = __fdiv_rn(q, __fadd_rn(q, 1.0f));      // largevis.py:189
+        const float c = -2.0f * rep_over_n * __fdiv_rn(Q * Q, __fsub_rn(1.0f, Q));
+        gx = fmaf(c, dx, gx);
+        gy = fmaf(c, dy, gy);
+    }
+    gx = warp_sum(gx);
+    gy = warp_sum(gy);
+    if (lane == 0) {
+        const float2 ps = push[r];
+        const float g0 = gx + ps.x, g1 = gy + ps.y;
+        // torch.optim.sgd: buf = g (first step) | buf.mul_(mu).add_(g) ; param.add_(buf, alpha=-lr)
+        float2 b;
+        if (first) {
+            b = make_float2(g0, g1);
+        } else {
+            const float2 old = mom[r];
+            b = make_float2(__fadd_rn(__fmul_rn(old.x, mu), g0), __fadd_rn(__fmul_rn(old.y, mu), g1));
+        }
+        mom[r] = b;
+        const float2 zo = make_float2(fmaf(neg_lr, b.x, zi.x), fmaf(neg_lr, b.y, zi.y));
+        Zout[gi] = zo;
+        for (int q = 0; q < peers.n; ++q) peers.out[q][gi] = zo;
+        if (gnorm_sq) atomicAdd(gnorm_sq, (double)g0 * g0 + (double)g1 * g1);
+        if (nan_flag && (zo.x != zo.x || zo.y != zo.y)) atomicExch(nan_flag, 1);
     }
 }
 
@@ -344,6 +454,41 @@ extern "C" TDR_API int tdr_largevis_grad_f32(const float* Z, int64_t n_total, in
     largevis_grad_kernel<<<blocks, kAgWarps * 32, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float2*>(Z), n_total, row0, n_local, P, idx, k, neg, n_neg, seed, n_iter, lam,
         repulsion / (float)n_total, grad);
+    TDR_LAUNCH_CHECK();
+    return TDR_OK;
+}
+
+extern "C" TDR_API int tdr_largevis_step_f32(const float* Z_in, float* Z_out, int64_t n_total, int64_t row0, int64_t n_local,
+                                             const int64_t* rowptr, const int32_t* col, const float* val, int n_neg,
+                                             uint64_t seed, int64_t n_iter, float lam, float repulsion,
+                                             float* grad_scratch, float* mom, float lr, float momentum, int first,
+                                             double* gnorm_sq, int* nan_flag, const uint64_t* peer_out_ptrs /*host*/,
+                                             int n_peers, tdr_stream_t stream) {
+    TDR_CHECK_ARG(Z_in && Z_out && Z_in != Z_out && rowptr && col && val && grad_scratch && mom,
+                  "tdr_largevis_step_f32: null pointer / aliased buffers");
+    TDR_CHECK_ARG(n_total >= 2 && row0 >= 0 && n_local >= 0 && row0 + n_local <= n_total && n_neg >= 0,
+                  "tdr_largevis_step_f32: bad shape");
+    TDR_CHECK_ARG(n_peers >= 0 && n_peers <= 8 && (n_peers == 0 || peer_out_ptrs), "tdr_largevis_step_f32: at most 8 peers");
+    if (n_local == 0) return TDR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const float rep_over_n = repulsion / (float)n_total;
+    TDR_CUDA(cudaMemsetAsync(grad_scratch, 0, (size_t)n_local * 8, st));
+    if (n_neg > 0) {
+        const unsigned pgrid = (unsigned)std::min<int64_t>((int64_t)kNumSMs * 16, (n_total + 255) / 256);
+        largevis_push_kernel<<<pgrid, 256, 0, st>>>(reinterpret_cast<const float2*>(Z_in), n_total, row0, n_local, n_neg,
+                                                    seed, n_iter, rep_over_n, grad_scratch);
+    }
+    LvPeers peers{};
+    peers.n = n_peers;
+    for (int q = 0; q < n_peers; ++q) {
+        peers.out[q] = reinterpret_cast<float2*>(peer_out_ptrs[q]);
+        TDR_CHECK_ARG(peers.out[q] && (const float*)peers.out[q] != Z_in, "tdr_largevis_step_f32: bad peer buffer");
+    }
+    const unsigned blocks = (unsigned)((n_local + kAgWarps - 1) / kAgWarps);
+    largevis_pull_update_kernel<<<blocks, kAgWarps * 32, 0, st>>>(
+        reinterpret_cast<const float2*>(Z_in), reinterpret_cast<float2*>(Z_out), n_total, row0, n_local, rowptr, col, val,
+        n_neg, seed, n_iter, lam, rep_over_n, reinterpret_cast<const float2*>(grad_scratch),
+        reinterpret_cast<float2*>(mom), -lr, momentum, first, gnorm_sq, nan_flag, peers);
     TDR_LAUNCH_CHECK();
     return TDR_OK;
 }

@@ -69,7 +69,7 @@ sym_heads_kernel(const uint64_t* __restrict__ sk, int64_t m, uint64_t sentinel, 
 __global__ void __launch_bounds__(256)
 sym_combine_kernel(const uint64_t* __restrict__ sk, const float* __restrict__ sv, int64_t m,
                    uint64_t sentinel, int64_t n_total, const int* __restrict__ head,
-                   const int64_t* __restrict__ pos, int32_t* __restrict__ col, float* __restrict__ val) {
+                   const int64_t* __restrict__ pos, int mode, int32_t* __restrict__ col, float* __restrict__ val) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m || !head[i]) return;
     const uint64_t cell = sk[i] >> 1;
@@ -80,8 +80,9 @@ sym_combine_kernel(const uint64_t* __restrict__ sk, const float* __restrict__ sv
     }
     const int64_t o = pos[i];
     col[o] = (int32_t)(cell % (uint64_t)n_total);
-    // sparse.py:163-164: vP + vPT - vP * vPT, three separately rounded ops
-    val[o] = __fsub_rn(__fadd_rn(from_p, from_pt), __fmul_rn(from_p, from_pt));
+    // sparse.py:163-164: vP + vPT - vP * vPT, three separately rounded ops; mode SUM (sparse.py:159-160): vP + vPT
+    const float sum = __fadd_rn(from_p, from_pt);
+    val[o] = mode == TDR_SYM_SUM ? sum : __fsub_rn(sum, __fmul_rn(from_p, from_pt));
 }
 
 __global__ void __launch_bounds__(256)
@@ -257,10 +258,11 @@ extern "C" TDR_API size_t tdr_symmetrize_workspace_bytes(int64_t n_local, int k,
 
 extern "C" TDR_API int tdr_symmetrize_csr_f32(const float* P, const int32_t* idx, int64_t n_local, int k, int64_t row0,
                                       int64_t n_total, const int64_t* ext_row, const int32_t* ext_col,
-                                      const float* ext_val, int64_t n_ext, int transpose_local,
+                                      const float* ext_val, int64_t n_ext, int transpose_local, int mode,
                                       int64_t* rowptr, int32_t* col, float* val, int64_t* nnz_out, void* ws,
                                       size_t ws_bytes, tdr_stream_t stream) {
     TDR_CHECK_ARG(P && idx && rowptr && col && val, "tdr_symmetrize_csr_f32: null pointer");
+    TDR_CHECK_ARG(mode == TDR_SYM_SUM_MINUS_PROD || mode == TDR_SYM_SUM, "tdr_symmetrize_csr_f32: unknown mode %d", mode);
     TDR_CHECK_ARG(n_local >= 1 && k >= 1 && n_total >= n_local && row0 >= 0 && row0 + n_local <= n_total,
                   "tdr_symmetrize_csr_f32: bad shape");
     TDR_CHECK_ARG(n_ext == 0 || (ext_row && ext_col && ext_val), "tdr_symmetrize_csr_f32: null ext arrays");
@@ -283,7 +285,7 @@ extern "C" TDR_API int tdr_symmetrize_csr_f32(const float* P, const int32_t* idx
     sym_heads_kernel<<<blocks_for(m + 1), 256, 0, st>>>(w.k_out, m, sentinel, w.head);
     tmp = w.cub_bytes;
     TDR_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tmp, w.head, w.pos, m + 1, st));
-    sym_combine_kernel<<<blocks_for(m), 256, 0, st>>>(w.k_out, w.v_out, m, sentinel, n_total, w.head, w.pos, col, val);
+    sym_combine_kernel<<<blocks_for(m), 256, 0, st>>>(w.k_out, w.v_out, m, sentinel, n_total, w.head, w.pos, mode, col, val);
     sym_rowptr_kernel<<<blocks_for(n_local + 1), 256, 0, st>>>(w.k_out, m, n_local, n_total, w.pos, rowptr, nnz_out);
     TDR_LAUNCH_CHECK();
     return TDR_OK;

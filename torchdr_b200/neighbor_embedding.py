@@ -782,13 +782,14 @@ class LargeVis(_EntropicInputMixin, _NeighborEmbeddingB200):
                  max_iter=1000, device="auto", backend=None, verbose=False, random_state=None, max_iter_affinity=100,
                  metric="sqeuclidean", n_negatives=5, sparsity=True, early_exaggeration_coeff=None,
                  early_exaggeration_iter=None, check_interval=50, discard_NNs=False, compile=False,
-                 distributed="auto", **kwargs):
+                 distributed="auto", row_local=True, **kwargs):
         self.metric = metric
         self.perplexity = perplexity
         self.max_iter_affinity = max_iter_affinity
         self.sparsity = sparsity
         self.n_negatives = n_negatives
         self.discard_NNs = discard_NNs
+        self.row_local = row_local  # engine-native: False forces the reference's scatter + all-reduce formulation
         super().__init__(n_components=n_components, lr=lr, optimizer=optimizer, optimizer_kwargs=optimizer_kwargs,
                          scheduler=scheduler, scheduler_kwargs=scheduler_kwargs, min_grad_norm=min_grad_norm,
                          max_iter=max_iter, init=init, init_scaling=init_scaling, device=device, backend=backend,
@@ -799,6 +800,92 @@ class LargeVis(_EntropicInputMixin, _NeighborEmbeddingB200):
         self.affinity_in = EntropicAffinity(perplexity=perplexity, metric=metric, max_iter=max_iter_affinity,
                                             device=self.device, backend=backend, verbose=verbose, sparsity=sparsity,
                                             distributed=self.distributed)
+
+    def _row_local(self):
+        """True when the fit can use the row-local step (tdr_largevis_step_f32): momentum SGD fused in the kernel,
+        negatives drawn in-kernel, no per-step hooks.  Otherwise: scatter kernel + all-reduce, as the reference."""
+        base = _NeighborEmbeddingB200
+        hooks = any(getattr(type(self), h) is not getattr(base, h) for h in ("on_training_step_start", "on_training_step_end"))
+        return self.row_local and self._uses_native_sgd() and not hooks and not self.discard_NNs
+
+    def _compute_affinity(self, X):
+        super()._compute_affinity(X)
+        self._graph = None
+        if self._row_local():
+            # union graph S = P + P^T of the local rows (the same edge exchange as UMAP's symmetrisation): row i's
+            # attraction then gathers its own edges and the edges pointing at it — no scatter, no N x 2 all-reduce
+            n = X.shape[0]
+            s, e = self.chunk_start_, self.chunk_end_
+            ext = None
+            if self.world_size > 1:
+                from .distributed import exchange_edges
+
+                counts, er, ec, ev = ops.symmetrize_export(self.affinity_in_, self.NN_indices_, s, n, self.world_size, self.rank)
+                ext = exchange_edges(counts, er, ec, ev)
+            self._graph = ops.symmetrize_csr(self.affinity_in_, self.NN_indices_, s, n, ext=ext, mode="sum")
+
+    def _loop(self):
+        if getattr(self, "_graph", None) is None:
+            return super()._loop()
+        rowptr, col, val = self._graph
+        s, e = self.chunk_start_, self.chunk_end_
+        n_local = e - s
+        Za = self.embedding_
+        dev = Za.device
+        peer, cur = None, 0
+        self.exchange_ = "none" if self.world_size == 1 else "nccl-allgather"
+        if self.world_size > 1 and os.environ.get("TDR_NO_P2P") != "1":
+            try:
+                peer = PeerEmbedding.get(Za)
+                Za, Zb = peer.bufs[0], peer.bufs[1]
+                self.exchange_ = "p2p-fused"
+            except Exception as exc:  # symmetric memory unavailable on this system
+                self.logger.warning(f"symmetric memory unavailable ({exc}); falling back to NCCL all-gather")
+                peer = None
+        if peer is None:
+            pair = torch.empty((2,) + tuple(Za.shape), dtype=Za.dtype, device=dev)
+            pair[0], pair[1] = Za, Za
+            Za, Zb = pair[0], pair[1]
+        self._mom = torch.zeros((n_local, 2), dtype=torch.float32, device=dev)
+        self._grad = torch.empty((n_local, 2), dtype=torch.float32, device=dev)
+        seed, rep = self._kernel_seed(), float(self.repulsion_strength)
+        first = True
+        self._last_step = -1
+        for step in range(self.max_iter):
+            self.n_iter_ = torch.tensor(step, dtype=torch.long)
+            self._last_step = step
+            check = step % self.check_interval == 0
+            lr, mom = self._hyper()
+            if check:
+                self._gnorm.zero_()
+            ops.largevis_step(Za, Zb, s, n_local, rowptr, col, val, self._grad, self._mom, step, lr, mom,
+                              first or mom == 0.0, n_neg=self.n_negatives, seed=seed,
+                              lam=float(self.early_exaggeration_coeff_), repulsion=rep,
+                              gnorm_sq=self._gnorm if check else None, nan_flag=self._nan,
+                              peer_ptrs=peer.peer_ptrs(1 - cur) if peer is not None else ())
+            first = False
+            if peer is not None:
+                peer.barrier(1 - cur)  # every rank's rows have landed in every copy of the new buffer
+                cur = 1 - cur
+            elif self.world_size > 1:
+                all_gather_rows(Zb, self._bounds, self.rank)
+            Za, Zb = Zb, Za
+            self.embedding_ = Za
+            self._advance_schedule()
+            if self.early_exaggeration_coeff_ > 1 and step == self.early_exaggeration_iter:  # NE base.py:282-295
+                self.early_exaggeration_coeff_ = 1
+                self._set_learning_rate()
+                self._configure_optimizer()
+                self._configure_scheduler()
+                first = True
+            if check:
+                if self.world_size > 1:
+                    dist.all_reduce(self._gnorm, op=dist.ReduceOp.SUM)
+                self._check_nan(step)
+                if self._converged(step, float(self._gnorm.item()) ** 0.5):
+                    break
+        self._check_nan(self._last_step)
+        self.embedding_ = Za.clone() if peer is not None else Za
 
     def _compute_gradient(self, Z, step):
         s, e = self.chunk_start_, self.chunk_end_

@@ -167,8 +167,9 @@ def entropic_dense_rows(C, target_entropy, log_n_total, bounds=None, max_iter=10
     return logP, eps, log_norm
 
 
-def symmetrize_csr(Pm, idx, row0, n_total, ext=None, transpose_local=True):
-    """Q = P + P^T - P o P^T for the local rows -> (rowptr i64[n+1], col i32[nnz], val f32[nnz])."""
+def symmetrize_csr(Pm, idx, row0, n_total, ext=None, transpose_local=True, mode="sum_minus_prod"):
+    """Q = P + P^T - P o P^T (mode "sum_minus_prod") or P + P^T ("sum") for the local rows
+    -> (rowptr i64[n+1], col i32[nnz], val f32[nnz])."""
     Pm = _dev_f32(Pm, "P")
     idx = idx.contiguous()
     assert idx.dtype == torch.int32 and idx.shape == Pm.shape
@@ -190,7 +191,7 @@ def symmetrize_csr(Pm, idx, row0, n_total, ext=None, transpose_local=True):
     nnz = torch.zeros((1,), dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         check(lib.tdr_symmetrize_csr_f32(ptr(Pm), ptr(idx), n_local, k, row0, n_total, ptr(er), ptr(ec), ptr(ev),
-                                         n_ext, int(transpose_local), ptr(rowptr), ptr(col), ptr(val), ptr(nnz),
+                                         n_ext, int(transpose_local), _lib.SYM_MODES[mode], ptr(rowptr), ptr(col), ptr(val), ptr(nnz),
                                          ptr(ws), ws.numel(), stream()), "tdr_symmetrize_csr_f32")
     m = int(nnz.item())
     return rowptr, col[:m].clone(), val[:m].clone()
@@ -348,6 +349,19 @@ def largevis_grad(Z, row0, n_local, Pm, idx, grad, n_iter, neg=None, n_neg=5, se
         check(_lib.load().tdr_largevis_grad_f32(ptr(Z), Z.shape[0], row0, n_local, ptr(Pm), ptr(idx), Pm.shape[1],
                                                 ptr(neg), n_neg, seed, n_iter, float(lam), float(repulsion),
                                                 ptr(grad), stream()), "tdr_largevis_grad_f32")
+
+
+def largevis_step(Z_in, Z_out, row0, n_local, rowptr, col, val, grad_scratch, mom, n_iter, lr, momentum, first, n_neg=5,
+                  seed=0, lam=1.0, repulsion=1.0, gnorm_sq=None, nan_flag=None, peer_ptrs=()):
+    """One row-local LargeVis iteration (gradient from the P + P^T graph, momentum SGD on the local rows, rows written to
+    Z_out and to the NVLink peers' Z_out)."""
+    arr = (ctypes.c_uint64 * max(len(peer_ptrs), 1))(*[int(x) for x in peer_ptrs])
+    with torch.cuda.device(Z_in.device):
+        check(_lib.load().tdr_largevis_step_f32(ptr(Z_in), ptr(Z_out), Z_in.shape[0], row0, n_local, ptr(rowptr), ptr(col),
+                                                ptr(val), n_neg, seed, n_iter, float(lam), float(repulsion),
+                                                ptr(grad_scratch), ptr(mom), float(lr), float(momentum), int(first),
+                                                ptr(gnorm_sq), ptr(nan_flag), arr, len(peer_ptrs), stream()),
+              "tdr_largevis_step_f32")
 
 
 def tsne_workspace(n_local, device):
