@@ -81,7 +81,8 @@ report(f"8 sharded iterations vs single GPU (rel {err:.2e})", err < 1e-3)
 try:
     from torchdr_b200.distributed import PeerEmbedding
 
-    peer = PeerEmbedding(Z0)
+    peer = PeerEmbedding(Z0.numel(), Z0.dtype, Z0.device)
+    peer.load(Z0)
     Zp, Zq = peer.bufs[0], peer.bufs[1]
     eons2 = g_loc[3].clone()
     cur = 0
@@ -93,7 +94,8 @@ try:
         cur = 1 - cur
     report("p2p-fused step: 8 iterations bit-identical to the all-gather path", torch.equal(Zp, Zc))
     # native multi-step loop (flag barrier kernel instead of the host-driven barrier)
-    peer2 = PeerEmbedding(Z0)
+    peer2 = PeerEmbedding(Z0.numel(), Z0.dtype, Z0.device)
+    peer2.load(Z0)
     c2 = ops.umap_run_p2p(peer2, 0, s, e - s, g_loc[0], g_loc[1], g_loc[2], g_loc[3].clone(), 0, lrs, pa, pb, seed=11)
     torch.cuda.synchronize()
     report("native p2p loop (tdr_umap_run_p2p_f32): 8 iterations bit-identical", torch.equal(peer2.bufs[c2], Zc))
@@ -133,6 +135,33 @@ for cls, kw in ((tb.UMAP, dict(n_neighbors=15, max_iter=60)), (tb.LargeVis, dict
     dist.broadcast(Z0r, src=0)
     same = float((Zt - Z0r).abs().max())
     report(f"{cls.__name__} fit under torchrun x{world}: finite={fin}, max |rank0 - rank{rank}| = {same:.1e}", fin and same == 0.0)
+
+# rows WITHOUT index locality: the fit runs in rank 0's Voronoi-tree order (broadcast), result in input order on all ranks
+Xs = blobs(30011, 48, 40, 7)
+Xs = Xs[torch.randperm(30011, generator=torch.Generator().manual_seed(1))].contiguous()
+from torchdr_b200 import reorder as _ro
+seen = {}
+_orig = tb.UMAPAffinity.compute_csr
+def _spy(self, X):
+    seen["order"] = self.knn_order
+    return _orig(self, X)
+tb.UMAPAffinity.compute_csr = _spy
+m = tb.UMAP(n_neighbors=15, max_iter=40, init="normal", random_state=0, process_duplicates=False)
+Zs = m.fit_transform(Xs.numpy())
+tb.UMAPAffinity.compute_csr = _orig
+Zt = torch.from_numpy(Zs).to(dev)
+Z0r = Zt.clone()
+dist.broadcast(Z0r, src=0)
+report(f"UMAP on shuffled rows x{world}: order={seen.get('order')}, locality {_ro.index_locality(Xs.to(dev)):.2f}, identical on all ranks",
+       seen.get("order") == "presorted" and bool(np.isfinite(Zs).all()) and float((Zt - Z0r).abs().max()) == 0.0)
+# LargeVis: row-local form (default) vs the scatter + all-reduce form, 6 iterations from the same initialisation
+g1 = torch.Generator().manual_seed(5)
+Zi2 = torch.randn(n, 2, generator=g1)
+Za_ = tb.LargeVis(perplexity=10, max_iter=6, init=Zi2, random_state=0, process_duplicates=False, knn_order="input").fit_transform(Xh)
+Zb_ = tb.LargeVis(perplexity=10, max_iter=6, init=Zi2, random_state=0, process_duplicates=False, knn_order="input", row_local=False).fit_transform(Xh)
+Zc_ = tb.LargeVis(perplexity=10, max_iter=6, init=Zi2, random_state=0, process_duplicates=False, knn_order="input", distributed=False).fit_transform(Xh)
+rel_ab = float(np.linalg.norm(Za_ - Zb_) / np.linalg.norm(Zb_)); rel_ac = float(np.linalg.norm(Za_ - Zc_) / np.linalg.norm(Zc_))
+report(f"LargeVis x{world}: row-local vs scatter+all-reduce (rel {rel_ab:.2e}), vs single-GPU row-local (rel {rel_ac:.2e})", rel_ab < 1e-4 and rel_ac < 1e-4)
 
 # row-sharded dense SNE / sampled InfoTSNE vs the same fit on one GPU (short run, injected init)
 g0 = torch.Generator().manual_seed(3)

@@ -606,14 +606,17 @@ def test_largevis_row_local_step_equals_scatter_gradient(ops):
     n = 300
     Z = _cuda(t(g["Z0"])).clone()
     rowptr, col, val = ops.symmetrize_csr(P, I, 0, n, mode="sum")
-    # union graph: S = P + P^T exactly (dense check)
+    # union graph: S = P + P^T exactly, on the union of the edge sets (dense check; P may hold exact zeros)
     S = torch.zeros(n, n, device=DEV)
-    S[torch.arange(n, device=DEV).repeat_interleave(P.shape[1]), I.reshape(-1).long()] = P.reshape(-1)
-    S = S + S.T
+    M = torch.zeros(n, n, dtype=torch.bool, device=DEV)
+    ri = torch.arange(n, device=DEV).repeat_interleave(P.shape[1])
+    S[ri, I.reshape(-1).long()] = P.reshape(-1)
+    M[ri, I.reshape(-1).long()] = True
+    S, M = S + S.T, M | M.T
     cnt = (rowptr[1:] - rowptr[:-1]).long()
     rows = torch.repeat_interleave(torch.arange(n, device=DEV), cnt)
     torch.testing.assert_close(S[rows, col.long()], val, rtol=1e-7, atol=0)
-    assert int(cnt.sum()) == int((S != 0).sum())
+    assert int(cnt.sum()) == int(M.sum()) and bool(M[rows, col.long()].all())
     lr, mu = 75.0, 0.8
     Zc = Z.clone()
     momf = torch.zeros(n, 2, device=DEV)

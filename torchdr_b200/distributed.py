@@ -173,18 +173,28 @@ class PeerEmbedding:
 
     @classmethod
     def get(cls, Z0: torch.Tensor, group=None):
-        """Cached instance for this shape, loaded with ``Z0`` (collective: every rank calls it)."""
-        key = (tuple(Z0.shape), Z0.dtype, Z0.device, id(group) if group is not None else None)
+        """Instance for this shape, loaded with ``Z0`` (collective: every rank calls it).  The symmetric-memory
+        buffers are kept per (device, group) with their capacity and re-used by every later fit that fits in them."""
+        key = (Z0.dtype, Z0.device, id(group) if group is not None else None)
         peer = cls._cache.get(key)
-        if peer is None:
-            cls._cache.clear()  # one live embedding at a time: release the previous shape's buffers
-            peer = cls(Z0, group)
+        if peer is None or peer.capacity < Z0.numel():
+            cls._cache.pop(key, None)
+            peer = cls(Z0.numel(), Z0.dtype, Z0.device, group)
             cls._cache[key] = peer
-        else:
-            peer.load(Z0)
+        peer.load(Z0)
         return peer
 
-    def __init__(self, Z0: torch.Tensor, group=None):
+    @classmethod
+    def reserve(cls, n_points: int, device, q: int = 2, dtype=torch.float32, group=None):
+        """Allocate (once per process) exchange buffers for embeddings of up to ``n_points`` rows, so that the first
+        fit does not pay the symmetric-memory allocation + rendezvous (tens of milliseconds).  Collective."""
+        key = (dtype, torch.device(device), id(group) if group is not None else None)
+        peer = cls._cache.get(key)
+        if peer is None or peer.capacity < n_points * q:
+            cls._cache.pop(key, None)
+            cls._cache[key] = cls(n_points * q, dtype, torch.device(device), group)
+
+    def __init__(self, capacity: int, dtype, device, group=None):
         import torch.distributed._symmetric_memory as symm
 
         from . import ops
@@ -194,16 +204,18 @@ class PeerEmbedding:
         self.world = dist.get_world_size(group)
         if self.world > 9:
             raise RuntimeError("tdr_umap_run_p2p_f32 addresses at most 8 peers")
-        self.bufs, self.handles = [], []
+        self.capacity = int(capacity)
+        self._flat, self.handles = [], []
         for _ in range(2):
-            t = symm.empty(tuple(Z0.shape), dtype=Z0.dtype, device=Z0.device)
+            t = symm.empty((self.capacity,), dtype=dtype, device=device)
             self.handles.append(symm.rendezvous(t, group))
-            self.bufs.append(t)
+            self._flat.append(t)
+        self.bufs = list(self._flat)
         # peer-mapped flag words of the in-kernel exchange barrier: one uint32 per rank
-        self.flags = symm.empty((64,), dtype=torch.int32, device=Z0.device)
+        self.flags = symm.empty((64,), dtype=torch.int32, device=device)
         self.flags.zero_()
         self.flag_handle = symm.rendezvous(self.flags, group)
-        self.sync = ops.RunSync(Z0.device)
+        self.sync = ops.RunSync(device)
         import ctypes
 
         def arr(ptrs):
@@ -211,9 +223,12 @@ class PeerEmbedding:
 
         self.ptr_arrays = (arr(self.peer_ptrs(0)), arr(self.peer_ptrs(1)))
         self.flag_ptr_array = arr([int(p) for r, p in enumerate(self.flag_handle.buffer_ptrs) if r != self.rank])
-        self.load(Z0)
+        torch.cuda.synchronize(device)
+        self.handles[0].barrier(channel=0)  # flags are zero everywhere before anyone announces an epoch
 
     def load(self, Z0: torch.Tensor):
+        n = Z0.numel()
+        self.bufs = [f[:n].view(Z0.shape) for f in self._flat]  # views at offset 0: the peers' base addresses apply
         self.bufs[0].copy_(Z0)
         self.bufs[1].copy_(Z0)
         # no rank may start storing into its peers before every peer has loaded its buffers
