@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
     assert sorted(_lib.SIGNATURES) == names  # the ctypes table binds exactly the header
-    assert _lib.load().tdr_abi_version() == 1
+    assert _lib.load().tdr_abi_version() == 2
 
 
 def test_shared_library_is_sm100a_native():

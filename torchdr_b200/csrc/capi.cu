@@ -13,7 +13,7 @@ void set_error(const char* fmt, ...) {
 }
 }  // namespace tdr
 
-extern "C" TDR_API int tdr_abi_version(void) { return 1; }
+extern "C" TDR_API int tdr_abi_version(void) { return 2; }  // 2: per-call kNN options, persistent run entry points, row-local LargeVis step
 
 extern "C" TDR_API const char* tdr_last_error(void) { return tdr::g_err; }
 

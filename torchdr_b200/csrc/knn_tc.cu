@@ -43,6 +43,7 @@ constexpr size_t SMEM_LIMIT = 227 * 1024;
 constexpr size_t SMEM_MISC = 512 + 1024;    // barriers + TMEM slot, 1024-byte alignment slack
 constexpr int MAX_K = 96;                   // top-k lists in shared memory next to the operand tiles
 constexpr int kMaxEpl = MAX_K / 32;
+constexpr int kMaxUnion = 2 * MAX_K / 32;  // entries per lane of the union of two lists
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -186,29 +187,13 @@ __device__ __forceinline__ int lds_s32(uint32_t a) {
 __device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts_s32(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
-// Sorted insert into a thread-private list in shared memory (shared-space addresses); equal
-// distances keep index order because columns arrive in ascending index.  Rare (~k ln(N/k) calls
-// per row per sweep): kept out of line so the filter loop stays small.
-__device__ __noinline__ float list_insert(uint32_t my_d, uint32_t my_i, int k, float dist, int col) {
-    int p = k - 1;
-    while (p > 0) {
-        const float v = lds_f32(my_d + 4u * (uint32_t)(p - 1));
-        if (!(v > dist)) break;
-        sts_f32(my_d + 4u * (uint32_t)p, v);
-        sts_s32(my_i + 4u * (uint32_t)p, lds_s32(my_i + 4u * (uint32_t)(p - 1)));
-        --p;
-    }
-    sts_f32(my_d + 4u * (uint32_t)p, dist);
-    sts_s32(my_i + 4u * (uint32_t)p, col);
-    return lds_f32(my_d + 4u * (uint32_t)(k - 1));
-}
-
-// Unsorted variant for short lists (k <= 32).  While the list is not full a candidate is appended (two stores);
-// once it is full the candidate overwrites the current worst entry (position amax) and one pass over the list
-// finds the new worst by (distance, index).  The loads of that pass are independent, whereas the sorted insert
-// above walks a chain of dependent shared-memory round trips (~750 cycles per call at k = 15): in the pruned
-// sweep, where every tile is a near one, the inserts are what the epilogue spends its time on.
-// Returns (worst distance bits | its position << 32).  The list is rank-sorted once after the sweep.
+// Per-row candidate lists are kept UNSORTED in shared memory during the sweep.  While the list is not full a
+// candidate is appended (two stores); once it is full the candidate overwrites the current worst entry (position
+// amax) and one pass over the list finds the new worst by (distance, index).  The loads of that pass are
+// independent, whereas a sorted insert walks a chain of dependent shared-memory round trips (~750 cycles per call at
+// k = 15, ~4500 at k = 90 — round 1 measured the k = 90 search of t-SNE / LargeVis at 28x the k = 15 one): in the
+// pruned sweep, where every tile is a near one, the inserts are what the epilogue spends its time on.
+// Returns (worst distance bits | its position << 32).  The lists are rank-sorted once after the sweep.
 __device__ __noinline__ unsigned long long list_scan_max(uint32_t my_d, uint32_t my_i, int k) {
     float m = -INFINITY;
     int mi = -1, mp = 0;
@@ -233,7 +218,7 @@ struct Params {
     const int* absmax_bits;
     int k, kpad, atoms, stages;
     int exclude_self, metric, fused, max_iter;
-    int unsorted;  // 1: lists are kept unsorted during the sweep (list_replace; k <= 32) and rank-sorted at the end
+    int minima_a;  // phase A keeps 32 running minima per thread instead of lists (k <= 32, see below)
     int dual;   // 1: two epilogue warpgroups (384 threads), each with its own top-k lists, on alternate tiles
     int debug;  // timing experiments only (env TDR_TC_DEBUG): 1 = skip filter, 2 = skip MMAs, 4 = skip database TMA
     // tile-pruned sweep (see the "pruned sweep" section below): which database tiles this CTA visits
@@ -433,8 +418,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
             if (sd < INFINITY)
                 tau = sd >= 0.0f ? __uint_as_float(__float_as_uint(sd + 0.0f) + 1u) : __uint_as_float(__float_as_uint(sd) - 1u);
         }
-        int amax = 0, cnt = 0;  // unsorted mode: position of the list's worst entry, filled slots
-        const bool unsorted = prm.unsorted != 0;
+        int amax = 0, cnt = 0;  // position of the list's worst entry, filled slots
         const uint32_t lane_addr = (uint32_t)(((warp - 4) & 3) * 32) << 16;
 
         auto filter = [&](uint32_t(&big)[32], uint32_t(&small)[32], int col_base) {
@@ -461,17 +445,13 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                 for (int j = 0; j < 32; ++j) {
                     const float dist = __uint_as_float(big[j]);
                     if (dist < tau && (int64_t)(col_base + j) != self) {
-                        if (unsorted) {
-                            const int slot = cnt < k ? cnt : amax;
-                            sts_f32(my_d + 4u * (uint32_t)slot, dist);
-                            sts_s32(my_i + 4u * (uint32_t)slot, col_base + j);
-                            if (++cnt >= k) {
-                                const unsigned long long r = list_scan_max(my_d, my_i, k);
-                                tau = fminf(tau, __uint_as_float((uint32_t)r));
-                                amax = (int)(r >> 32);
-                            }
-                        } else {
-                            tau = fminf(tau, list_insert(my_d, my_i, k, dist, col_base + j));
+                        const int slot = cnt < k ? cnt : amax;
+                        sts_f32(my_d + 4u * (uint32_t)slot, dist);
+                        sts_s32(my_i + 4u * (uint32_t)slot, col_base + j);
+                        if (++cnt >= k) {
+                            const unsigned long long r = list_scan_max(my_d, my_i, k);
+                            tau = fminf(tau, __uint_as_float((uint32_t)r));
+                            amax = (int)(r >> 32);
                         }
                     }
                 }
@@ -531,7 +511,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                 tc_fence_before();
                 mbar_arrive(BAR(T_EMPTY + as));
             }
-        } else if (prm.kth_out && unsorted) {
+        } else if (prm.kth_out && prm.minima_a) {
             // ---- phase A of the pruned sweep, k <= 32: no lists.  gm[j] = smallest distance among the columns this
             // thread sees at chunk position j; the row's 32 (x 2 warpgroups) minima belong to disjoint column sets,
             // so their k-th smallest bounds the k-th neighbour distance (k columns at most that far) — and it is
@@ -633,7 +613,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
         if (gr >= prm.nq) continue;
         float* ldr = ld_s + row * kpad;
         int* lir = li_s + row * kpad;
-        if (prm.kth_out && prm.unsorted) {
+        if (prm.kth_out && prm.minima_a) {
             // phase A, k <= 32: k-th smallest of the row's nl * 32 group minima (ranked by (value, group id))
             const float* scratch = reinterpret_cast<const float*>(b_tiles);
             float v[2];
@@ -651,73 +631,40 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                 if (e < nl && rk[e] == k - 1) prm.kth_out[gr] = v[e];
             continue;
         }
-        if (prm.unsorted) {
-            // rank-sort the union of the row's (unsorted) lists by (distance, index) into list 0; k <= 32, so the
-            // union has at most 64 entries = 2 per lane.  Unused slots are (+inf, INT_MAX) and rank last.
+        {
+            // rank-sort the union of the row's (unsorted) lists by (distance, index) into list 0: at most
+            // 2 x 96 = 192 entries = kMaxUnion per lane.  Unused slots are (+inf, INT_MAX) and rank last.
             const int total = nl * k;
-            float dv[2];
-            int iv[2], rk[2];
+            const int epl = (total + 31) >> 5;
+            float dv[kMaxUnion];
+            int iv[kMaxUnion], rk[kMaxUnion];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
+            for (int e = 0; e < kMaxUnion; ++e) {
                 const int q = lane + 32 * e;  // entry q: list q / k, slot q % k
-                const bool ok = q < total;
+                const bool ok = e < epl && q < total;
                 const int li = ok ? q / k : 0, sl = ok ? q - li * k : 0;
                 dv[e] = ok ? ld_s[(li * BM + row) * kpad + sl] : INFINITY;
                 iv[e] = ok ? li_s[(li * BM + row) * kpad + sl] : 0x7fffffff;
                 rk[e] = 0;
             }
-            for (int q = 0; q < total; ++q) {
-                const int li = q / k, sl = q - li * k;
-                const float x = ld_s[(li * BM + row) * kpad + sl];
-                const int y = li_s[(li * BM + row) * kpad + sl];
+            for (int li = 0; li < nl; ++li) {
+                const float* xs = ld_s + (li * BM + row) * kpad;
+                const int* ys = li_s + (li * BM + row) * kpad;
+                for (int sl = 0; sl < k; ++sl) {
+                    const float x = xs[sl];
+                    const int y = ys[sl];
 #pragma unroll
-                for (int e = 0; e < 2; ++e) rk[e] += (x < dv[e] || (x == dv[e] && y < iv[e])) ? 1 : 0;
+                    for (int e = 0; e < kMaxUnion; ++e)
+                        if (e < epl) rk[e] += (x < dv[e] || (x == dv[e] && y < iv[e])) ? 1 : 0;
+                }
             }
             __syncwarp();
 #pragma unroll
-            for (int e = 0; e < 2; ++e)
-                if (lane + 32 * e < total && rk[e] < k) {
+            for (int e = 0; e < kMaxUnion; ++e)
+                if (e < epl && lane + 32 * e < total && rk[e] < k) {
                     ldr[rk[e]] = dv[e];
                     lir[rk[e]] = iv[e];
                 }
-            __syncwarp();
-        } else if (nl == 2) {
-            // merge the two sorted lists of the row (disjoint index sets) by (distance, index) into list 0
-            const float* ldb = ld_s + (BM + row) * kpad;
-            const int* lib = li_s + (BM + row) * kpad;
-            float da[kMaxEpl], db[kMaxEpl];
-            int ia[kMaxEpl], ib[kMaxEpl], ra[kMaxEpl], rb[kMaxEpl];
-#pragma unroll
-            for (int e = 0; e < kMaxEpl; ++e) {
-                const int p = lane + 32 * e;
-                da[e] = p < k ? ldr[p] : INFINITY;
-                db[e] = p < k ? ldb[p] : INFINITY;
-                ia[e] = p < k ? lir[p] : 0x7fffffff;
-                ib[e] = p < k ? lib[p] : 0x7fffffff;
-                ra[e] = rb[e] = p;
-            }
-            for (int j = 0; j < k; ++j) {
-                const float xb = ldb[j], xa = ldr[j];
-                const int yb = lib[j], ya = lir[j];
-#pragma unroll
-                for (int e = 0; e < kMaxEpl; ++e) {
-                    ra[e] += (xb < da[e] || (xb == da[e] && yb < ia[e])) ? 1 : 0;
-                    rb[e] += (xa < db[e] || (xa == db[e] && ya < ib[e])) ? 1 : 0;
-                }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int e = 0; e < kMaxEpl; ++e) {
-                const int p = lane + 32 * e;
-                if (p < k && ra[e] < k) {
-                    ldr[ra[e]] = da[e];
-                    lir[ra[e]] = ia[e];
-                }
-                if (p < k && rb[e] < k) {
-                    ldr[rb[e]] = db[e];
-                    lir[rb[e]] = ib[e];
-                }
-            }
             __syncwarp();
         }
         if (prm.kth_out) {  // phase A of the pruned sweep: the row's bound, nothing else
@@ -1161,10 +1108,7 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
     prm.P = P;
     prm.rho = rho;
     prm.sigma = sigma;
-    {
-        const char* us = getenv("TDR_TC_UNSORTED");
-        prm.unsorted = (k <= 32 && !(us && atoi(us) == 0)) ? 1 : 0;
-    }
+    prm.minima_a = k <= 32 ? 1 : 0;
     int stages = 0;
     size_t smem = 0;
     if (!tc_smem_plan(d, k, false, &prm.dual, &stages, &smem)) {
