@@ -317,6 +317,23 @@ def gpu_arm(args):
     s, e = bounds[rank]
     parity_knn = knn_parity_sample(X, knn_idx, s, K_NEIGHBORS) if not args.no_parity else None
     del knn_idx
+    # the same stage on rows WITHOUT index locality (the generator's order shuffled), through the product path of
+    # UMAPAffinity: locality probe -> Voronoi-tree order -> certified pruned sweep -> rows / neighbour ids mapped back
+    shuffled = None
+    if world == 1 and not args.no_shuffled:
+        from torchdr_b200 import UMAPAffinity
+
+        Xs = X[torch.randperm(n, generator=torch.Generator(device=dev).manual_seed(7), device=dev)].contiguous()
+        aff = UMAPAffinity(n_neighbors=K_NEIGHBORS, max_iter=100, symmetrize=False, knn_order="auto")
+        aff.compute_csr(Xs[:max(20000, n // 50)])  # warm-up (module loading of the ordering kernels)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        aff.compute_csr(Xs)
+        torch.cuda.synchronize()
+        shuffled = {"ms": 1e3 * (time.perf_counter() - t0),
+                    "note": "UMAPAffinity(knn_order='auto') kNN + sigma/rho on the shuffled rows: locality probe, Voronoi-tree "
+                            "order, certified pruned sweep (bit-identical to the full sweep), map-back to the input order"}
+        del Xs, aff
     a, b = find_ab_params(1.0, 0.1)
     g = torch.Generator(device=dev).manual_seed(0)
     Z = torch.randn(n, 2, generator=g, device=dev)
@@ -440,6 +457,7 @@ def gpu_arm(args):
                           "tile-pruned sweep)",
                 "ms": knn["ms"], "algorithmic_bytes": aff_bytes, "gbs": aff_bytes / (knn["ms"] * 1e-3) / 1e9,
                 "tile_pairs_swept": knn["tile_pairs_swept"], "tile_pairs_all": knn["tile_pairs_all"],
+                "shuffled_rows": shuffled,
                 "full_sweep_ms": full_ms, "full_sweep_measured_on_rows": knn["full_rows"],
                 "full_sweep_gbs": aff_bytes / (full_ms * 1e-3) / 1e9, "full_sweep_tflops_2nnd": tf_equiv,
                 "full_sweep_tensor_tflops_3pass": 3.0 * tf_equiv,
@@ -530,10 +548,32 @@ def e2e_arm(args, dev, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     assert Z.shape == (n, 2) and np.isfinite(Z).all()
+    e2e_shuffled = None
+    if args.order == "generator" and not args.no_shuffled:
+        # the same fit on the same points in shuffled row order (no index locality: the fit runs in a tree order)
+        Xd = clustered(n, d, dev)
+        Xs = Xd[torch.randperm(n, generator=torch.Generator(device=dev).manual_seed(7), device=dev)].cpu().pin_memory().numpy()
+        del Xd
+        m.fit_transform(Xs[:max(20000, n // 50)])
+        _sync_all(world)
+        t0 = time.perf_counter()
+        Z2 = m.fit_transform(Xs)
+        torch.cuda.synchronize()
+        dt2 = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt2], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt2 = float(t.item())
+        assert Z2.shape == (n, 2) and np.isfinite(Z2).all()
+        e2e_shuffled = {"value": E2E_ITERS / dt2, "unit": "iters/s", "seconds": dt2,
+                        "note": "same fit, rows shuffled: locality probe + Voronoi-tree order + certified sweep, whole fit in "
+                                "the tree order, permutation undone on the embedding"}
+        del Xs, Z2
     h2d = Xh.nbytes / world  # per rank: its own row chunk crosses PCIe, the rest arrives over NVLink
     return {"value": E2E_ITERS / dt, "unit": "iters/s", "h2d_bytes_per_step": h2d / E2E_ITERS,
             "d2h_bytes_per_step": Z.nbytes / E2E_ITERS, "seconds": dt, "iters": E2E_ITERS,
             "exchange": getattr(m, "exchange_", None), "stages_seconds_rank0_instrumented_refit": stages,
+            "shuffled_rows": e2e_shuffled,
             "note": "UMAP(n_neighbors=15, max_iter=500, init='normal').fit_transform(numpy X): iters / wall time (max over "
                     "ranks) incl. H2D, exact kNN, sigma search, symmetrise, loop, D2H; h2d bytes are per rank"}
 
@@ -859,6 +899,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-shuffled", action="store_true", help="skip the shuffled-row-order legs (affinity stage, e2e)")
     ap.add_argument("--e2e-stages", action="store_true", help="add a second, instrumented fit that reports stage seconds")
     ap.add_argument("--full-sweep-rows", type=int, default=65536,
                     help="query rows on which the unpruned kNN sweep is timed (scaled to the rank's rows)")

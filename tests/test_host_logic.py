@@ -303,6 +303,60 @@ def test_umap_loop_bookkeeping_without_a_gpu(monkeypatch):
     assert [(c[0], len(c[1])) for c in calls] == [(0, 1), (1, 25), (26, 25), (51, 24)]
 
 
+def test_umap_early_exaggeration_switch_without_a_gpu(monkeypatch):
+    """UMAP(early_exaggeration_coeff > 1, early_exaggeration_iter = k), accepted through **kwargs as in the reference:
+    iterations 0..k run with lambda = coeff, then the coefficient drops to 1 and optimiser + scheduler are rebuilt
+    (NE base.py:282-295) — the batch is split at k and the learning-rate sequence restarts from the new scheduler."""
+    from torchdr_b200 import neighbor_embedding as ne
+    from torchdr_b200 import ops
+
+    calls = []
+
+    def fake_run(Za, Zb, rowptr, col, eps, eons, n_iter0, lrs, a, b, gnorm_sq=None, lam=1.0, **kw):
+        calls.append((int(n_iter0), len(lrs), float(lam), [float(x) for x in lrs]))
+        if gnorm_sq is not None:
+            gnorm_sq.fill_(1.0)
+        return Za if len(lrs) % 2 == 0 else Zb
+
+    monkeypatch.setattr(ops, "umap_run", fake_run)
+    m = ne.UMAP(n_neighbors=5, max_iter=40, check_interval=10, a=1.5, b=0.9, random_state=0, distributed=False,
+                early_exaggeration_coeff=4.0, early_exaggeration_iter=13)
+    m.n_samples_in_, m.chunk_start_, m.chunk_end_ = 8, 0, 8
+    m.early_exaggeration_coeff_ = m.early_exaggeration_coeff
+    m._native_opt = m._uses_native_sgd()
+    m._graph = (torch.zeros(9, dtype=torch.long), torch.zeros(0, dtype=torch.int32), torch.zeros(0), torch.zeros(0))
+    m.embedding_ = torch.zeros(8, 2)
+    m._gnorm, m._nan = torch.zeros(1, dtype=torch.float64), torch.zeros(1, dtype=torch.int32)
+    m._dummy = torch.nn.Parameter(torch.zeros(1))
+    m.params_ = [{"params": [m._dummy]}]
+    m._set_learning_rate()
+    m._configure_optimizer()
+    m._configure_scheduler()
+    m._loop()
+    assert [(c[0], c[1], c[2]) for c in calls] == [(0, 1, 4.0), (1, 10, 4.0), (11, 3, 4.0), (14, 7, 1.0), (21, 10, 1.0),
+                                                   (31, 9, 1.0)]
+    lrs = [x for c in calls for x in c[3]]
+    # the reference's own objects, rebuilt the reference's way (ONE params_ dict reused by the rebuild,
+    # affinity_matcher.py:588-590: torch keeps the group's current lr / initial_lr, so the new LinearLR continues from
+    # the lr reached at the switch instead of restarting at 1 — the quirk DESIGN.md section 1 documents)
+    dummy = torch.nn.Parameter(torch.zeros(1))
+    params = [{"params": [dummy]}]
+    kw = {"start_factor": torch.tensor(1.0), "end_factor": torch.tensor(0), "total_iters": 40}
+    opt = torch.optim.SGD(params, lr=1.0)
+    sch = torch.optim.lr_scheduler.LinearLR(opt, **kw)
+    expect = []
+    for t in range(40):
+        expect.append(float(opt.param_groups[0]["lr"]))
+        opt.step()
+        sch.step()
+        if t == 13:
+            opt = torch.optim.SGD(params, lr=1.0)
+            sch = torch.optim.lr_scheduler.LinearLR(opt, **kw)
+    np.testing.assert_allclose(lrs, expect, rtol=1e-6)
+    assert abs(lrs[14] - lrs[13] * (1 - 1 / 40) / 1.0) < 0.05 and lrs[14] < 0.7  # continues, does not restart at 1
+    assert m.early_exaggeration_coeff_ == 1 and m._last_step == 39
+
+
 def test_momentum_loop_bookkeeping_matches_reference_sequences(monkeypatch):
     """The gradient + momentum-SGD loop shared by LargeVis / TSNE / InfoTSNE / SNE with the two native calls replaced
     by recorders: the (lr, momentum, buffer-restart) triple handed to `tdr_sgd_momentum_f32` at every step must be the
