@@ -1099,10 +1099,7 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
     prm.metric = metric;
     prm.fused = fused;
     prm.max_iter = max_iter;
-    {
-        const char* dbg = getenv("TDR_TC_DEBUG");
-        prm.debug = dbg ? atoi(dbg) : 0;
-    }
+    prm.debug = 0;  // ablation bits (skip filter / MMAs / TMA), set by hand in timing experiments only
     prm.out_dist = out_dist;
     prm.out_idx = out_idx;
     prm.P = P;
