@@ -422,8 +422,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
         const uint32_t lane_addr = (uint32_t)(((warp - 4) & 3) * 32) << 16;
 
         auto filter = [&](uint32_t(&big)[32], uint32_t(&small)[32], int col_base) {
-            // minima of the four 8-column groups of the chunk (four independent chains)
-            float mg[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+            float m0 = INFINITY, m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;
 #pragma unroll
             for (int j4 = 0; j4 < 32; j4 += 4) {
                 const float4 nb = __ldg(reinterpret_cast<const float4*>(prm.dbn + col_base + j4));
@@ -436,29 +435,23 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                 big[j4 + 1] = __float_as_uint(d1);
                 big[j4 + 2] = __float_as_uint(d2);
                 big[j4 + 3] = __float_as_uint(d3);
-                mg[j4 >> 3] = fminf(mg[j4 >> 3], fminf(fminf(d0, d1), fminf(d2, d3)));
+                m0 = fminf(m0, d0);
+                m1 = fminf(m1, d1);
+                m2 = fminf(m2, d2);
+                m3 = fminf(m3, d3);
             }
-            // The per-element test runs only for 8-column groups that hold a candidate of THIS row: in the pruned sweep
-            // every tile is a near one and some lane of the warp has a candidate in almost every chunk, so an
-            // all-or-nothing 32-element scan would run (mostly idle) for the whole warp nearly every time.  Groups and
-            // columns are visited in ascending order: equal distances enter in index order.
-            if (fminf(fminf(mg[0], mg[1]), fminf(mg[2], mg[3])) < tau) {
+            if (fminf(fminf(m0, m1), fminf(m2, m3)) < tau) {
 #pragma unroll
-                for (int g8 = 0; g8 < 4; ++g8) {
-                    if (mg[g8] < tau) {
-#pragma unroll
-                        for (int j = 8 * g8; j < 8 * g8 + 8; ++j) {
-                            const float dist = __uint_as_float(big[j]);
-                            if (dist < tau && (int64_t)(col_base + j) != self) {
-                                const int slot = cnt < k ? cnt : amax;
-                                sts_f32(my_d + 4u * (uint32_t)slot, dist);
-                                sts_s32(my_i + 4u * (uint32_t)slot, col_base + j);
-                                if (++cnt >= k) {
-                                    const unsigned long long r = list_scan_max(my_d, my_i, k);
-                                    tau = fminf(tau, __uint_as_float((uint32_t)r));
-                                    amax = (int)(r >> 32);
-                                }
-                            }
+                for (int j = 0; j < 32; ++j) {
+                    const float dist = __uint_as_float(big[j]);
+                    if (dist < tau && (int64_t)(col_base + j) != self) {
+                        const int slot = cnt < k ? cnt : amax;
+                        sts_f32(my_d + 4u * (uint32_t)slot, dist);
+                        sts_s32(my_i + 4u * (uint32_t)slot, col_base + j);
+                        if (++cnt >= k) {
+                            const unsigned long long r = list_scan_max(my_d, my_i, k);
+                            tau = fminf(tau, __uint_as_float((uint32_t)r));
+                            amax = (int)(r >> 32);
                         }
                     }
                 }
