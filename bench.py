@@ -651,6 +651,18 @@ def largevis_arm(args):
     torch.cuda.synchronize()
     t_aff = time.perf_counter() - t0
     k = P.shape[1]
+    parity = None
+    if not args.no_parity:
+        # untimed checkers at the bench size: sampled fp64 kNN (k = 90) and the eps of the same rows against the oracle
+        import oracle
+
+        parity = {"knn_sampled_rows_fp64": knn_parity_sample(X, idx, s, k)}
+        C_knn = aff.knn_[0]
+        pick = torch.randperm(e - s, generator=torch.Generator().manual_seed(3))[:256]
+        _, eps_ref, _ = oracle.entropic_affinity_rows(C_knn[pick.to(dev)].cpu(), LV_PERPLEXITY, n_total=n, use_bounds=False)
+        rel = float(((aff.eps_[pick.to(dev)].cpu() - eps_ref).abs() / eps_ref.abs()).max())
+        parity["eps_sampled_rows_vs_oracle"] = {"rows_checked": 256, "max_rel_err": rel, "tolerance": 1e-4,
+                                                "note": "same kNN distances through oracle/affinity.py (entropic.py:272-310), bracket from 1"}
     # union graph S = P + P^T of the local rows (one edge exchange when sharded), as LargeVis._compute_affinity builds it
     t0 = time.perf_counter()
     ext = None
@@ -777,7 +789,7 @@ def largevis_arm(args):
             "reference_formulation_ms_per_iteration": dict({k_: v / 5 for k_, v in parts.items()}, total=scatter_ms,
                                                            note="scatter kernel (fp32 atomics) -> NCCL all-reduce of N x 2 -> SGD on all "
                                                                 "rows, affinity_matcher.py:418-425; same engine, measured after the timed blocks"),
-            "affinity_seconds": t_aff, "union_graph_seconds": t_graph,
+            "affinity_seconds": t_aff, "union_graph_seconds": t_graph, "parity": parity,
             "roofline": {"bound": "hbm", "kernel": "tdr::largevis_pull_update_kernel (+ largevis_push_kernel)",
                          "achieved": alg / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg / (ms_per_step * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes_per_launch": alg,
@@ -930,7 +942,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps, warm = min(args.steps, 20), min(max(args.warmup, 1), 3)
+        steps, warm = min(args.steps, 50), min(max(args.warmup, 1), 10)  # as asked (bounded: ~60 ms per CPU step at 50 k points)
         r = cpu_reference(steps, warm, args.points, args.dim)
         line = {
             "impl": "reference", "metric": metric,
@@ -938,7 +950,8 @@ def main():
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "value_measured": r["value_measured"], "ms_per_step_measured": r["ms_per_step_measured"],
-            "config": {"workload": workload, "points": args.points, "dim": args.dim,
+            "config": {"workload": workload, "points": args.points, "dim": args.dim, "row_order": args.order,
+                       "n_negatives": N_NEG, "schedule_max_iter": MAX_ITER,
                        "note": f"`value` / `ms_per_step` are EXTRAPOLATED from a measured {r['sample_points']}-point sample to "
                                f"{args.points} points (the real backend=None path cannot allocate N x N beyond ~50 k rows); "
                                "`value_measured` / `ms_per_step_measured` are the sample's own and are what fits this run's "
