@@ -3,7 +3,7 @@
 set -u
 O=gpurun_out; mkdir -p $O
 echo "== [1] ncu --set full, knn_tc_kernel phase B at 10M"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:knn_tc_kernel --launch-skip 2 -c 1 -f -o $O/r2_knn_phaseB_10m \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:knn_tc_kernel --launch-skip 1 -c 1 -f -o $O/r2_knn_phaseB_10m \
     python scripts/knn_time.py 10000000 128 15 generator > $O/ncu_knn.log 2>&1
 ncu -i $O/r2_knn_phaseB_10m.ncu-rep --page raw --csv > $O/r2_knn_phaseB_10m_raw.csv 2>/dev/null
 python - <<'PY'
@@ -30,7 +30,3 @@ print("stall samples", tot, "warp inst", sum(int(r[ix["Instructions Executed"]] 
 for r in sorted(data, key=lambda r: -int(r[ix["# Samples"]] or 0))[:14]:
     print(f'{100.0 * int(r[ix["# Samples"]]) / tot:5.1f} %  {int(r[ix["Instructions Executed"]]):>11}  {r[ix["Source"]].strip()[:90]}')
 PY
-echo "== [2] c4 at N=1 on the final kNN kernel"
-timeout 900 python bench.py --config c4 --steps 10 --no-cpu > $O/r2_c4_n1.json 2> $O/r2_c4_n1.err; tail -2 $O/r2_c4_n1.err
-python -c "
-import json; d=json.loads(open('gpurun_out/r2_c4_n1.json').read()); print('c4 n1: value', round(d['value'],2), 'ms/step', round(d['ms_per_step'],3), 'e2e', d['e2e']['seconds'], 'aff s', d['affinity_seconds'], d['union_graph_seconds'])"

@@ -70,6 +70,25 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// Producer / MMA-issuer flavour: these single threads share their SM sub-partition with epilogue warps; a hot
+// try_wait loop would take issue slots from them (ncu on the pruned sweep: 22 % of all executed instructions were
+// these polls), so failed polls back off for a few nanoseconds.
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        __nanosleep(32);
+    }
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
@@ -174,18 +193,22 @@ __global__ void __launch_bounds__(256) sqnorm_pad_kernel(const float* __restrict
     if (lane == 0) out[row] = (float)s;
 }
 
-__device__ __forceinline__ float lds_f32(uint32_t a) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t a) {
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
     return v;
 }
-__device__ __forceinline__ int lds_s32(uint32_t a) {
-    int v;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
+__device__ __forceinline__ void sts_u64(uint32_t a, unsigned long long v) {
+    asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
 }
-__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
-__device__ __forceinline__ void sts_s32(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// List entries are 64-bit keys  (order-preserving image of the fp32 distance) << 32 | column index : one unsigned
+// compare orders entries by (distance, index) — the tie rule of every kernel of this engine.
+__device__ __forceinline__ uint32_t ord_f32(float f) {
+    const uint32_t b = __float_as_uint(f + 0.0f);  // -0 -> +0
+    return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float unord_f32(uint32_t u) { return __uint_as_float(u ^ (((u >> 31) - 1u) | 0x80000000u)); }
+constexpr unsigned long long kEmptyKey = ~0ull;  // sorts after every real entry
 
 // Per-row candidate lists are kept UNSORTED in shared memory during the sweep.  While the list is not full a
 // candidate is appended (two stores); once it is full the candidate overwrites the current worst entry (position
@@ -193,20 +216,18 @@ __device__ __forceinline__ void sts_s32(uint32_t a, int v) { asm volatile("st.sh
 // independent, whereas a sorted insert walks a chain of dependent shared-memory round trips (~750 cycles per call at
 // k = 15, ~4500 at k = 90 — round 1 measured the k = 90 search of t-SNE / LargeVis at 28x the k = 15 one): in the
 // pruned sweep, where every tile is a near one, the inserts are what the epilogue spends its time on.
-// Returns (worst distance bits | its position << 32).  The lists are rank-sorted once after the sweep.
-__device__ __noinline__ unsigned long long list_scan_max(uint32_t my_d, uint32_t my_i, int k) {
-    float m = -INFINITY;
-    int mi = -1, mp = 0;
+// Returns (ordered image of the worst distance << 32 | its position).  The lists are rank-sorted once after the sweep.
+__device__ __noinline__ unsigned long long list_scan_max(uint32_t my_k, int k) {
+    unsigned long long m = 0ull;
+    int mp = 0;
 #pragma unroll 4
     for (int p = 0; p < k; ++p) {
-        const float v = lds_f32(my_d + 4u * (uint32_t)p);
-        const int i = lds_s32(my_i + 4u * (uint32_t)p);
-        const bool gt = v > m || (v == m && i > mi);
+        const unsigned long long v = lds_u64(my_k + 8u * (uint32_t)p);
+        const bool gt = v > m;
         m = gt ? v : m;
-        mi = gt ? i : mi;
         mp = gt ? p : mp;
     }
-    return (unsigned long long)__float_as_uint(m) | ((unsigned long long)(uint32_t)mp << 32);
+    return (m & 0xffffffff00000000ull) | (unsigned long long)(uint32_t)mp;
 }
 
 // ------------------------------------------------------------------ main kernel
@@ -260,9 +281,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
     unsigned char* b_tiles = smem + a_bytes;          // [stages][hi, lo][16 KB]: one atom of a database tile per stage
     const int nl = 1 + prm.dual;  // list sets (epilogue warpgroups)
     const int n_lists = prm.c_full ? 0 : nl;
-    float* ld_s = reinterpret_cast<float*>(b_tiles + (size_t)stages * STAGE_BYTES);  // [n_lists][128][kpad]
-    int* li_s = reinterpret_cast<int*>(ld_s + n_lists * BM * kpad);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(li_s + n_lists * BM * kpad);
+    unsigned long long* lk_s = reinterpret_cast<unsigned long long*>(b_tiles + (size_t)stages * STAGE_BYTES);  // [n_lists][128][kpad] keys
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lk_s + n_lists * BM * kpad);
     // barrier slots: 0 a_full | 1..S full | 1+S..2S empty | 2S+1, 2S+2 tmem_full | 2S+3, 2S+4 tmem_empty
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 5);
 
@@ -318,8 +338,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     for (int i = tid; i < n_lists * BM * kpad; i += (int)blockDim.x) {
-        ld_s[i] = INFINITY;
-        li_s[i] = 0x7fffffff;
+        lk_s[i] = kEmptyKey;
     }
     tc_fence_before();
     __syncthreads();
@@ -342,7 +361,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                 for (int a = 0; a < atoms; ++a, ++c) {
                     const int s = (int)(c % stages);
                     const uint32_t ph = (uint32_t)((c / stages) & 1);
-                    mbar_wait(BAR(B_EMPTY + s), ph ^ 1u);
+                    mbar_wait_backoff(BAR(B_EMPTY + s), ph ^ 1u);
                     if ((prm.debug & 4) && c >= stages) {
                         mbar_arrive(BAR(B_FULL + s));
                         continue;
@@ -362,13 +381,13 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
             for (int64_t t = 0; t < n_sweep; ++t) {
                 const int as = (int)(t & 1);
                 const uint32_t aph = (uint32_t)((t >> 1) & 1);
-                mbar_wait(BAR(T_EMPTY + as), aph ^ 1u);
+                mbar_wait_backoff(BAR(T_EMPTY + as), aph ^ 1u);
                 const uint32_t d_big = tmem_base + (uint32_t)(as * 256);
                 const uint32_t d_small = d_big + 128u;
                 for (int a = 0; a < atoms; ++a, ++c) {
                     const int s = (int)(c % stages);
                     const uint32_t ph = (uint32_t)((c / stages) & 1);
-                    mbar_wait(BAR(B_FULL + s), ph);
+                    mbar_wait_backoff(BAR(B_FULL + s), ph);
                     tc_fence_after();
                     if (!(prm.debug & 2)) {
                         const unsigned char* bt = b_tiles + (size_t)s * STAGE_BYTES;
@@ -408,7 +427,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
         const float qn = gq < prm.nq ? __ldg(prm.qn + gq) : 0.0f;
         const int e = scale_exponent(__int_as_float(__ldg(prm.absmax_bits)));
         const float neg2s = -2.0f * ldexpf(1.0f, -2 * e);  // power of two: the FFMA below rounds once, like sub(add, 2*dot)
-        const uint32_t my_d = smem_u32(ld_s + (wg * BM + row) * kpad), my_i = smem_u32(li_s + (wg * BM + row) * kpad);
+        const uint32_t my_k = smem_u32(lk_s + (wg * BM + row) * kpad);
         // Threshold of the row.  Phase B of the pruned sweep starts it one ulp above the bound of phase A (so the
         // strict test below admits every candidate <= bound); the lists start empty either way, and since at least
         // k candidates of the swept tiles lie within the bound the union of the row's lists fills up.
@@ -446,12 +465,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                     const float dist = __uint_as_float(big[j]);
                     if (dist < tau && (int64_t)(col_base + j) != self) {
                         const int slot = cnt < k ? cnt : amax;
-                        sts_f32(my_d + 4u * (uint32_t)slot, dist);
-                        sts_s32(my_i + 4u * (uint32_t)slot, col_base + j);
+                        sts_u64(my_k + 8u * (uint32_t)slot,
+                                ((unsigned long long)ord_f32(dist) << 32) | (unsigned long long)(uint32_t)(col_base + j));
                         if (++cnt >= k) {
-                            const unsigned long long r = list_scan_max(my_d, my_i, k);
-                            tau = fminf(tau, __uint_as_float((uint32_t)r));
-                            amax = (int)(r >> 32);
+                            const unsigned long long r = list_scan_max(my_k, k);
+                            tau = fminf(tau, unord_f32((uint32_t)(r >> 32)));
+                            amax = (int)(uint32_t)r;
                         }
                     }
                 }
@@ -611,8 +630,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
     for (int row = warp; row < (prm.c_full ? 0 : BM); row += n_warps) {
         const int64_t gr = q0 + row;
         if (gr >= prm.nq) continue;
-        float* ldr = ld_s + row * kpad;
-        int* lir = li_s + row * kpad;
+        // the row's storage in list 0: keys during the sweep, (fp32 distances | int32 indices), sorted, after the rank sort
+        float* ldr = reinterpret_cast<float*>(lk_s + row * kpad);
+        int* lir = reinterpret_cast<int*>(ldr + kpad);
         if (prm.kth_out && prm.minima_a) {
             // phase A, k <= 32: k-th smallest of the row's nl * 32 group minima (ranked by (value, group id))
             const float* scratch = reinterpret_cast<const float*>(b_tiles);
@@ -636,35 +656,43 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
             // 2 x 96 = 192 entries = kMaxUnion per lane.  Unused slots are (+inf, INT_MAX) and rank last.
             const int total = nl * k;
             const int epl = (total + 31) >> 5;
-            float dv[kMaxUnion];
-            int iv[kMaxUnion], rk[kMaxUnion];
+            unsigned long long kv[kMaxUnion];
+            int rk[kMaxUnion];
 #pragma unroll
             for (int e = 0; e < kMaxUnion; ++e) {
                 const int q = lane + 32 * e;  // entry q: list q / k, slot q % k
                 const bool ok = e < epl && q < total;
                 const int li = ok ? q / k : 0, sl = ok ? q - li * k : 0;
-                dv[e] = ok ? ld_s[(li * BM + row) * kpad + sl] : INFINITY;
-                iv[e] = ok ? li_s[(li * BM + row) * kpad + sl] : 0x7fffffff;
+                kv[e] = ok ? lk_s[(li * BM + row) * kpad + sl] : kEmptyKey;
                 rk[e] = 0;
             }
             for (int li = 0; li < nl; ++li) {
-                const float* xs = ld_s + (li * BM + row) * kpad;
-                const int* ys = li_s + (li * BM + row) * kpad;
+                const unsigned long long* xs = lk_s + (li * BM + row) * kpad;
                 for (int sl = 0; sl < k; ++sl) {
-                    const float x = xs[sl];
-                    const int y = ys[sl];
+                    const unsigned long long x = xs[sl];
 #pragma unroll
                     for (int e = 0; e < kMaxUnion; ++e)
-                        if (e < epl) rk[e] += (x < dv[e] || (x == dv[e] && y < iv[e])) ? 1 : 0;
+                        if (e < epl) rk[e] += (x < kv[e]) ? 1 : 0;  // keys are distinct (distinct columns) except empty slots
                 }
             }
-            __syncwarp();
+            __syncwarp();  // every entry of the row is in registers: its storage can change layout
 #pragma unroll
             for (int e = 0; e < kMaxUnion; ++e)
-                if (e < epl && lane + 32 * e < total && rk[e] < k) {
-                    ldr[rk[e]] = dv[e];
-                    lir[rk[e]] = iv[e];
+                if (e < epl && lane + 32 * e < total && rk[e] < k && kv[e] != kEmptyKey) {
+                    ldr[rk[e]] = unord_f32((uint32_t)(kv[e] >> 32));
+                    lir[rk[e]] = (int)(uint32_t)kv[e];
                 }
+            // slots that stay empty (fewer than k candidates: phase A windows) read as +inf
+            {
+                int filled = 0;
+#pragma unroll
+                for (int e = 0; e < kMaxUnion; ++e) filled += (e < epl && kv[e] != kEmptyKey) ? 1 : 0;
+                filled = warp_sum_int(filled);
+                for (int p = filled + lane; p < k; p += 32) {
+                    ldr[p] = INFINITY;
+                    lir[p] = 0x7fffffff;
+                }
+            }
             __syncwarp();
         }
         if (prm.kth_out) {  // phase A of the pruned sweep: the row's bound, nothing else
