@@ -70,25 +70,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-// Producer / MMA-issuer flavour: these single threads share their SM sub-partition with epilogue warps; a hot
-// try_wait loop would take issue slots from them (ncu on the pruned sweep: 22 % of all executed instructions were
-// these polls), so failed polls back off for a few nanoseconds.
-__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
-    for (;;) {
-        uint32_t done;
-        asm volatile(
-            "{\n"
-            ".reg .pred P1;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, P1;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) return;
-        __nanosleep(32);
-    }
-}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
@@ -361,7 +342,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                 for (int a = 0; a < atoms; ++a, ++c) {
                     const int s = (int)(c % stages);
                     const uint32_t ph = (uint32_t)((c / stages) & 1);
-                    mbar_wait_backoff(BAR(B_EMPTY + s), ph ^ 1u);
+                    mbar_wait(BAR(B_EMPTY + s), ph ^ 1u);
                     if ((prm.debug & 4) && c >= stages) {
                         mbar_arrive(BAR(B_FULL + s));
                         continue;
@@ -381,13 +362,13 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
             for (int64_t t = 0; t < n_sweep; ++t) {
                 const int as = (int)(t & 1);
                 const uint32_t aph = (uint32_t)((t >> 1) & 1);
-                mbar_wait_backoff(BAR(T_EMPTY + as), aph ^ 1u);
+                mbar_wait(BAR(T_EMPTY + as), aph ^ 1u);
                 const uint32_t d_big = tmem_base + (uint32_t)(as * 256);
                 const uint32_t d_small = d_big + 128u;
                 for (int a = 0; a < atoms; ++a, ++c) {
                     const int s = (int)(c % stages);
                     const uint32_t ph = (uint32_t)((c / stages) & 1);
-                    mbar_wait_backoff(BAR(B_FULL + s), ph);
+                    mbar_wait(BAR(B_FULL + s), ph);
                     tc_fence_after();
                     if (!(prm.debug & 2)) {
                         const unsigned char* bt = b_tiles + (size_t)s * STAGE_BYTES;
