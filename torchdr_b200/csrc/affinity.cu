@@ -33,6 +33,32 @@ umap_affinity_kernel(const float* __restrict__ C, int64_t n, int k, int max_iter
     }
 }
 
+// k <= 16: two rows per warp (a half warp each).  The search is a chain of ~35 dependent evaluations per row, issue-bound
+// (~100 warp instructions each); with 15 of 32 lanes busy a warp per row wasted half of them.  Same bits as the
+// warp-per-row kernel (rowsearch.cuh: group reductions).
+__global__ void __launch_bounds__(kRowsPerBlock * 32)
+umap_affinity_half_kernel(const float* __restrict__ C, int64_t n, int k, int max_iter, float target,
+                          float* __restrict__ P, float* __restrict__ rho, float* __restrict__ sigma) {
+    const int lane = threadIdx.x & 15;
+    const int half = (threadIdx.x >> 4) & 1;
+    const int64_t row = ((int64_t)blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5)) * 2 + half;
+    if (row >= n) return;  // whole half warp
+    UmapRow<1, 16> r;
+    r.k = k;
+    r.lane = lane;
+    r.target = target;
+    r.mask = half ? 0xffff0000u : 0x0000ffffu;
+    const float* crow = C + row * k;
+    r.c[0] = r.valid(0) ? __ldg(crow + lane) : INFINITY;
+    r.init();
+    const float s = r.solve(max_iter);
+    if (r.valid(0)) P[row * k + lane] = r.p(0, s);
+    if (lane == 0) {
+        rho[row] = r.rho;
+        sigma[row] = s;
+    }
+}
+
 template <int EPL>
 __global__ void __launch_bounds__(kRowsPerBlock * 32)
 entropic_affinity_kernel(const float* __restrict__ C, int64_t n, int k, int max_iter, EntropicConsts K,
@@ -246,6 +272,13 @@ extern "C" TDR_API int tdr_umap_affinity_f32(const float* C, int64_t n, int k, i
     TDR_CHECK_ARG(n < ((int64_t)1 << 31) * kRowsPerBlock, "tdr_umap_affinity_f32: n too large");
     if (n == 0) return TDR_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (k <= 16) {
+        const int64_t blocks = (n + 2 * kRowsPerBlock - 1) / (2 * kRowsPerBlock);
+        umap_affinity_half_kernel<<<(unsigned)blocks, kRowsPerBlock * 32, 0, st>>>(C, n, k, max_iter, log2f((float)k), P,
+                                                                                 rho, sigma);
+        TDR_LAUNCH_CHECK();
+        return TDR_OK;
+    }
     switch ((k + 31) / 32) {
         case 1: return launch_umap<1>(C, n, k, max_iter, P, rho, sigma, st);
         case 2: return launch_umap<2>(C, n, k, max_iter, P, rho, sigma, st);

@@ -219,6 +219,7 @@ struct Params {
     const float* dbn;  // padded to a multiple of 128 with +inf
     const int* absmax_bits;
     int k, kpad, atoms, stages;
+    int aps;  // K-atoms per ring stage: `atoms` (a stage = a whole database tile) when two such stages fit, else 1
     int exclude_self, metric, fused, max_iter;
     int minima_a;  // phase A keeps 32 running minima per thread instead of lists (k <= 32, see below)
     int dual;   // 1: two epilogue warpgroups (384 threads), each with its own top-k lists, on alternate tiles
@@ -256,13 +257,14 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
               const Params prm) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int atoms = prm.atoms, stages = prm.stages, k = prm.k, kpad = prm.kpad;
+    const int atoms = prm.atoms, stages = prm.stages, k = prm.k, kpad = prm.kpad, aps = prm.aps;
+    const int stage_bytes = aps * STAGE_BYTES;
     const int a_bytes = atoms * STAGE_BYTES;  // hi + lo
     unsigned char* a_tiles = smem;                    // [atoms][hi, lo][16 KB]
     unsigned char* b_tiles = smem + a_bytes;          // [stages][hi, lo][16 KB]: one atom of a database tile per stage
     const int nl = 1 + prm.dual;  // list sets (epilogue warpgroups)
     const int n_lists = prm.c_full ? 0 : nl;
-    unsigned long long* lk_s = reinterpret_cast<unsigned long long*>(b_tiles + (size_t)stages * STAGE_BYTES);  // [n_lists][128][kpad] keys
+    unsigned long long* lk_s = reinterpret_cast<unsigned long long*>(b_tiles + (size_t)stages * stage_bytes);  // [n_lists][128][kpad] keys
     uint64_t* bars = reinterpret_cast<uint64_t*>(lk_s + n_lists * BM * kpad);
     // barrier slots: 0 a_full | 1..S full | 1+S..2S empty | 2S+1, 2S+2 tmem_full | 2S+3, 2S+4 tmem_empty
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 5);
@@ -336,10 +338,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                 tma_load_2d(smem_u32(a_tiles + (a * 2 + 1) * TILE_BYTES), &map_q_lo, BAR(0), a * KATOM,
                             (int)(prm.q_tile_row0 + q0));
             }
-            int64_t c = 0;  // ring slot counter: one slot per (tile, atom)
+            int64_t c = 0;  // ring slot counter: one slot per (tile, group of aps atoms)
             for (int64_t t = 0; t < n_sweep; ++t) {
                 const int row_db = (int)(tile_of(t) * BN);
-                for (int a = 0; a < atoms; ++a, ++c) {
+                for (int a0 = 0; a0 < atoms; a0 += aps, ++c) {
                     const int s = (int)(c % stages);
                     const uint32_t ph = (uint32_t)((c / stages) & 1);
                     mbar_wait(BAR(B_EMPTY + s), ph ^ 1u);
@@ -347,10 +349,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                         mbar_arrive(BAR(B_FULL + s));
                         continue;
                     }
-                    mbar_expect_tx(BAR(B_FULL + s), (uint32_t)STAGE_BYTES);
-                    unsigned char* dst = b_tiles + (size_t)s * STAGE_BYTES;
-                    tma_load_2d(smem_u32(dst), &map_db_hi, BAR(B_FULL + s), a * KATOM, row_db);
-                    tma_load_2d(smem_u32(dst + TILE_BYTES), &map_db_lo, BAR(B_FULL + s), a * KATOM, row_db);
+                    mbar_expect_tx(BAR(B_FULL + s), (uint32_t)stage_bytes);
+                    unsigned char* dst = b_tiles + (size_t)s * stage_bytes;
+                    for (int a = 0; a < aps; ++a) {
+                        tma_load_2d(smem_u32(dst + (a * 2 + 0) * TILE_BYTES), &map_db_hi, BAR(B_FULL + s), (a0 + a) * KATOM, row_db);
+                        tma_load_2d(smem_u32(dst + (a * 2 + 1) * TILE_BYTES), &map_db_lo, BAR(B_FULL + s), (a0 + a) * KATOM, row_db);
+                    }
                 }
             }
         }
@@ -365,13 +369,13 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                 mbar_wait(BAR(T_EMPTY + as), aph ^ 1u);
                 const uint32_t d_big = tmem_base + (uint32_t)(as * 256);
                 const uint32_t d_small = d_big + 128u;
-                for (int a = 0; a < atoms; ++a, ++c) {
+                for (int a0 = 0; a0 < atoms; a0 += aps, ++c) {
                     const int s = (int)(c % stages);
                     const uint32_t ph = (uint32_t)((c / stages) & 1);
                     mbar_wait(BAR(B_FULL + s), ph);
                     tc_fence_after();
-                    if (!(prm.debug & 2)) {
-                        const unsigned char* bt = b_tiles + (size_t)s * STAGE_BYTES;
+                    for (int a = a0; a < a0 + aps && !(prm.debug & 2); ++a) {
+                        const unsigned char* bt = b_tiles + (size_t)s * stage_bytes + (size_t)(a - a0) * STAGE_BYTES;
                         const uint64_t a_hi = make_smem_desc(smem_u32(a_tiles + (a * 2 + 0) * TILE_BYTES));
                         const uint64_t a_lo = make_smem_desc(smem_u32(a_tiles + (a * 2 + 1) * TILE_BYTES));
                         const uint64_t b_hi = make_smem_desc(smem_u32(bt));
@@ -974,20 +978,25 @@ static int make_map(CUtensorMap* m, const __half* base, int64_t rows, int dp) {
 }  // namespace tc
 
 // Shared-memory plan: resident query tile (atoms x 32 KB) + ring of >= 2 atom stages (32 KB each) + list sets + misc.
-static bool tc_smem_plan(int d, int k, bool dense, int* dual_out, int* stages_out, size_t* smem_out) {
+static bool tc_smem_plan(int d, int k, bool dense, int* dual_out, int* stages_out, size_t* smem_out, int* aps_out = nullptr) {
     using namespace tc;
     if (d > MAX_ATOMS * KATOM || (!dense && k > MAX_K)) return false;
-    const size_t q_bytes = (size_t)((d + KATOM - 1) / KATOM) * STAGE_BYTES;
+    const int atoms = (d + KATOM - 1) / KATOM;
+    const size_t q_bytes = (size_t)atoms * STAGE_BYTES;
     const size_t one_list = dense ? 0 : (size_t)BM * k * 8;
     auto fits = [&](int nl, int st) { return q_bytes + (size_t)st * STAGE_BYTES + nl * one_list + SMEM_MISC <= SMEM_LIMIT; };
     if (!fits(1, 2)) return false;
-    // two epilogue warpgroups (each with its own list set) when that still leaves a ring of >= 3 stages
+    // two epilogue warpgroups (each with its own list set) when that still leaves a ring of >= 3 atom stages
     const int dual = (dense || fits(2, 3)) ? 1 : 0;
-    int stages = (int)((SMEM_LIMIT - q_bytes - (1 + dual) * one_list - SMEM_MISC) / STAGE_BYTES);
-    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    int atom_stages = (int)((SMEM_LIMIT - q_bytes - (1 + dual) * one_list - SMEM_MISC) / STAGE_BYTES);
+    if (atom_stages > MAX_STAGES) atom_stages = MAX_STAGES;
+    // a stage = a whole database tile (one barrier round trip per tile, as in round 1) when two of them fit; else K-atoms
+    const int aps = atom_stages >= 2 * atoms ? atoms : 1;
+    const int stages = atom_stages / aps;
     if (dual_out) *dual_out = dual;
     if (stages_out) *stages_out = stages;
-    if (smem_out) *smem_out = q_bytes + (size_t)stages * STAGE_BYTES + (1 + dual) * one_list + SMEM_MISC;
+    if (aps_out) *aps_out = aps;
+    if (smem_out) *smem_out = q_bytes + (size_t)stages * aps * STAGE_BYTES + (1 + dual) * one_list + SMEM_MISC;
     return true;
 }
 
@@ -1117,7 +1126,7 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
     prm.minima_a = k <= 32 ? 1 : 0;
     int stages = 0;
     size_t smem = 0;
-    if (!tc_smem_plan(d, k, false, &prm.dual, &stages, &smem)) {
+    if (!tc_smem_plan(d, k, false, &prm.dual, &stages, &smem, &prm.aps)) {
         set_error("knn (tensor-core path): shared memory budget exceeded for d=%d k=%d", d, k);
         return TDR_E_UNSUPPORTED;
     }
@@ -1296,7 +1305,7 @@ int knn_tc_full_launch(const float* X, int64_t n, const float* Y, int64_t m, int
     prm.c_full = C;
     prm.full_exclude_diag = (exclude_diag && same) ? 1 : 0;
     size_t smem = 0;
-    if (!tc_smem_plan(d, 1, true, &prm.dual, &prm.stages, &smem)) {
+    if (!tc_smem_plan(d, 1, true, &prm.dual, &prm.stages, &smem, &prm.aps)) {
         set_error("pairwise (tensor-core path): d=%d exceeds %d", d, MAX_ATOMS * KATOM);
         return TDR_E_UNSUPPORTED;
     }

@@ -51,22 +51,45 @@ __device__ __forceinline__ float bracket_bisect(F f, float lo, float hi, int max
     return mid;
 }
 
+// Reductions over a group of W lanes (W = 32: the warp; W = 16: a half warp, two rows per warp).  xor-butterflies from
+// W/2 down: a 32-lane butterfly whose upper 16 lanes hold the neutral element gives the same bits as the 16-lane one
+// (x + 0, min(x, +inf), max(x, -inf) are exact), so results do not depend on the group width.
+template <int W>
+__device__ __forceinline__ float grp_sum(float v, unsigned mask) {
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    return v;
+}
+template <int W>
+__device__ __forceinline__ float grp_max(float v, unsigned mask) {
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(mask, v, o));
+    return v;
+}
+template <int W>
+__device__ __forceinline__ float grp_min(float v, unsigned mask) {
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(mask, v, o));
+    return v;
+}
+
 // ---- UMAP ------------------------------------------------------------------------------
-// c[e] holds C[row, lane + 32 e]; entries with index >= k are ignored.
-template <int EPL>
+// c[e] holds C[row, lane + W e] (lane = index inside the row's group of W lanes); entries with index >= k are ignored.
+template <int EPL, int W = 32>
 struct UmapRow {
     float c[EPL];
     int k, lane;
     float rho, target;
+    unsigned mask = 0xffffffffu;  // the lanes of this row's group
 
-    __device__ __forceinline__ bool valid(int e) const { return lane + 32 * e < k; }
+    __device__ __forceinline__ bool valid(int e) const { return lane + W * e < k; }
 
     __device__ __forceinline__ void init() {
         float m = INFINITY;
 #pragma unroll
         for (int e = 0; e < EPL; ++e)
             if (valid(e)) m = fminf(m, c[e]);
-        rho = warp_min(m);  // knn_normalized.py:445
+        rho = grp_min<W>(m, mask);  // knn_normalized.py:445
     }
     // knn_normalized.py:452-454: exp(logsumexp(-(C-rho)/sigma)) - log2(k)
     __device__ __forceinline__ float gap(float sigma) const {
@@ -77,12 +100,12 @@ struct UmapRow {
             x[e] = __fdiv_rn(-__fsub_rn(c[e], rho), sigma);
             if (valid(e)) m = fmaxf(m, x[e]);
         }
-        m = warp_max(m);
+        m = grp_max<W>(m, mask);
         float s = 0.0f;
 #pragma unroll
         for (int e = 0; e < EPL; ++e)
             if (valid(e)) s += expf(__fsub_rn(x[e], m));
-        s = warp_sum(s);
+        s = grp_sum<W>(s, mask);
         return __fsub_rn(expf(__fadd_rn(logf(s), m)), target);
     }
     __device__ __forceinline__ float solve(int max_iter) {
