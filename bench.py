@@ -434,17 +434,20 @@ def gpu_arm(args):
     peak, peak_src = (float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json, copy kernel)") if "hbm_gbs" in peaks \
         else (FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)")
     achieved = alg_bytes / world / (ms_per_step * 1e-3) / 1e9  # per GPU
-    traffic = None
+    traffic, ncu_detail = None, None
     prof = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
     if os.path.exists(prof) and world == 1:
         try:
-            traffic = json.load(open(prof)).get(f"dram_bytes_per_iteration_{n}")
+            tj = json.load(open(prof))
+            traffic = tj.get(f"dram_bytes_per_iteration_{n}")
+            ncu_detail = (tj.get("detail") or {}).get(str(n))
         except Exception:
             pass
     roofline = {"bound": "hbm", "kernel": "tdr::umap_run_kernel_persist (one launch = one timed block of iterations; figures per iteration)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes / world * K,
                 "algorithmic_bytes_per_iteration": alg_bytes / world,
+                "ncu_same_kernel_same_size": ncu_detail,  # profiles/step_kernel_traffic.json (per iteration), if captured at this size
                 "note": ("per GPU; achieved = algorithmic bytes per iteration (DESIGN.md 3.5, counts taken in-kernel) / mean "
                          "iteration time of the median timed block; ncu (profiles/) shows the kernel is bound by "
                          "instruction issue and by the L2/DRAM sector rate of the random 8-byte z_j gathers (a 32-byte sector "
