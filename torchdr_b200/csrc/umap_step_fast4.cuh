@@ -63,11 +63,9 @@ __device__ __forceinline__ float2 ld_z(const float2* a) {
     return __ldg(a);
 }
 
-// rows [rb, rb + nrows) of the rank's chunk, nrows <= 32 (the persistent loop hands out its last rows in 8-row units so
-// that the warps finish an iteration closer together; lanes >= nrows own an empty row)
 template <bool COH>
 __device__ __forceinline__ void step_block32(const UmapStepParams& p, const IterArgs& it, Warp4Smem& sm, const int lane,
-                                             const int64_t rb, const int nrows, Accum& acc) {
+                                             const int64_t rb, Accum& acc) {
     constexpr unsigned FULL = 0xffffffffu;
     const unsigned lt_mask = (1u << lane) - 1u;
     const float due_before = (float)(it.n_iter + 1);  // umap.py:251
@@ -76,11 +74,10 @@ __device__ __forceinline__ void step_block32(const UmapStepParams& p, const Iter
     const uint32_t c0 = (uint32_t)it.n_iter, c1 = (uint32_t)(it.n_iter >> 32);
 
     const int64_t r = rb + lane;
-    const int64_t lim = min(rb + nrows, p.n_local);
-    const bool live = r < lim;
+    const bool live = r < p.n_local;
     const int gi = (int)(p.row0 + (live ? r : rb));  // global row owned by this lane (indices are int32)
     const float2 zi = ld_z<COH>(it.Zin + gi);
-    const int64_t rp = __ldg(p.rowptr + min(r, lim)), rp_next = __ldg(p.rowptr + min(r + 1, lim));
+    const int64_t rp = __ldg(p.rowptr + min(r, p.n_local)), rp_next = __ldg(p.rowptr + min(r + 1, p.n_local));
     const int64_t E0 = __shfl_sync(FULL, (long long)rp, 0);
     const int off = (int)(rp - E0), off_next = (int)(rp_next - E0);  // my row's slice of the pooled edge range
     const int total = __shfl_sync(FULL, off_next, 31);
@@ -268,7 +265,7 @@ __global__ void __launch_bounds__(kFastThreads, kOcc4) umap_step_kernel_fast4(co
     it.n_iter = p.n_iter;
     it.lr = p.lr;
     Accum acc;
-    for (int64_t rb = warp_global * 32; rb < p.n_local; rb += n_warps * 32) step_block32<false>(p, it, sm, lane, rb, 32, acc);
+    for (int64_t rb = warp_global * 32; rb < p.n_local; rb += n_warps * 32) step_block32<false>(p, it, sm, lane, rb, acc);
     block_flush(true, acc.gn, acc.saw_nan, acc.n_act, acc.n_neg, p, p.gnorm_sq);
 }
 
@@ -386,15 +383,7 @@ umap_run_kernel_persist(const UmapStepParams p, const __grid_constant__ RunParam
     __shared__ int s_alive;
     Warp4Smem& sm = reinterpret_cast<Warp4Smem*>(s_raw4)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
-    // work units: 32-row blocks, then the last rows — about three quarters of one round of blocks over all warps — in
-    // 8-row units: with 6-8 blocks per warp and iteration the last block of the slowest warp used to leave the others idle
-    // for ~half a block (7 % of an iteration at 1 M points on one GPU, 5 % at 10 M on eight)
-    const int64_t n_warps_grid = (int64_t)gridDim.x * kWarps4;
-    int64_t tail_rows = min(p.n_local >> 2, n_warps_grid * 24);
-    tail_rows &= ~(int64_t)31;
-    const int64_t n_big = (p.n_local - tail_rows + 31) >> 5;  // 32-row blocks cover [0, n_big * 32)
-    const int64_t small_row0 = min(n_big << 5, p.n_local);
-    const int64_t n_units = n_big + ((p.n_local - small_row0 + 7) >> 3);
+    const int64_t n_blocks = (p.n_local + 31) >> 5;
     for (int t = 0; t < rp.n_steps; ++t) {
         const int src = (cur0 + t) & 1;
         IterArgs it;
@@ -410,12 +399,10 @@ umap_run_kernel_persist(const UmapStepParams p, const __grid_constant__ RunParam
         uint32_t blk = 0;
         if (lane == 0) blk = atomicAdd(work, 1u);
         blk = __shfl_sync(0xffffffffu, blk, 0);
-        while ((int64_t)blk < n_units) {
+        while ((int64_t)blk < n_blocks) {
             uint32_t nxt = 0;
             if (lane == 0) nxt = atomicAdd(work, 1u);
-            const bool big = (int64_t)blk < n_big;
-            step_block32<true>(p, it, sm, lane, big ? (int64_t)blk << 5 : small_row0 + (((int64_t)blk - n_big) << 3),
-                               big ? 32 : 8, acc);
+            step_block32<true>(p, it, sm, lane, (int64_t)blk << 5, acc);
             blk = __shfl_sync(0xffffffffu, nxt, 0);
         }
         const bool last = t == rp.n_steps - 1;
