@@ -316,6 +316,19 @@ def gpu_arm(args):
     (rowptr, col, eps, eons), bounds, knn, nnz_sym, knn_idx = build_graph(X, rank, world, sched, args)
     s, e = bounds[rank]
     parity_knn = knn_parity_sample(X, knn_idx, s, K_NEIGHBORS) if not args.no_parity else None
+    parity_rows = None
+    if not args.no_parity:
+        # the row search at this size: 256 consecutive rows through the same fused call, their sigma / rho / P against the
+        # oracle restatement of knn_normalized.py:445-468 fed with the engine's own distances (what the tests do at small n)
+        import oracle
+
+        o = s + (e - s) // 3
+        dq, iq, Pq, rq, sq = ops.knn_umap_fused(X[o:o + 256], X, K_NEIGHBORS, q_row0=o)
+        P_ref, rho_ref, sig_ref = oracle.umap_affinity_rows(dq.cpu(), K_NEIGHBORS)
+        parity_rows = {"rows_checked": int(dq.shape[0]), "rho_bit_equal": bool(torch.equal(rq.cpu(), rho_ref)),
+                       "sigma_max_rel_err": float(((sq.cpu() - sig_ref).abs() / sig_ref.abs()).max()),
+                       "P_max_rel_err": float(((Pq.cpu() - P_ref).abs() / P_ref.abs().clamp_min(1e-30)).max()),
+                       "same_indices_as_full_call": bool(torch.equal(iq, knn_idx[o - s:o - s + 256])), "tolerance": 1e-5}
     del knn_idx
     # the same stage on rows WITHOUT index locality (the generator's order shuffled), through the product path of
     # UMAPAffinity: locality probe -> Voronoi-tree order -> certified pruned sweep -> rows / neighbour ids mapped back
@@ -494,7 +507,7 @@ def gpu_arm(args):
             "clocks": clk.summary(),
             "graph": {"nnz_symmetrised": nnz_sym, "nnz_live": nnz, "sampled_edges_per_iter": act,
                       "negatives_per_iter": negs},
-            "parity": {"knn_sampled_rows_fp64": parity_knn,
+            "parity": {"knn_sampled_rows_fp64": parity_knn, "sigma_rows_vs_oracle": parity_rows,
                        "statement": "kNN indices bit-exact on decided entries (tests + the sampled check above at this size); "
                                     "sigma/P rtol 1e-5; graph, schedule bit-exact; UMAP step <= 1e-5 relative per step "
                                     "(measured ~1e-7), <= 1e-4 after T <= 3 steps from the reference's own Z0; beyond that "
