@@ -109,6 +109,14 @@ TDR_API int tdr_indexed_dist_f32(const float* X, const int64_t* query_idx, int64
 TDR_API int tdr_tree_assign_f32(const float* X, int d, const int64_t* rows, const int64_t* node, int64_t m,
                                 const float* centres, const float* cnorm, int B, int64_t* child_out,
                                 tdr_stream_t stream);
+/* Lloyd step of the same tree: sums[(node, child), d] and cnt[(node, child)] of the member rows (entries grouped by
+ * node as above; child[i] in [0, B), B <= 16, d <= 512).  Both outputs are zeroed by the call and must hold
+ * n_nodes + TDR_TREE_SPARE_NODES nodes (a tile's shared-memory accumulators are flushed for up to that many nodes past
+ * the tile's first). */
+#define TDR_TREE_SPARE_NODES 2
+TDR_API int tdr_tree_accumulate_f32(const float* X, int d, const int64_t* rows, const int64_t* node,
+                                    const int64_t* child, int64_t m, int64_t n_nodes, int B,
+                                    float* sums, float* cnt, tdr_stream_t stream);
 
 /* ---- (ii) per-row bandwidth search --------------------------------------
  * UMAPAffinity rows: rho = row min, sigma by bracket+bisection

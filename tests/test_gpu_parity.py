@@ -257,6 +257,44 @@ def test_pairwise_full_on_tensor_cores(ops, n, m, d):
             assert bool((Ct >= 0).all())
 
 
+def test_tree_order_kernels(ops):
+    """The two kernels of the Voronoi-tree ordering (csrc/reorder.cu) against their tensor-op restatements of
+    torchdr_b200/reorder.py, and the ordering itself: a permutation that creates index locality on shuffled clusters."""
+    from torchdr_b200 import reorder
+
+    g = torch.Generator().manual_seed(5)
+    n, d, B = 20_000, 96, 16
+    X = clustered(n, d)
+    X = X[torch.randperm(n, generator=g)].contiguous()
+    Xd = _cuda(X)
+    # 37 nodes of uneven sizes (> 128 rows each), entries grouped by node as the host hands them over
+    cuts = torch.sort(torch.randperm(n // 200, generator=g)[:36] * 200 + 150).values
+    node = torch.bucketize(torch.arange(n), cuts, right=True)
+    n_nodes = int(node.max()) + 1
+    rows = torch.randperm(n, generator=g)
+    centres = X[torch.randint(0, n, (n_nodes, B), generator=g)]
+    valid = torch.rand(n_nodes, B, generator=g) < 0.8
+    valid[:, 0] = True
+    cn = torch.where(valid, (centres * centres).sum(-1), torch.full((n_nodes, B), float("inf")))
+    child = ops.tree_assign(Xd, _cuda(rows), _cuda(node), _cuda(centres), _cuda(cn)).cpu()
+    d2 = cn[node] - 2.0 * torch.einsum("nd,nbd->nb", X[rows].double(), centres[node].double()).float()
+    ref = d2.argmin(1)
+    assert float((child == ref).float().mean()) > 0.999  # fp32 summation order may flip exact near-ties
+    assert bool(valid[node, child].all())
+    sums, cnt = ops.tree_accumulate(Xd, _cuda(rows), _cuda(node), _cuda(child), n_nodes, B)
+    flat = node * B + child
+    sums_ref = torch.zeros(n_nodes * B, d, dtype=torch.float64).index_add_(0, flat, X[rows].double())
+    cnt_ref = torch.bincount(flat, minlength=n_nodes * B).float()
+    assert torch.equal(cnt.cpu(), cnt_ref)
+    torch.testing.assert_close(sums.cpu().double(), sums_ref, rtol=1e-5, atol=1e-3)
+    before = reorder.index_locality(Xd)
+    perm = reorder.voronoi_tree_order(Xd, generator=torch.Generator(device=DEV).manual_seed(1))
+    assert torch.equal(torch.sort(perm).values.cpu(), torch.arange(n))
+    after = reorder.index_locality(Xd, perm=perm)
+    print(f"index locality {before:.3f} -> {after:.3f}")
+    assert before > reorder.LOCALITY_THRESHOLD and after < 0.5 * before
+
+
 def test_knn_large_properties(ops):
     """Config-2-like data at a size the oracle cannot hold densely: check sampled rows in fp64."""
     n, d, k = 60_000, 128, 15

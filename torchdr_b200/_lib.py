@@ -20,6 +20,7 @@ TDR_E_INVALID = -1
 TDR_MAX_K = 160
 TDR_RUN_SYNC_WORDS = 8
 TDR_RUN_STATUS_WORD = 4
+TDR_TREE_SPARE_NODES = 2
 METRIC_IDS = {"sqeuclidean": 0, "euclidean": 1}
 SYM_MODES = {"sum_minus_prod": 0, "sum": 1}
 KNN_PATHS = {"auto": 0, "simt": 1, "tc": 2}
@@ -37,6 +38,7 @@ SIGNATURES = {
                             c_size_t, P]),
     "tdr_pairwise_full_f32": (c_int, [P, c_int64, P, c_int64, c_int, c_int, c_int, P, c_int, P, c_size_t, P]),
     "tdr_tree_assign_f32": (c_int, [P, c_int, P, P, c_int64, P, P, c_int, P, P]),
+    "tdr_tree_accumulate_f32": (c_int, [P, c_int, P, P, P, c_int64, c_int64, c_int, P, P, P]),
     "tdr_umap_affinity_f32": (c_int, [P, c_int64, c_int, c_int, P, P, P, P]),
     "tdr_entropic_affinity_f32": (c_int, [P, c_int64, c_int, c_float, c_float, c_int, c_float, c_float, c_float,
                                           c_float, c_int, P, P, P, P]),

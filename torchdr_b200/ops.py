@@ -103,6 +103,21 @@ def tree_assign(X, rows, node_of_row, centres, cnorm):
     return out
 
 
+def tree_accumulate(X, rows, node_of_row, child, n_nodes, branch):
+    """Sums [n_nodes * branch, d] and counts [n_nodes * branch] of the rows of every (node, child) (reorder.py)."""
+    X = _dev_f32(X, "X")
+    rows, node_of_row, child = rows.contiguous(), node_of_row.contiguous(), child.contiguous()
+    assert rows.dtype == node_of_row.dtype == child.dtype == torch.int64
+    d = X.shape[1]
+    spare = _lib.TDR_TREE_SPARE_NODES
+    sums = torch.empty(((n_nodes + spare) * branch, d), dtype=torch.float32, device=X.device)
+    cnt = torch.empty(((n_nodes + spare) * branch,), dtype=torch.float32, device=X.device)
+    with torch.cuda.device(X.device):
+        check(_lib.load().tdr_tree_accumulate_f32(ptr(X), d, ptr(rows), ptr(node_of_row), ptr(child), rows.numel(), n_nodes,
+                                                  branch, ptr(sums), ptr(cnt), stream()), "tdr_tree_accumulate_f32")
+    return sums[:n_nodes * branch], cnt[:n_nodes * branch]
+
+
 def umap_affinity_rows(C, max_iter=100):
     C = _dev_f32(C, "C")
     n, k = C.shape

@@ -84,58 +84,73 @@ def choose_order(X, mode="auto", generator=None):
     return perm
 
 
+def _child_stats(X, rows, node_of_row, child, n_nodes, branch):
+    """Per (node, child): sum of the member rows [n_nodes * branch, d] and member count [n_nodes * branch]."""
+    if X.is_cuda and X.shape[1] <= 512:
+        from . import ops
+
+        return ops.tree_accumulate(X, rows, node_of_row, child, n_nodes, branch)  # csrc/reorder.cu: per-CTA partial sums
+    flat = node_of_row * branch + child
+    sums = torch.zeros((n_nodes * branch, X.shape[1]), dtype=torch.float32, device=X.device)
+    sums.index_add_(0, flat, X[rows])
+    cnt = torch.zeros(n_nodes * branch, dtype=torch.float32, device=X.device)
+    cnt.index_add_(0, flat, torch.ones_like(flat, dtype=torch.float32))
+    return sums, cnt
+
+
 def voronoi_tree_order(X, branch=16, leaf=128, lloyd=1, generator=None):
-    """Permutation (int64, on X's device) that sorts the rows of X[n, d] by the leaves of the tree."""
+    """Permutation (int64, on X's device) that sorts the rows of X[n, d] by the leaves of the tree.
+
+    Level-synchronous.  ``perm`` holds the rows sorted by their node's key (the path from the root, 4 bits per level)
+    at all times, so a node is a run of equal keys: no per-level ``unique`` / group-by, one stable sort per level after
+    the keys of the split nodes have received their next 4 bits."""
     assert 2 <= branch <= (1 << _BITS)
     n = X.shape[0]
     dev = X.device
     X = X.float()
-    key = torch.zeros(n, dtype=torch.long, device=dev)  # path of the row's node, 4 bits per level, left-aligned
-    open_rows = torch.arange(n, device=dev)  # rows whose node may still be split
+    perm = torch.arange(n, device=dev)
+    key = torch.zeros(n, dtype=torch.long, device=dev)     # key[i] = key of row perm[i]
+    closed = torch.zeros(n, dtype=torch.bool, device=dev)  # closed[i]: the node of perm[i] cannot be split (duplicates)
     for depth in range(_MAX_DEPTH):
-        if open_rows.numel() == 0:
-            break
         shift = 60 - _BITS * (depth + 1)
-        node_keys, node_of_row, sizes = torch.unique(key[open_rows], return_inverse=True, return_counts=True)
-        big = sizes > leaf
+        # nodes = runs of equal keys in the sorted order
+        first = torch.ones(n, dtype=torch.bool, device=dev)
+        first[1:] = key[1:] != key[:-1]
+        node_of_pos = torch.cumsum(first.long(), 0) - 1
+        starts_all = torch.nonzero(first).squeeze(1)
+        sizes_all = torch.diff(starts_all, append=torch.tensor([n], device=dev))
+        big = (sizes_all > leaf) & ~closed[starts_all]
         if not bool(big.any()):
             break
-        keep = big[node_of_row]
-        open_rows, node_of_row = open_rows[keep], node_of_row[keep]
-        # compact node ids over the nodes that are split at this level
-        remap = torch.cumsum(big.long(), 0) - 1
-        node_of_row = remap[node_of_row]
-        sizes = sizes[big]
+        sel = big[node_of_pos]
+        pos = torch.nonzero(sel).squeeze(1)               # positions of the rows of the nodes that are split, ascending
+        rows = perm[pos]                                   # grouped by node: a node's rows are consecutive
+        remap = torch.cumsum(big.long(), 0) - 1            # compact ids over the split nodes
+        node_of_row = remap[node_of_pos[pos]]
+        sizes = sizes_all[big]
         n_nodes = sizes.numel()
-        # rows grouped by node (stable): member rows are sampled as centres, and the assignment kernel finds a node's
-        # centres in cache while it walks the node's rows
-        order = torch.argsort(node_of_row, stable=True)
-        open_rows, node_of_row = open_rows[order], node_of_row[order]
         starts = torch.cumsum(sizes, 0) - sizes
         n_centres = torch.clamp(sizes // leaf, min=2, max=branch)  # [n_nodes]
         u = torch.rand((n_nodes, branch), generator=generator, device=dev)
         pick = starts.unsqueeze(1) + torch.clamp((u * sizes.unsqueeze(1)).long(), max=(sizes - 1).unsqueeze(1))
-        centres = X[open_rows[pick]]  # [n_nodes, branch, d]
+        centres = X[rows[pick]]  # [n_nodes, branch, d]: member rows sampled as centres
         valid = torch.arange(branch, device=dev).unsqueeze(0) < n_centres.unsqueeze(1)
-        child = _assign(X, open_rows, node_of_row, centres, valid)
+        child = _assign(X, rows, node_of_row, centres, valid)
         for _ in range(lloyd):
-            flat = node_of_row * branch + child
-            sums = torch.zeros((n_nodes * branch, X.shape[1]), dtype=torch.float32, device=dev)
-            sums.index_add_(0, flat, X[open_rows])
-            cnt = torch.zeros(n_nodes * branch, dtype=torch.float32, device=dev)
-            cnt.index_add_(0, flat, torch.ones_like(flat, dtype=torch.float32))
+            sums, cnt = _child_stats(X, rows, node_of_row, child, n_nodes, branch)
             has = (cnt > 0).view(n_nodes, branch)
             centres = torch.where(has.unsqueeze(-1), (sums / cnt.clamp_min(1).unsqueeze(1)).view(n_nodes, branch, -1),
                                   centres)
-            child = _assign(X, open_rows, node_of_row, centres, valid & has)
+            child = _assign(X, rows, node_of_row, centres, valid & has)
         # a node whose rows all chose the same child (duplicates) cannot be split: it becomes a leaf as it is
-        flat = node_of_row * branch + child
         cnt = torch.zeros(n_nodes * branch, dtype=torch.long, device=dev)
-        cnt.index_add_(0, flat, torch.ones_like(flat))
+        cnt.index_add_(0, node_of_row * branch + child, torch.ones_like(child))
         stuck = (cnt.view(n_nodes, branch).max(1).values == sizes)[node_of_row]
-        key[open_rows] |= torch.where(stuck, torch.zeros_like(child), child) << shift
-        open_rows = open_rows[~stuck]
-    return torch.argsort(key, stable=True)
+        key[pos] |= torch.where(stuck, torch.zeros_like(child), child) << shift
+        closed[pos] = stuck
+        key, order = torch.sort(key, stable=True)
+        perm, closed = perm[order], closed[order]
+    return perm
 
 
 def unpermute_knn_rows(perm, idx_p, dist_p, *aligned):
