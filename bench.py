@@ -564,6 +564,8 @@ def e2e_arm(args, dev, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     assert Z.shape == (n, 2) and np.isfinite(Z).all()
+    x_bytes, z_bytes = Xh.nbytes, Z.nbytes
+    del Xh, Z  # one pinned copy of X per rank at a time
     e2e_shuffled = None
     if args.order == "generator" and not args.no_shuffled:
         # the same fit on the same points in shuffled row order (no index locality: the fit runs in a tree order)
@@ -585,9 +587,9 @@ def e2e_arm(args, dev, world):
                         "note": "same fit, rows shuffled: locality probe + Voronoi-tree order + certified sweep, whole fit in "
                                 "the tree order, permutation undone on the embedding"}
         del Xs, Z2
-    h2d = Xh.nbytes / world  # per rank: its own row chunk crosses PCIe, the rest arrives over NVLink
+    h2d = x_bytes / world  # per rank: its own row chunk crosses PCIe, the rest arrives over NVLink
     return {"value": E2E_ITERS / dt, "unit": "iters/s", "h2d_bytes_per_step": h2d / E2E_ITERS,
-            "d2h_bytes_per_step": Z.nbytes / E2E_ITERS, "seconds": dt, "iters": E2E_ITERS,
+            "d2h_bytes_per_step": z_bytes / E2E_ITERS, "seconds": dt, "iters": E2E_ITERS,
             "exchange": getattr(m, "exchange_", None), "stages_seconds_rank0_instrumented_refit": stages,
             "shuffled_rows": e2e_shuffled,
             "note": "UMAP(n_neighbors=15, max_iter=500, init='normal').fit_transform(numpy X): iters / wall time (max over "
