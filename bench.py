@@ -931,7 +931,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-shuffled", action="store_true", help="skip the shuffled-row-order legs (affinity stage, e2e)")
     ap.add_argument("--e2e-stages", action="store_true", help="add a second, instrumented fit that reports stage seconds")
-    ap.add_argument("--full-sweep-rows", type=int, default=65536,
+    ap.add_argument("--full-sweep-rows", type=int, default=4 * 148 * 128,  # whole waves of 128-row query tiles on 148 SMs
                     help="query rows on which the unpruned kNN sweep is timed (scaled to the rank's rows)")
     ap.add_argument("--order", default="generator", choices=["generator", "shuffled"],
                     help="row order of the synthetic points: the reference generator's (clusters contiguous) or shuffled")

@@ -157,16 +157,25 @@ def unpermute_knn_rows(perm, idx_p, dist_p, *aligned):
     """Map kNN rows computed on ``X[perm]`` back: neighbour ids become original ids, equal distances within a row
     are put in ascending original id (the tie order of every kernel of this engine), ``aligned`` tensors ([n, k],
     entry-aligned with dist_p, e.g. the affinity values) follow their entries, and row r of the result is the row of
-    original point r.  Returns (idx, dist, *aligned) — idx in idx_p's dtype."""
+    original point r.  Returns (idx, dist, *aligned) — idx in idx_p's dtype.
+
+    The rows arrive sorted by distance (ties by permuted id), so only rows that contain EQUAL distances can need a
+    different entry order after the ids are mapped: those (rare: duplicates) are re-sorted, the others only re-labelled."""
     idx_o = perm[idx_p.long()]
-    o1 = torch.argsort(idx_o, dim=1, stable=True)
-    o2 = torch.argsort(dist_p.gather(1, o1), dim=1, stable=True)
-    order = o1.gather(1, o2)
+    tens = [idx_o, dist_p] + list(aligned)
+    tied = (dist_p[:, 1:] == dist_p[:, :-1]).any(1) if dist_p.shape[1] > 1 else torch.zeros(0, dtype=torch.bool)
+    if bool(tied.any()):
+        r = torch.nonzero(tied).squeeze(1)
+        o1 = torch.argsort(idx_o[r], dim=1, stable=True)
+        o2 = torch.argsort(dist_p[r].gather(1, o1), dim=1, stable=True)
+        order = o1.gather(1, o2)
+        tens = [t.clone() if t is dist_p or any(t is a for a in aligned) else t for t in tens]
+        for t in tens:
+            t[r] = t[r].gather(1, order)
     out = []
-    for tns in (idx_o, dist_p) + tuple(aligned):
-        rows = tns.gather(1, order)
-        back = torch.empty_like(rows)
-        back[perm] = rows
+    for t in tens:
+        back = torch.empty_like(t)
+        back[perm] = t
         out.append(back)
     out[0] = out[0].to(idx_p.dtype)
     return tuple(out)
