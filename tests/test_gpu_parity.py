@@ -295,6 +295,33 @@ def test_tree_order_kernels(ops):
     assert before > reorder.LOCALITY_THRESHOLD and after < 0.5 * before
 
 
+def test_affinity_in_tree_order_equals_input_order(ops):
+    """UMAPAffinity / EntropicAffinity with knn_order="auto" on rows without index locality (shuffled clusters, with
+    duplicated points so that equal distances occur): searched in the Voronoi-tree order with the certified sweep and
+    mapped back, the result must be what the search in the input order gives — graph, sigma / rho, eps, indices."""
+    import torchdr_b200 as tb
+    from torchdr_b200 import reorder
+
+    g = torch.Generator().manual_seed(3)
+    n, d = 24_000, 64
+    X = clustered(n, d)
+    X[n - 500:] = X[:500]  # duplicates -> ties
+    X = X[torch.randperm(n, generator=g)].contiguous()
+    Xd = _cuda(X)
+    assert reorder.index_locality(Xd) > reorder.LOCALITY_THRESHOLD
+    a_in = tb.UMAPAffinity(n_neighbors=15, max_iter=100, knn_order="input")
+    a_tr = tb.UMAPAffinity(n_neighbors=15, max_iter=100, knn_order="auto")
+    csr_in, csr_tr = a_in.compute_csr(Xd), a_tr.compute_csr(Xd)
+    for x, y in zip(csr_in, csr_tr):
+        assert torch.equal(x, y)
+    assert torch.equal(a_in.eps_, a_tr.eps_) and torch.equal(a_in.rho_, a_tr.rho_)
+    assert torch.equal(a_in.knn_[1], a_tr.knn_[1]) and torch.equal(a_in.knn_[0], a_tr.knn_[0])
+    e_in = tb.EntropicAffinity(perplexity=10, max_iter=100, knn_order="input")
+    e_tr = tb.EntropicAffinity(perplexity=10, max_iter=100, knn_order="tree")
+    (l_in, i_in), (l_tr, i_tr) = e_in(Xd, log=True), e_tr(Xd, log=True)
+    assert torch.equal(i_in, i_tr) and torch.equal(l_in, l_tr) and torch.equal(e_in.eps_, e_tr.eps_)
+
+
 def test_knn_large_properties(ops):
     """Config-2-like data at a size the oracle cannot hold densely: check sampled rows in fp64."""
     n, d, k = 60_000, 128, 15
