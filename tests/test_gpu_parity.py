@@ -334,7 +334,8 @@ def test_affinity_in_tree_order_equals_input_order(ops):
     Ii, It = a_in.knn_[1].long(), a_tr.knn_[1].long()
     diff = Ii != It
     assert int(diff.sum()) < 50 and torch.equal(Xd2[Ii[diff]], Xd2[It[diff]])
-    assert bool((diff[:, :-1] <= ((a_in.knn_[0][:, :-1] == a_in.knn_[0][:, -1:]) | ~diff[:, :-1])).all())  # only inside the last tie group
+    D = a_in.knn_[0]
+    assert bool((D[diff] == D[:, -1:].expand_as(D)[diff]).all())  # only inside the tie group of the k-th place
 
 
 def test_knn_large_properties(ops):
