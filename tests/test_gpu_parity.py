@@ -296,46 +296,41 @@ def test_tree_order_kernels(ops):
 
 
 def test_affinity_in_tree_order_equals_input_order(ops):
-    """UMAPAffinity / EntropicAffinity with knn_order="auto" on rows without index locality (shuffled clusters):
-    searched in the Voronoi-tree order with the certified sweep and mapped back, the result must be what the search in
-    the input order gives — graph, sigma / rho, eps, indices, bit for bit.  With exact DUPLICATE points the distances
-    (hence sigma / rho / eps) are still identical; where two duplicates tie for the k-th place either one is a correct
-    k-th neighbour and the two orders may name different copies of the same point (the engine's tie rule is "lower
-    index in the order searched"; torch.topk's own tie order is implementation-defined)."""
+    """UMAPAffinity / EntropicAffinity with knn_order="auto" / "tree" on rows without index locality (shuffled clusters,
+    some points duplicated): searched in the Voronoi-tree order with the certified sweep and mapped back, the result
+    must be what the search in the input order gives: identical distances (hence identical sigma / rho / eps / P / log P),
+    and identical indices except where several candidates TIE in fp32 for the k-th place — the expanded-form distances
+    have a resolution of one ulp of |x|^2 + |y|^2 (2e-3 here), so ~1e-4 of the rows end in such a tie, either candidate is
+    a correct k-th neighbour (oracle/knn.py classifies these entries as undecided) and the engine's rule "lower index in
+    the order searched" may pick the other one.  torch.topk's own tie order is implementation-defined."""
     import torchdr_b200 as tb
     from torchdr_b200 import reorder
 
     g = torch.Generator().manual_seed(3)
     n, d = 24_000, 64
     X = clustered(n, d)
+    X[n - 500:] = X[:500]  # exact duplicates as well
     X = X[torch.randperm(n, generator=g)].contiguous()
     Xd = _cuda(X)
     assert reorder.index_locality(Xd) > reorder.LOCALITY_THRESHOLD
+
+    def only_kth_place_ties(D, I_a, I_b):
+        diff = I_a != I_b
+        assert float(diff.float().mean()) < 1e-3, float(diff.float().mean())
+        return bool((D[diff] == D[:, -1:].expand_as(D)[diff]).all())
+
     a_in = tb.UMAPAffinity(n_neighbors=15, max_iter=100, knn_order="input")
     a_tr = tb.UMAPAffinity(n_neighbors=15, max_iter=100, knn_order="auto")
-    csr_in, csr_tr = a_in.compute_csr(Xd), a_tr.compute_csr(Xd)
-    for x, y in zip(csr_in, csr_tr):
-        assert torch.equal(x, y)
+    a_in.symmetrize = a_tr.symmetrize = False
+    (P_in, I_in), (P_tr, I_tr) = a_in.compute_csr(Xd), a_tr.compute_csr(Xd)
+    assert torch.equal(a_in.knn_[0], a_tr.knn_[0]) and torch.equal(P_in, P_tr)
     assert torch.equal(a_in.eps_, a_tr.eps_) and torch.equal(a_in.rho_, a_tr.rho_)
-    assert torch.equal(a_in.knn_[1], a_tr.knn_[1]) and torch.equal(a_in.knn_[0], a_tr.knn_[0])
+    assert only_kth_place_ties(a_in.knn_[0], I_in, I_tr)
     e_in = tb.EntropicAffinity(perplexity=10, max_iter=100, knn_order="input")
     e_tr = tb.EntropicAffinity(perplexity=10, max_iter=100, knn_order="tree")
     (l_in, i_in), (l_tr, i_tr) = e_in(Xd, log=True), e_tr(Xd, log=True)
-    assert torch.equal(i_in, i_tr) and torch.equal(l_in, l_tr) and torch.equal(e_in.eps_, e_tr.eps_)
-    # duplicates: same distances and rows; indices may differ only between copies of the same point
-    X2 = clustered(n, d)
-    X2[n - 500:] = X2[:500]
-    X2 = X2[torch.randperm(n, generator=g)].contiguous()
-    Xd2 = _cuda(X2)
-    a_in.compute_csr(Xd2)
-    a_tr.compute_csr(Xd2)
-    assert torch.equal(a_in.knn_[0], a_tr.knn_[0])
-    assert torch.equal(a_in.eps_, a_tr.eps_) and torch.equal(a_in.rho_, a_tr.rho_)
-    Ii, It = a_in.knn_[1].long(), a_tr.knn_[1].long()
-    diff = Ii != It
-    assert int(diff.sum()) < 50 and torch.equal(Xd2[Ii[diff]], Xd2[It[diff]])
-    D = a_in.knn_[0]
-    assert bool((D[diff] == D[:, -1:].expand_as(D)[diff]).all())  # only inside the tie group of the k-th place
+    assert torch.equal(l_in, l_tr) and torch.equal(e_in.eps_, e_tr.eps_) and torch.equal(e_in.knn_[0], e_tr.knn_[0])
+    assert only_kth_place_ties(e_in.knn_[0], i_in, i_tr)
 
 
 def test_knn_large_properties(ops):
