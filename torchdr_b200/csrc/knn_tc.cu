@@ -10,16 +10,17 @@
 //
 // One CTA (256 or 384 threads, 1 per SM) owns 128 query rows: their hi/lo tiles stay resident in
 // shared memory (TMA, 128B swizzle) for the whole sweep over the database, which streams through
-// a ring of TMA stages.  A stage is one K-ATOM of a 128-row database tile ([128 x 64] hi + lo = 32 KB), not a
-// whole tile: the ring then fits next to the resident queries and the top-k lists for every shape up to
-// d = 256 / k = 33 and d = 128 / k = 96 (the entropic k = 3 * perplexity of t-SNE / LargeVis), and the
-// MMAs of an atom start as soon as that atom has landed.  Warp 0 = TMA producer, warp 1 = MMA issuer (one
-// thread), warp 2 = TMEM allocator, warps 4-7 = epilogue: thread t owns TMEM lane t = query row
-// t, reads its 128 accumulator columns with tcgen05.ld, forms the distance and compares it with
-// its row's running k-th best held in a register; the rare survivor is insertion-sorted into the
-// row's list in shared memory.  Two accumulator stages (2 x 256 TMEM columns) overlap the MMAs of
-// tile t+1 with the filter of tile t.  MODE_FUSED runs the UMAP rho/sigma search (rowsearch.cuh)
-// on the finished rows before they leave the SM.
+// a ring of TMA stages.  A stage holds a whole 128-row database tile when two such stages fit next to the
+// resident queries and the top-k lists (d = 128 / k <= 33, d <= 64), else ONE K-ATOM of a tile
+// ([128 x 64] hi + lo = 32 KB): that is what extends the kernel to d = 256 / k = 33 and d = 128 / k = 96
+// (the entropic k = 3 * perplexity of t-SNE / LargeVis).  Warp 0 = TMA producer, warp 1 = MMA issuer (one
+// thread), warp 2 = TMEM allocator, warps 4-11 = two epilogue warpgroups: thread t owns TMEM lane t = query
+// row t, reads its accumulator columns with tcgen05.ld, forms the distance and compares it with its row's
+// running k-th best held in a register; the rare survivor goes into the row's UNSORTED list of 64-bit
+// (distance, index) keys in shared memory, rank-sorted once after the sweep.  Two accumulator stages
+// (2 x 256 TMEM columns) overlap the MMAs of tile t+1 with the filter of tile t.  Fused mode runs the UMAP
+// rho/sigma search (rowsearch.cuh) on the finished rows before they leave the SM; dense mode
+// (tdr_pairwise_full_f32) writes every distance of the sweep instead of filtering.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -223,7 +224,7 @@ struct Params {
     int exclude_self, metric, fused, max_iter;
     int minima_a;  // phase A keeps 32 running minima per thread instead of lists (k <= 32, see below)
     int dual;   // 1: two epilogue warpgroups (384 threads), each with its own top-k lists, on alternate tiles
-    int debug;  // timing experiments only (env TDR_TC_DEBUG): 1 = skip filter, 2 = skip MMAs, 4 = skip database TMA
+    int debug;  // ablation bits for timing experiments (always 0 in the library): 1 = skip filter, 2 = skip MMAs, 4 = skip database TMA
     // tile-pruned sweep (see the "pruned sweep" section below): which database tiles this CTA visits
     int win;                 // > 0: only the tiles within +-win of the CTA's own rows (phase A)
     const int* tile_list;    // [gridDim.x][list_cap] ascending tile ids (phase B), or null = all tiles

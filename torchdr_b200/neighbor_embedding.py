@@ -3,10 +3,13 @@
 Mirrors ``torchdr/base.py:27-229`` (``DRModule.fit / fit_transform / transform``),
 ``torchdr/affinity_matcher.py:201-352`` (affinity -> init -> optimisation loop with the
 ``on_*`` lifecycle hooks) and ``torchdr/neighbor_embedding/{base,umap,largevis,tsne,infotsne,sne}.py``.
-The loop body is one CUDA kernel per iteration (UMAP) or two (gradient + momentum SGD); the
-optimiser / scheduler objects are the reference's own ``torch.optim`` classes stepped on a
-dummy parameter, so learning-rate and momentum sequences — including the reference's
-param-group reuse when the optimiser is rebuilt after early exaggeration — are identical.
+UMAP: the iterations between two convergence checks run in ONE persistent kernel launch (row-sharded: with the NVLink
+row exchange and the cross-GPU barrier inside it); LargeVis: one row-local step per iteration (gradient gathered from
+P + P^T, fused momentum SGD, rows stored into the peers); t-SNE / InfoTSNE / SNE: gradient kernel + momentum-SGD kernel.
+The optimiser / scheduler objects are the reference's own ``torch.optim`` classes stepped on a dummy parameter, so
+learning-rate and momentum sequences — including the reference's param-group reuse when the optimiser is rebuilt after
+early exaggeration — are identical.  Inputs whose row order carries no locality are fitted in a Voronoi-tree order
+(``reorder.py``) and the permutation is undone on the embedding.
 """
 
 import logging
