@@ -702,7 +702,11 @@ class UMAP(_NeighborEmbeddingB200):
             self._last_step = last
             step = last + 1
             if peer is not None or self.world_size == 1:
-                sync.check()
+                try:
+                    sync.check()
+                except _lib.B200EngineError:
+                    PeerEmbedding._cache.clear()  # an aborted exchange leaves flags / epochs undefined: never reuse them
+                    raise
             self._check_nan(last)
             if exag_end:  # NE base.py:282-295: coefficient back to 1, fresh optimiser and scheduler
                 self.early_exaggeration_coeff_ = 1
