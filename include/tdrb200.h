@@ -72,7 +72,12 @@ TDR_API size_t tdr_knn_workspace_bytes(int64_t nq, int64_t ndb, int d, int k);
  *        certification pass and a second sweep of the uncertified query tiles — for inputs that were brought
  *        into a locality-creating order first (torchdr_b200/reorder.py), also bit-identical.
  * sweep_stats  optional device pointer to two uint64 counters, [0] += tiles swept, [1] += tiles a full sweep
- *        would visit (summed over query tiles); NULL disables them. */
+ *        would visit (summed over query tiles); NULL disables them.
+ * db_labels    optional int32[ndb]: the id reported in out_idx for database row c is db_labels[c], and candidates
+ *        that tie in distance are ranked by that id — the k neighbours are the k smallest by (distance, label)
+ *        whatever the order of the database rows.  Used when the database was re-ordered (torchdr_b200/reorder.py)
+ *        and labels = the rows' ids in the caller's order: the result then does not depend on the re-ordering.
+ *        NULL: the row index is the label.  (The fp32 SIMT kernel re-labels after the search: ties by row index.) */
 #define TDR_KNN_PATH_AUTO 0
 #define TDR_KNN_PATH_SIMT 1
 #define TDR_KNN_PATH_TC 2
@@ -84,7 +89,7 @@ TDR_API int tdr_knn_f32(const float* Xq, int64_t nq, int64_t q_row0,
                 const float* Xdb, int64_t ndb, int d, int k,
                 int exclude_self, int metric,
                 float* out_dist /*[nq,k]*/, int32_t* out_idx /*[nq,k]*/,
-                int path, int prune, uint64_t* sweep_stats,
+                int path, int prune, uint64_t* sweep_stats, const int32_t* db_labels,
                 void* ws, size_t ws_bytes, tdr_stream_t stream);
 
 /* Full matrix C[n,m] (k=None path, distance/torch.py:81-116).  Y may equal X.  path as above: AUTO = the
@@ -157,7 +162,7 @@ TDR_API int tdr_knn_umap_fused_f32(const float* Xq, int64_t nq, int64_t q_row0,
                            int exclude_self, int max_iter,
                            float* out_dist /*[nq,k] or NULL*/, int32_t* out_idx /*[nq,k]*/,
                            float* P /*[nq,k]*/, float* rho /*[nq]*/, float* sigma /*[nq]*/,
-                           int path, int prune, uint64_t* sweep_stats,
+                           int path, int prune, uint64_t* sweep_stats, const int32_t* db_labels,
                            void* ws, size_t ws_bytes, tdr_stream_t stream);
 
 /* ---- graph stage ---------------------------------------------------------

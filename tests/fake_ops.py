@@ -28,10 +28,22 @@ def install(monkeypatch):
         monkeypatch.setattr(ops, name, fn)
 
 
+def _relabel(C, I, labels):
+    """ids -> labels, distance ties inside a row ranked by label (what the kernel's label keys do)."""
+    if labels is None:
+        return C, I
+    L = labels.long()[I.long()]
+    o1 = torch.argsort(L, dim=1, stable=True)
+    o2 = torch.argsort(C.gather(1, o1), dim=1, stable=True)
+    order = o1.gather(1, o2)
+    return C.gather(1, order), L.gather(1, order).to(I.dtype)
+
+
 def knn_umap_fused(Xq, Xdb, k, q_row0=0, exclude_self=True, max_iter=100, want_dist=True, path="auto", prune=None,
-                   sweep_stats=None):
+                   sweep_stats=None, labels=None):
     assert Xq.shape[0] == Xdb.shape[0] and q_row0 == 0 and exclude_self
     C, I = oracle.knn_dense(Xdb, k)
+    C, I = _relabel(C, I, labels)
     P, rho, sigma = oracle.umap_affinity_rows(C, k, max_iter=max_iter)
     return C, I, P, rho, sigma
 
@@ -103,9 +115,10 @@ def umap_run(Z_a, Z_b, rowptr, col, eps, eons, n_iter0, lrs, a, b, n_neg=75, rat
 
 
 # ---- entropic-affinity estimators (LargeVis, TSNE): gradients by autograd of the oracle's losses, as in the reference
-def knn(Xq, Xdb, k, q_row0=0, exclude_self=True, metric="sqeuclidean", path="auto", prune=None, sweep_stats=None):
+def knn(Xq, Xdb, k, q_row0=0, exclude_self=True, metric="sqeuclidean", path="auto", prune=None, sweep_stats=None,
+        labels=None):
     if Xq is Xdb or (Xq.shape == Xdb.shape and Xq.data_ptr() == Xdb.data_ptr()):
-        return oracle.knn_dense(Xdb, k, metric, exclude_self)
+        return _relabel(*oracle.knn_dense(Xdb, k, metric, exclude_self), labels)
     # cross / chunk queries: distance/torch.py:81-122 on (Xq, Xdb), self excluded by global id
     C = oracle.pairwise_full(Xq, Xdb, metric)
     if exclude_self:
@@ -241,7 +254,7 @@ def install_sharded(monkeypatch):
 
 
 def knn_umap_fused_chunk(Xq, Xdb, k, q_row0=0, exclude_self=True, max_iter=100, want_dist=True, path="auto", prune=None,
-                         sweep_stats=None):
+                         sweep_stats=None, labels=None):
     C, I = oracle.knn_dense(Xdb, k)  # full problem, then this rank's rows: identical values for every partition
     P, rho, sigma = oracle.umap_affinity_rows(C, k, max_iter=max_iter)
     s, e = q_row0, q_row0 + Xq.shape[0]

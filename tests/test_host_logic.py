@@ -213,9 +213,9 @@ def test_knn_options_validate_without_a_gpu():
     lib = _lib.load()
     one = ctypes.c_void_p(256)  # never dereferenced: argument validation comes first
     args = (one, 4, 0, one, 4, 8, 2, 1, 0, one, one)
-    assert lib.tdr_knn_f32(*args, 7, -1, None, None, 0, None) == _lib.TDR_E_INVALID
+    assert lib.tdr_knn_f32(*args, 7, -1, None, None, None, 0, None) == _lib.TDR_E_INVALID
     assert "path" in _lib.last_error()
-    assert lib.tdr_knn_f32(*args, 0, 3, None, None, 0, None) == _lib.TDR_E_INVALID
+    assert lib.tdr_knn_f32(*args, 0, 3, None, None, None, 0, None) == _lib.TDR_E_INVALID
     assert "prune" in _lib.last_error()
     assert not hasattr(lib, "tdr_knn_set_prune_") and "tdr_knn_set_prune" not in _lib.SIGNATURES
     # the workspace query covers the pruned sweep's buffers (boxes, bounds, tile lists) once there are >= 64 tiles

@@ -34,7 +34,7 @@ SIGNATURES = {
     "tdr_last_error": (c_char_p, []),
     "tdr_device_info": (c_int, [ctypes.POINTER(c_int)] * 3),
     "tdr_knn_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int]),
-    "tdr_knn_f32": (c_int, [P, c_int64, c_int64, P, c_int64, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P, P,
+    "tdr_knn_f32": (c_int, [P, c_int64, c_int64, P, c_int64, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P, P, P,
                             c_size_t, P]),
     "tdr_pairwise_full_f32": (c_int, [P, c_int64, P, c_int64, c_int, c_int, c_int, P, c_int, P, c_size_t, P]),
     "tdr_tree_assign_f32": (c_int, [P, c_int, P, P, c_int64, P, P, c_int, P, P]),
@@ -46,7 +46,7 @@ SIGNATURES = {
     "tdr_entropic_dense_f32": (c_int, [P, c_int64, c_int64, c_float, c_float, c_int, c_float, c_float, c_float,
                                        c_float, c_int, P, P, P, P]),
     "tdr_knn_umap_fused_f32": (c_int, [P, c_int64, c_int64, P, c_int64, c_int, c_int, c_int, c_int, P, P, P, P, P,
-                                       c_int, c_int, P, P, c_size_t, P]),
+                                       c_int, c_int, P, P, P, c_size_t, P]),
     "tdr_symmetrize_workspace_bytes": (c_size_t, [c_int64, c_int, c_int64]),
     "tdr_symmetrize_csr_f32": (c_int, [P, P, c_int64, c_int, c_int64, c_int64, P, P, P, c_int64, c_int, c_int, P, P, P,
                                        P, P, c_size_t, P]),

@@ -180,18 +180,21 @@ class UMAPAffinity(_SparseAffinityBase):
             t0 = time.perf_counter()
         perm, prune = self._search_order(X)
         if perm is not None:
-            # no index locality in the input: search in the tree order with the certified sweep, map the rows back
-            from .reorder import unpermute_knn_rows, unpermute_rows
+            # no index locality in the input: search in the tree order with the certified sweep.  The rows' own ids travel
+            # as labels: the kernel reports them and ranks distance ties by them, so the result is the input-order
+            # search's bit for bit; only the rows have to be put back in place
+            from .reorder import unpermute_rows
 
             Xp = X[perm].contiguous()
+            lab = perm.to(torch.int32)
             if self.metric == "sqeuclidean":
                 dist, idx, P, rho, sigma = ops.knn_umap_fused(Xp, Xp, k, q_row0=0, exclude_self=bool(self.zero_diag),
-                                                              max_iter=self.max_iter, prune=prune)
+                                                              max_iter=self.max_iter, prune=prune, labels=lab)
             else:
-                dist, idx = ops.knn(Xp, Xp, k, q_row0=0, exclude_self=bool(self.zero_diag), metric=self.metric, prune=prune)
+                dist, idx = ops.knn(Xp, Xp, k, q_row0=0, exclude_self=bool(self.zero_diag), metric=self.metric, prune=prune,
+                                    labels=lab)
                 P, rho, sigma = ops.umap_affinity_rows(dist, self.max_iter)
-            idx, dist, P = unpermute_knn_rows(perm, idx, dist, P)
-            rho, sigma = unpermute_rows(perm, rho, sigma)
+            idx, dist, P, rho, sigma = unpermute_rows(perm, idx, dist, P, rho, sigma)
             del Xp
         elif self.metric == "sqeuclidean":
             dist, idx, P, rho, sigma = ops.knn_umap_fused(X[s:e], X, k, q_row0=s, exclude_self=bool(self.zero_diag),
@@ -260,11 +263,12 @@ class EntropicAffinity(_SparseAffinityBase):
         s, e = self._chunk(n)
         perm, prune = self._search_order(X)
         if perm is not None:
-            from .reorder import unpermute_knn_rows
+            from .reorder import unpermute_rows
 
             Xp = X[perm].contiguous()
-            C, idx = ops.knn(Xp, Xp, k, q_row0=0, exclude_self=bool(self.zero_diag), metric=self.metric, prune=prune)
-            idx, C = unpermute_knn_rows(perm, idx, C)
+            C, idx = ops.knn(Xp, Xp, k, q_row0=0, exclude_self=bool(self.zero_diag), metric=self.metric, prune=prune,
+                             labels=perm.to(torch.int32))
+            idx, C = unpermute_rows(perm, idx, C)
             del Xp
         else:
             C, idx = ops.knn(X[s:e], X, k, q_row0=s, exclude_self=bool(self.zero_diag), metric=self.metric, prune=prune)

@@ -36,8 +36,14 @@ int knn_tc_full_launch(const float* X, int64_t n, const float* Y, int64_t m, int
 size_t knn_tc_workspace_bytes(int64_t nq, int64_t ndb, int d, int k, bool same);
 int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb, int64_t ndb, int d, int k,
                   bool same, int exclude_self, int metric, int fused, int max_iter, float* out_dist, int32_t* out_idx,
-                  float* P, float* rho, float* sigma, int prune, unsigned long long* sweep_stats, void* ws,
-                  size_t ws_bytes, cudaStream_t st);
+                  float* P, float* rho, float* sigma, int prune, unsigned long long* sweep_stats,
+                  const int32_t* db_labels, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// fp32 SIMT path with labels: the search ranks ties by row index; the reported ids are re-labelled afterwards
+__global__ void __launch_bounds__(256) relabel_kernel(int32_t* __restrict__ idx, int64_t n, const int32_t* __restrict__ labels) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) idx[i] = __ldg(labels + idx[i]);
+}
 
 struct KnnParams {
     const float* Xq;   // [nq, ld]
@@ -463,7 +469,7 @@ static int launch_knn(const KnnParams& prm, dim3 grid, cudaStream_t st) {
 static int knn_common(int mode, const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb, int64_t ndb,
                       int d, int k, int exclude_self, int metric, int max_iter, float* out_dist,
                       int32_t* out_idx, float* P, float* rho, float* sigma, int path, int prune,
-                      uint64_t* sweep_stats, void* ws, size_t ws_bytes, cudaStream_t st) {
+                      uint64_t* sweep_stats, const int32_t* db_labels, void* ws, size_t ws_bytes, cudaStream_t st) {
     TDR_CHECK_ARG(Xq && Xdb && out_idx, "knn: null pointer");
     TDR_CHECK_ARG(path >= TDR_KNN_PATH_AUTO && path <= TDR_KNN_PATH_TC, "knn: path must be 0 (auto), 1 (SIMT fp32) or 2 (tcgen05)");
     TDR_CHECK_ARG(prune >= TDR_KNN_PRUNE_DEFAULT && prune <= TDR_KNN_PRUNE_CERTIFIED, "knn: prune must be -1 .. 2");
@@ -482,7 +488,7 @@ static int knn_common(int mode, const float* Xq, int64_t nq, int64_t q_row0, con
         const bool inside = (Xq == Xdb + q_row0 * d) && q_row0 + nq <= ndb;
         return knn_tc_launch(Xq, nq, q_row0, Xdb, ndb, d, k, inside, exclude_self, metric, mode == MODE_FUSED,
                              max_iter, out_dist, out_idx, P, rho, sigma, prune,
-                             reinterpret_cast<unsigned long long*>(sweep_stats), ws, ws_bytes, st);
+                             reinterpret_cast<unsigned long long*>(sweep_stats), db_labels, ws, ws_bytes, st);
     }
     if (path == TDR_KNN_PATH_TC) {
         set_error("knn: tensor-core path forced but unsupported for d=%d k=%d", d, k);
@@ -512,7 +518,12 @@ static int knn_common(int mode, const float* Xq, int64_t nq, int64_t q_row0, con
     prm.rho = rho;
     prm.sigma = sigma;
     dim3 grid((unsigned)((nq + BM - 1) / BM));
-    return mode == MODE_FUSED ? launch_knn<MODE_FUSED>(prm, grid, st) : launch_knn<MODE_KNN>(prm, grid, st);
+    rc = mode == MODE_FUSED ? launch_knn<MODE_FUSED>(prm, grid, st) : launch_knn<MODE_KNN>(prm, grid, st);
+    if (rc == TDR_OK && db_labels) {
+        relabel_kernel<<<(unsigned)((nq * k + 255) / 256), 256, 0, st>>>(out_idx, nq * k, db_labels);
+        TDR_LAUNCH_CHECK();
+    }
+    return rc;
 }
 
 }  // namespace tdr
@@ -528,20 +539,21 @@ extern "C" TDR_API size_t tdr_knn_workspace_bytes(int64_t nq, int64_t ndb, int d
 
 extern "C" TDR_API int tdr_knn_f32(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb, int64_t ndb, int d,
                            int k, int exclude_self, int metric, float* out_dist, int32_t* out_idx, int path,
-                           int prune, uint64_t* sweep_stats, void* ws, size_t ws_bytes, tdr_stream_t stream) {
+                           int prune, uint64_t* sweep_stats, const int32_t* db_labels, void* ws, size_t ws_bytes,
+                           tdr_stream_t stream) {
     TDR_CHECK_ARG(out_dist, "tdr_knn_f32: out_dist is null");
     return knn_common(MODE_KNN, Xq, nq, q_row0, Xdb, ndb, d, k, exclude_self, metric, 0, out_dist, out_idx,
-                      nullptr, nullptr, nullptr, path, prune, sweep_stats, ws, ws_bytes, (cudaStream_t)stream);
+                      nullptr, nullptr, nullptr, path, prune, sweep_stats, db_labels, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 extern "C" TDR_API int tdr_knn_umap_fused_f32(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
                                       int64_t ndb, int d, int k, int exclude_self, int max_iter,
                                       float* out_dist, int32_t* out_idx, float* P, float* rho, float* sigma,
-                                      int path, int prune, uint64_t* sweep_stats, void* ws, size_t ws_bytes,
-                                      tdr_stream_t stream) {
+                                      int path, int prune, uint64_t* sweep_stats, const int32_t* db_labels, void* ws,
+                                      size_t ws_bytes, tdr_stream_t stream) {
     TDR_CHECK_ARG(P && rho && sigma, "tdr_knn_umap_fused_f32: null output");
     return knn_common(MODE_FUSED, Xq, nq, q_row0, Xdb, ndb, d, k, exclude_self, TDR_METRIC_SQEUCLIDEAN,
-                      max_iter, out_dist, out_idx, P, rho, sigma, path, prune, sweep_stats, ws, ws_bytes,
+                      max_iter, out_dist, out_idx, P, rho, sigma, path, prune, sweep_stats, db_labels, ws, ws_bytes,
                       (cudaStream_t)stream);
 }
 

@@ -232,6 +232,7 @@ struct Params {
     int list_cap;
     float* kth_out;          // phase A: only a bound on the k-th distance of every row is written (squared domain)
     const float* tau_seed;   // phase B: that bound; the row's threshold starts there instead of at +inf
+    const int32_t* col_label;  // optional [ndb]: the id reported for a database row AND the tie-break key (null: the row index)
     unsigned long long* sweep_stats;  // optional: [0] += tiles swept, [1] += tiles of a full sweep
     float* out_dist;
     int32_t* out_idx;
@@ -424,6 +425,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                 tau = sd >= 0.0f ? __uint_as_float(__float_as_uint(sd + 0.0f) + 1u) : __uint_as_float(__float_as_uint(sd) - 1u);
         }
         int amax = 0, cnt = 0;  // position of the list's worst entry, filled slots
+        const int32_t* const labels = prm.col_label;
+        int worst_lab = 0x7fffffff;  // label of the list's worst entry once the list is full (labels only)
         const uint32_t lane_addr = (uint32_t)(((warp - 4) & 3) * 32) << 16;
 
         auto filter = [&](uint32_t(&big)[32], uint32_t(&small)[32], int col_base) {
@@ -445,18 +448,27 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                 m2 = fminf(m2, d2);
                 m3 = fminf(m3, d3);
             }
-            if (fminf(fminf(m0, m1), fminf(m2, m3)) < tau) {
+            // With labels (a search in a re-ordered database whose result must not depend on that order) candidates that
+            // TIE with the list's worst distance are ranked by label, so the kept set is the k smallest by
+            // (distance, label) whatever the order of the columns; without labels the column index plays that role and
+            // ascending arrival makes the strict test sufficient.
+            const float mn = fminf(fminf(m0, m1), fminf(m2, m3));
+            if (mn < tau || (labels && cnt >= k && mn == tau)) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float dist = __uint_as_float(big[j]);
-                    if (dist < tau && (int64_t)(col_base + j) != self) {
+                    bool adm = dist < tau;
+                    if (labels && !adm && cnt >= k && dist == tau && col_base + j < (int)prm.ndb)
+                        adm = __ldg(labels + col_base + j) < worst_lab;
+                    if (adm && (int64_t)(col_base + j) != self) {
+                        const int lab = labels ? __ldg(labels + col_base + j) : col_base + j;
                         const int slot = cnt < k ? cnt : amax;
-                        sts_u64(my_k + 8u * (uint32_t)slot,
-                                ((unsigned long long)ord_f32(dist) << 32) | (unsigned long long)(uint32_t)(col_base + j));
+                        sts_u64(my_k + 8u * (uint32_t)slot, ((unsigned long long)ord_f32(dist) << 32) | (unsigned long long)(uint32_t)lab);
                         if (++cnt >= k) {
                             const unsigned long long r = list_scan_max(my_k, k);
                             tau = fminf(tau, unord_f32((uint32_t)(r >> 32)));
                             amax = (int)(uint32_t)r;
+                            if (labels) worst_lab = (int)(uint32_t)lds_u64(my_k + 8u * (uint32_t)amax);
                         }
                     }
                 }
@@ -1051,8 +1063,8 @@ size_t knn_tc_workspace_bytes(int64_t nq, int64_t ndb, int d, int k, bool same) 
 // `same`: the query rows are rows [q_row0, q_row0+nq) of the database buffer itself.
 int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb, int64_t ndb, int d, int k,
                   bool same, int exclude_self, int metric, int fused, int max_iter, float* out_dist, int32_t* out_idx,
-                  float* P, float* rho, float* sigma, int prune, unsigned long long* sweep_stats, void* ws,
-                  size_t ws_bytes, cudaStream_t st) {
+                  float* P, float* rho, float* sigma, int prune, unsigned long long* sweep_stats,
+                  const int32_t* db_labels, void* ws, size_t ws_bytes, cudaStream_t st) {
     using namespace tc;
     const size_t need = knn_tc_workspace_bytes(nq, ndb, d, k, same);
     if (!ws || ws_bytes < need || (uintptr_t)ws % 256) {
@@ -1119,6 +1131,7 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
     prm.fused = fused;
     prm.max_iter = max_iter;
     prm.debug = 0;  // ablation bits (skip filter / MMAs / TMA), set by hand in timing experiments only
+    prm.col_label = db_labels;
     prm.out_dist = out_dist;
     prm.out_idx = out_idx;
     prm.P = P;

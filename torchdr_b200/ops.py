@@ -34,11 +34,19 @@ def _check_stats(stats):
     return stats
 
 
-def knn(Xq, Xdb, k, q_row0=0, exclude_self=True, metric="sqeuclidean", path="auto", prune=None, sweep_stats=None):
+def _check_labels(labels, ndb):
+    if labels is not None:
+        assert labels.is_cuda and labels.dtype == torch.int32 and labels.numel() == ndb and labels.is_contiguous()
+    return labels
+
+
+def knn(Xq, Xdb, k, q_row0=0, exclude_self=True, metric="sqeuclidean", path="auto", prune=None, sweep_stats=None,
+        labels=None):
     """Exact kNN of query rows against the database -> (dist[nq,k] f32, idx[nq,k] i32).
 
     ``path``: "auto" | "simt" | "tc"; ``prune``: None (default = on) | 0/"off" | 1/"on" | 2/"certified";
-    ``sweep_stats``: optional int64[2] CUDA tensor accumulating (tiles swept, tiles of a full sweep)."""
+    ``sweep_stats``: optional int64[2] CUDA tensor accumulating (tiles swept, tiles of a full sweep);
+    ``labels``: optional int32[ndb] — ids to report (and to rank distance ties by) instead of the row indices."""
     Xq, Xdb = _dev_f32(Xq, "Xq"), _dev_f32(Xdb, "Xdb")
     lib = _lib.load()
     nq, d = Xq.shape
@@ -49,12 +57,12 @@ def knn(Xq, Xdb, k, q_row0=0, exclude_self=True, metric="sqeuclidean", path="aut
     with torch.cuda.device(Xq.device):
         check(lib.tdr_knn_f32(ptr(Xq), nq, q_row0, ptr(Xdb), ndb, d, k, int(exclude_self), _lib.METRIC_IDS[metric],
                               ptr(dist), ptr(idx), _lib.KNN_PATHS[path], _prune_id(prune), ptr(_check_stats(sweep_stats)),
-                              ptr(ws), ws.numel(), stream()), "tdr_knn_f32")
+                              ptr(_check_labels(labels, ndb)), ptr(ws), ws.numel(), stream()), "tdr_knn_f32")
     return dist, idx
 
 
 def knn_umap_fused(Xq, Xdb, k, q_row0=0, exclude_self=True, max_iter=100, want_dist=True, path="auto", prune=None,
-                   sweep_stats=None):
+                   sweep_stats=None, labels=None):
     """Fused kNN + UMAP rho/sigma search -> (dist|None, idx, P, rho, sigma).  Options as in ``knn``."""
     Xq, Xdb = _dev_f32(Xq, "Xq"), _dev_f32(Xdb, "Xdb")
     lib = _lib.load()
@@ -70,8 +78,8 @@ def knn_umap_fused(Xq, Xdb, k, q_row0=0, exclude_self=True, max_iter=100, want_d
     with torch.cuda.device(dev):
         check(lib.tdr_knn_umap_fused_f32(ptr(Xq), nq, q_row0, ptr(Xdb), ndb, d, k, int(exclude_self), max_iter,
                                          ptr(dist), ptr(idx), ptr(Pm), ptr(rho), ptr(sigma), _lib.KNN_PATHS[path],
-                                         _prune_id(prune), ptr(_check_stats(sweep_stats)), ptr(ws), ws.numel(),
-                                         stream()), "tdr_knn_umap_fused_f32")
+                                         _prune_id(prune), ptr(_check_stats(sweep_stats)), ptr(_check_labels(labels, ndb)),
+                                         ptr(ws), ws.numel(), stream()), "tdr_knn_umap_fused_f32")
     return dist, idx, Pm, rho, sigma
 
 
