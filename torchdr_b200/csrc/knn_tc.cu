@@ -252,7 +252,9 @@ struct Params {
 
 // REDO: the robust mode's second sweep (CTA -> query tile through prm.qtile_map); a separate instantiation so that
 // the default kernel keeps its register allocation (168, no spills)
-template <bool REDO>
+// LAB: database labels (prm.col_label) are reported and rank distance ties; a separate instantiation so that the default
+// kernel's filter carries none of it
+template <bool REDO, bool LAB = false>
 __global__ void __launch_bounds__(384, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
               const __grid_constant__ CUtensorMap map_db_hi, const __grid_constant__ CUtensorMap map_db_lo,
@@ -425,7 +427,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                 tau = sd >= 0.0f ? __uint_as_float(__float_as_uint(sd + 0.0f) + 1u) : __uint_as_float(__float_as_uint(sd) - 1u);
         }
         int amax = 0, cnt = 0;  // position of the list's worst entry, filled slots
-        const int32_t* const labels = prm.col_label;
+        const int32_t* const labels = LAB ? prm.col_label : nullptr;
         int worst_lab = 0x7fffffff;  // label of the list's worst entry once the list is full (labels only)
         const uint32_t lane_addr = (uint32_t)(((warp - 4) & 3) * 32) << 16;
 
@@ -453,22 +455,22 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
             // (distance, label) whatever the order of the columns; without labels the column index plays that role and
             // ascending arrival makes the strict test sufficient.
             const float mn = fminf(fminf(m0, m1), fminf(m2, m3));
-            if (mn < tau || (labels && cnt >= k && mn == tau)) {
+            if (mn < tau || (LAB && cnt >= k && mn == tau)) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float dist = __uint_as_float(big[j]);
                     bool adm = dist < tau;
-                    if (labels && !adm && cnt >= k && dist == tau && col_base + j < (int)prm.ndb)
+                    if (LAB && !adm && cnt >= k && dist == tau && col_base + j < (int)prm.ndb)
                         adm = __ldg(labels + col_base + j) < worst_lab;
                     if (adm && (int64_t)(col_base + j) != self) {
-                        const int lab = labels ? __ldg(labels + col_base + j) : col_base + j;
+                        const int lab = LAB ? __ldg(labels + col_base + j) : col_base + j;
                         const int slot = cnt < k ? cnt : amax;
                         sts_u64(my_k + 8u * (uint32_t)slot, ((unsigned long long)ord_f32(dist) << 32) | (unsigned long long)(uint32_t)lab);
                         if (++cnt >= k) {
                             const unsigned long long r = list_scan_max(my_k, k);
                             tau = fminf(tau, unord_f32((uint32_t)(r >> 32)));
                             amax = (int)(uint32_t)r;
-                            if (labels) worst_lab = (int)(uint32_t)lds_u64(my_k + 8u * (uint32_t)amax);
+                            if (LAB) worst_lab = (int)(uint32_t)lds_u64(my_k + 8u * (uint32_t)amax);
                         }
                     }
                 }
@@ -1060,6 +1062,21 @@ size_t knn_tc_workspace_bytes(int64_t nq, int64_t ndb, int d, int k, bool same) 
     return b;
 }
 
+// one launch of the sweep kernel: instantiation by (second sweep of the certified mode, labels)
+static cudaError_t launch_sweep(bool redo, const tc::Params& prm, unsigned grid, unsigned threads, size_t smem, cudaStream_t st,
+                                const CUtensorMap& mq_hi, const CUtensorMap& mq_lo, const CUtensorMap& mdb_hi,
+                                const CUtensorMap& mdb_lo) {
+    using namespace tc;
+    auto go = [&](auto kernel) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        kernel<<<grid, threads, smem, st>>>(mq_hi, mq_lo, mdb_hi, mdb_lo, prm);
+        return cudaGetLastError();
+    };
+    if (prm.col_label) return redo ? go(knn_tc_kernel<true, true>) : go(knn_tc_kernel<false, true>);
+    return redo ? go(knn_tc_kernel<true, false>) : go(knn_tc_kernel<false, false>);
+}
+
 // `same`: the query rows are rows [q_row0, q_row0+nq) of the database buffer itself.
 int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb, int64_t ndb, int d, int k,
                   bool same, int exclude_self, int metric, int fused, int max_iter, float* out_dist, int32_t* out_idx,
@@ -1150,8 +1167,6 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
     }
     prm.stages = stages;
     // per call: the attribute belongs to the current device's context (a process may drive several GPUs)
-    TDR_CUDA(cudaFuncSetAttribute(knn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    TDR_CUDA(cudaFuncSetAttribute(knn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const unsigned grid = (unsigned)((nq + BM - 1) / BM);
     const unsigned threads = prm.dual ? 384 : 256;
 
@@ -1203,7 +1218,7 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
         pa.fused = 0;
         pa.out_dist = nullptr;
         pa.out_idx = nullptr;
-        knn_tc_kernel<false><<<grid, threads, smem, st>>>(mq_hi, mq_lo, mdb_hi, mdb_lo, pa);
+        TDR_CUDA(launch_sweep(false, pa, grid, threads, smem, st, mq_hi, mq_lo, mdb_hi, mdb_lo));
         const unsigned pgrid = (unsigned)((L.n_qtiles + 7) / 8);
         if (robust)
             tile_prune_kernel<true><<<pgrid, 256, 0, st>>>(qlo, qhi, dlo_t, dhi_t, slo_t, shi_t, L.n_qtiles, L.n_tiles, L.ld_t,
@@ -1226,7 +1241,7 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
             const int fused_req = prm.fused;
             prm.fused = 0;
             if (!prm.out_dist) prm.out_dist = dist_scratch;
-            knn_tc_kernel<false><<<grid, threads, smem, st>>>(mq_hi, mq_lo, mdb_hi, mdb_lo, prm);
+            TDR_CUDA(launch_sweep(false, prm, grid, threads, smem, st, mq_hi, mq_lo, mdb_hi, mdb_lo));
             TDR_CUDA(cudaMemsetAsync(redo_count, 0, 4, st));
             const int is_sqrt = metric == TDR_METRIC_EUCLIDEAN ? 1 : 0;
             knn_certify_kernel<<<pgrid, 256, 0, st>>>(prm.out_dist, k, is_sqrt, nq, L.n_qtiles, bound_used, maxnorm, count,
@@ -1238,7 +1253,7 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
             pr.qtile_map = redo_map;
             pr.qtile_count = redo_count;
             pr.tau_seed = nullptr;
-            knn_tc_kernel<true><<<grid, threads, smem, st>>>(mq_hi, mq_lo, mdb_hi, mdb_lo, pr);
+            TDR_CUDA(launch_sweep(true, pr, grid, threads, smem, st, mq_hi, mq_lo, mdb_hi, mdb_lo));
             TDR_LAUNCH_CHECK();
             if (fused_req) return tdr_umap_affinity_f32(prm.out_dist, nq, k, max_iter, P, rho, sigma, (tdr_stream_t)st);
             return TDR_OK;
@@ -1249,13 +1264,11 @@ int knn_tc_launch(const float* Xq, int64_t nq, int64_t q_row0, const float* Xdb,
             // 3.5 ms for the standalone row kernel at full occupancy.  Same arithmetic, bit-identical rows.
             prm.fused = 0;
             if (!prm.out_dist) prm.out_dist = dist_scratch;
-            knn_tc_kernel<false><<<grid, threads, smem, st>>>(mq_hi, mq_lo, mdb_hi, mdb_lo, prm);
-            TDR_LAUNCH_CHECK();
+            TDR_CUDA(launch_sweep(false, prm, grid, threads, smem, st, mq_hi, mq_lo, mdb_hi, mdb_lo));
             return tdr_umap_affinity_f32(prm.out_dist, nq, k, max_iter, P, rho, sigma, (tdr_stream_t)st);
         }
     }
-    knn_tc_kernel<false><<<grid, threads, smem, st>>>(mq_hi, mq_lo, mdb_hi, mdb_lo, prm);
-    TDR_LAUNCH_CHECK();
+    TDR_CUDA(launch_sweep(false, prm, grid, threads, smem, st, mq_hi, mq_lo, mdb_hi, mdb_lo));
     return TDR_OK;
 }
 
