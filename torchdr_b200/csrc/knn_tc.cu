@@ -192,7 +192,7 @@ __device__ __forceinline__ uint32_t ord_f32(float f) {
 __device__ __forceinline__ float unord_f32(uint32_t u) { return __uint_as_float(u ^ (((u >> 31) - 1u) | 0x80000000u)); }
 constexpr unsigned long long kEmptyKey = ~0ull;  // sorts after every real entry
 
-// Per-row candidate lists are kept UNSORTED in shared memory during the sweep.  While the list is not full a
+// Lists of k <= kListScanMaxK entries are kept UNSORTED in shared memory during the sweep.  While the list is not full a
 // candidate is appended (two stores); once it is full the candidate overwrites the current worst entry (position
 // amax) and one pass over the list finds the new worst by (distance, index).  The loads of that pass are
 // independent, whereas a sorted insert walks a chain of dependent shared-memory round trips (~750 cycles per call at
@@ -210,6 +210,43 @@ __device__ __noinline__ unsigned long long list_scan_max(uint32_t my_k, int k) {
         mp = gt ? p : mp;
     }
     return (m & 0xffffffff00000000ull) | (unsigned long long)(uint32_t)mp;
+}
+
+// Longer lists (HEAP instantiations of the kernel): while the list is not full a candidate is appended (one store);
+// the k-th append turns the list into an implicit binary MAX-heap of keys (slot 0 = the list's worst entry, Floyd's
+// bottom-up construction, O(k)); from then on a candidate replaces the root and sifts down: <= floor(log2 k) levels
+// of two independent loads each (6 at k = 90) instead of a pass over all k entries.  Measured on one box (`profiles/r2_knn_orders.txt`): k = 90,
+// 1 M x 128: pruned sweep 147 -> 63 ms, full sweep 1262 -> 1012 ms; k = 15: the heap's 3 DEPENDENT round trips are
+// slower than 15 independent loads (11.1 -> 12.4 ms), hence the split.  The lists are rank-sorted once after the
+// sweep, so their internal order is free.
+constexpr int kListScanMaxK = 32;
+// sift_down: `key` is to be placed in the sub-heap rooted at hole i; returns what ends up in slot i.
+__device__ __forceinline__ unsigned long long sift_down(uint32_t my_k, int k, int i, unsigned long long key) {
+    unsigned long long top = key;
+    const int i0 = i;
+    for (;;) {
+        const int l = 2 * i + 1;
+        if (l >= k) break;
+        const unsigned long long vl = lds_u64(my_k + 8u * (uint32_t)l);
+        const unsigned long long vr = l + 1 < k ? lds_u64(my_k + 8u * (uint32_t)(l + 1)) : 0ull;
+        const bool right = vr > vl;
+        const unsigned long long vc = right ? vr : vl;
+        if (vc <= key) break;
+        sts_u64(my_k + 8u * (uint32_t)i, vc);
+        if (i == i0) top = vc;
+        i = right ? l + 1 : l;
+    }
+    sts_u64(my_k + 8u * (uint32_t)i, key);
+    return top;
+}
+// Both return the list's worst key (the heap's root) after the operation.
+__device__ __noinline__ unsigned long long list_replace_worst(uint32_t my_k, int k, unsigned long long key) {
+    return sift_down(my_k, k, 0, key);
+}
+__device__ __noinline__ unsigned long long list_make_heap(uint32_t my_k, int k) {
+    unsigned long long top = lds_u64(my_k);
+    for (int s = (k - 2) >> 1; s >= 0; --s) top = sift_down(my_k, k, s, lds_u64(my_k + 8u * (uint32_t)s));
+    return top;
 }
 
 // ------------------------------------------------------------------ main kernel
@@ -254,7 +291,8 @@ struct Params {
 // the default kernel keeps its register allocation (168, no spills)
 // LAB: database labels (prm.col_label) are reported and rank distance ties; a separate instantiation so that the default
 // kernel's filter carries none of it
-template <bool REDO, bool LAB = false>
+// HEAP: candidate lists are max-heaps (k > kListScanMaxK), else unsorted lists with a re-scan
+template <bool REDO, bool LAB = false, bool HEAP = false>
 __global__ void __launch_bounds__(384, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
               const __grid_constant__ CUtensorMap map_db_hi, const __grid_constant__ CUtensorMap map_db_lo,
@@ -426,7 +464,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
             if (sd < INFINITY)
                 tau = sd >= 0.0f ? __uint_as_float(__float_as_uint(sd + 0.0f) + 1u) : __uint_as_float(__float_as_uint(sd) - 1u);
         }
-        int amax = 0, cnt = 0;  // position of the list's worst entry, filled slots
+        int amax = 0, cnt = 0;  // position of the list's worst entry (unsorted lists), entries inserted so far
         const int32_t* const labels = LAB ? prm.col_label : nullptr;
         int worst_lab = 0x7fffffff;  // label of the list's worst entry once the list is full (labels only)
         const uint32_t lane_addr = (uint32_t)(((warp - 4) & 3) * 32) << 16;
@@ -464,13 +502,27 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                         adm = __ldg(labels + col_base + j) < worst_lab;
                     if (adm && (int64_t)(col_base + j) != self) {
                         const int lab = LAB ? __ldg(labels + col_base + j) : col_base + j;
-                        const int slot = cnt < k ? cnt : amax;
-                        sts_u64(my_k + 8u * (uint32_t)slot, ((unsigned long long)ord_f32(dist) << 32) | (unsigned long long)(uint32_t)lab);
-                        if (++cnt >= k) {
-                            const unsigned long long r = list_scan_max(my_k, k);
-                            tau = fminf(tau, unord_f32((uint32_t)(r >> 32)));
-                            amax = (int)(uint32_t)r;
-                            if (LAB) worst_lab = (int)(uint32_t)lds_u64(my_k + 8u * (uint32_t)amax);
+                        const unsigned long long key = ((unsigned long long)ord_f32(dist) << 32) | (unsigned long long)(uint32_t)lab;
+                        if constexpr (HEAP) {
+                            unsigned long long root;
+                            if (cnt < k) {  // filling: append; the k-th entry completes the list and orders it as a heap
+                                sts_u64(my_k + 8u * (uint32_t)cnt, key);
+                                root = cnt + 1 == k ? list_make_heap(my_k, k) : kEmptyKey;
+                            } else {
+                                root = list_replace_worst(my_k, k, key);
+                            }
+                            if (++cnt >= k) {  // full: the root is a real entry, the row's running k-th best
+                                tau = fminf(tau, unord_f32((uint32_t)(root >> 32)));
+                                if (LAB) worst_lab = (int)(uint32_t)root;
+                            }
+                        } else {
+                            sts_u64(my_k + 8u * (uint32_t)(cnt < k ? cnt : amax), key);
+                            if (++cnt >= k) {
+                                const unsigned long long r = list_scan_max(my_k, k);
+                                tau = fminf(tau, unord_f32((uint32_t)(r >> 32)));
+                                amax = (int)(uint32_t)r;
+                                if (LAB) worst_lab = (int)(uint32_t)lds_u64(my_k + 8u * (uint32_t)amax);
+                            }
                         }
                     }
                 }
@@ -1062,7 +1114,7 @@ size_t knn_tc_workspace_bytes(int64_t nq, int64_t ndb, int d, int k, bool same) 
     return b;
 }
 
-// one launch of the sweep kernel: instantiation by (second sweep of the certified mode, labels)
+// one launch of the sweep kernel: instantiation by (second sweep of the certified mode, labels, list structure)
 static cudaError_t launch_sweep(bool redo, const tc::Params& prm, unsigned grid, unsigned threads, size_t smem, cudaStream_t st,
                                 const CUtensorMap& mq_hi, const CUtensorMap& mq_lo, const CUtensorMap& mdb_hi,
                                 const CUtensorMap& mdb_lo) {
@@ -1073,6 +1125,10 @@ static cudaError_t launch_sweep(bool redo, const tc::Params& prm, unsigned grid,
         kernel<<<grid, threads, smem, st>>>(mq_hi, mq_lo, mdb_hi, mdb_lo, prm);
         return cudaGetLastError();
     };
+    if (prm.k > kListScanMaxK) {
+        if (prm.col_label) return redo ? go(knn_tc_kernel<true, true, true>) : go(knn_tc_kernel<false, true, true>);
+        return redo ? go(knn_tc_kernel<true, false, true>) : go(knn_tc_kernel<false, false, true>);
+    }
     if (prm.col_label) return redo ? go(knn_tc_kernel<true, true>) : go(knn_tc_kernel<false, true>);
     return redo ? go(knn_tc_kernel<true, false>) : go(knn_tc_kernel<false, false>);
 }
