@@ -182,6 +182,10 @@ def test_knn_certified_pruned_sweep(ops, kind):
     assert torch.equal(I0, I1) and torch.equal(C0, C1)
     for a, b in zip(F0, F1):
         assert torch.equal(a, b)
+    # heap candidate lists (k > 32) through the same three sweeps
+    C2, I2 = ops.knn(Xd, Xd, 40, prune="off")
+    C3, I3 = ops.knn(Xd, Xd, 40, prune="certified")
+    assert torch.equal(I2, I3) and torch.equal(C2, C3)
     n_tiles = (n + 127) // 128
     print(f"robust sweep, {kind}: {swept} tile pairs of {n_tiles * n_tiles}")
     if kind != "shuffled":
@@ -323,6 +327,12 @@ def test_affinity_in_tree_order_equals_input_order(ops):
     e_tr = tb.EntropicAffinity(perplexity=10, max_iter=100, knn_order="tree")
     (l_in, i_in), (l_tr, i_tr) = e_in(Xd, log=True), e_tr(Xd, log=True)
     assert torch.equal(i_in, i_tr) and torch.equal(l_in, l_tr) and torch.equal(e_in.eps_, e_tr.eps_)
+    # k = 42 > 32: the kernel instantiations whose candidate lists are heaps (labels + second sweep of the certified mode)
+    h_in = tb.EntropicAffinity(perplexity=14, max_iter=100, knn_order="input")
+    h_tr = tb.EntropicAffinity(perplexity=14, max_iter=100, knn_order="tree")
+    (l_in, i_in), (l_tr, i_tr) = h_in(Xd, log=True), h_tr(Xd, log=True)
+    assert i_in.shape[1] == 42
+    assert torch.equal(i_in, i_tr) and torch.equal(l_in, l_tr) and torch.equal(h_in.eps_, h_tr.eps_)
     # labels on the fp32 SIMT kernel: ids are re-labelled after the search (ties by row index there)
     lab = torch.randperm(3000, generator=g).int()
     Cs, Is = ops.knn(Xd[:3000], Xd[:3000], 7, path="simt")
