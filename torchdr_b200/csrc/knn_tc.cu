@@ -35,7 +35,6 @@ namespace tdr {
 namespace tc {
 
 constexpr int BM = 128, BN = 128, KATOM = 64;  // 64 fp16 = one 128-byte swizzle row
-constexpr int NT = 256;
 constexpr int TILE_BYTES = BM * KATOM * 2;  // 16 KB: one [128 x 64] fp16 box
 constexpr int MAX_ATOMS = 4;                // d <= 256
 constexpr int STAGE_BYTES = 2 * TILE_BYTES; // one ring stage: hi + lo of one atom of a database tile
@@ -43,7 +42,6 @@ constexpr int MAX_STAGES = 8;
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 constexpr size_t SMEM_MISC = 512 + 1024;    // barriers + TMEM slot, 1024-byte alignment slack
 constexpr int MAX_K = 96;                   // top-k lists in shared memory next to the operand tiles
-constexpr int kMaxEpl = MAX_K / 32;
 constexpr int kMaxUnion = 2 * MAX_K / 32;  // entries per lane of the union of two lists
 
 // ------------------------------------------------------------------ PTX wrappers
