@@ -77,3 +77,45 @@ def test_reference_paths_not_read_at_runtime():
         p = os.path.join(ROOT, rel)
         if os.path.exists(p):
             assert "/root/reference" not in open(p).read(), rel
+
+
+def test_every_entry_point_rejects_null_arguments_before_touching_cuda():
+    """Error behaviour of the boundary, checkable without a GPU: every compute entry point validates its arguments
+    first and answers TDR_E_INVALID with a message naming itself — never a crash, never a CUDA call."""
+    from torchdr_b200 import _lib
+
+    lib = _lib.load()
+    checked = 0
+    for name, (res, args) in sorted(_lib.SIGNATURES.items()):
+        if res is not ctypes.c_int or name in ("tdr_abi_version", "tdr_device_info"):
+            continue
+        zeros = []
+        for t in args:
+            try:
+                zeros.append(None if t in (ctypes.c_void_p, ctypes.c_char_p) else t(0))
+            except TypeError:
+                zeros.append(None)  # pointer-typed argument
+        assert getattr(lib, name)(*zeros) == _lib.TDR_E_INVALID, name
+        assert _lib.last_error().startswith(("tdr_", "knn:")), (name, _lib.last_error())
+        checked += 1
+    assert checked >= 24
+
+
+def test_knn_argument_errors_carry_the_reference_wording():
+    """`torch.py:63-64`: an unsupported metric is a ValueError with the reference's text; k beyond the available neighbours
+    and k outside the kernel's range are refused with the numbers in the message."""
+    from torchdr_b200 import _lib
+
+    lib = _lib.load()
+    p = ctypes.c_void_p(256)  # never dereferenced: validation comes first
+
+    def knn(ndb, d, k, exclude_self, metric):
+        return lib.tdr_knn_f32(p, 10, 0, p, ndb, d, k, exclude_self, metric, p, p, 0, -1, None, None, None, 0, None)
+
+    assert knn(10, 4, 3, 1, 7) == _lib.TDR_E_INVALID
+    assert _lib.last_error() == "[TorchDR] ERROR : metric id 7 is not supported."
+    assert knn(10, 4, 10, 1, 0) == _lib.TDR_E_INVALID and "exceeds the 9 available" in _lib.last_error()
+    assert knn(10, 4, 10, 0, 0) != _lib.TDR_E_INVALID or "exceeds" not in _lib.last_error()  # k = ndb is fine without self exclusion
+    assert knn(1000, 4, 161, 1, 0) == _lib.TDR_E_INVALID and "outside [1,160]" in _lib.last_error()
+    with pytest.raises(ValueError, match=r"\[TorchDR\] ERROR"):
+        _lib.check(knn(10, 4, 3, 1, 7), "tdr_knn_f32")
