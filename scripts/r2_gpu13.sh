@@ -1,5 +1,7 @@
 #!/usr/bin/env bash
 # A/B of the candidate-list structure (max-heap vs unsorted list + rescan) on one box.
+# Needs two prebuilt libraries (build/ travels to the box): build/libtdrb200_heap.so = ./build.sh of the tree under test,
+# build/libtdrb200_scan.so = the same link line with knn_tc.o compiled from the revision to compare against.
 set -uo pipefail
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 | tee gpurun_out/r2_pytest_gpu_heap.log
